@@ -1,0 +1,92 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference modules (imported from
+/root/reference, CPU fp32) on the deterministic synthetic checkpoint + inputs.
+Run in the build container:  python oracle/gen_golden.py     -- TEST INFRASTRUCTURE."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from ezaudio_b200 import synth, weights  # noqa: E402
+from oracle import refimport  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def checksum(sd):
+    return float(sum(v.double().abs().sum() for v in sd.values()))
+
+
+@torch.no_grad()
+def dit_case(ref, name, cfg, B, L, Lc, seed, inpaint, tscalar=None, tvec=None):
+    sd = weights.synthetic_state_dict(weights.dit_param_shapes(cfg), seed)
+    m = refimport.build(ref.MaskDiT, sd, **cfg)
+    x = synth.synth_latents(B, L)
+    ctx, mask = synth.synth_context(B, Lc, cfg["context_dim"])
+    if B > 1:  # last row plays the unconditional prompt
+        mask[-1] = False
+        mask[-1, 0] = True
+    t = torch.tensor(tscalar) if tvec is None else torch.tensor(tvec, dtype=torch.long)
+    gt, gm = (synth.synth_gt(B, L) if inpaint else (None, None))
+    out, mae = m(x, t, ctx, context_mask=mask, gt=None if gt is None else gt.clone(), mae_mask_infer=gm)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), out=out.numpy(), sd_checksum=checksum(sd),
+                        x_checksum=float(x.double().abs().sum()), seed=seed, B=B, L=L, Lc=Lc,
+                        inpaint=inpaint, t=t.numpy())
+    print(name, tuple(out.shape), float(out.std()), float(out.abs().max()))
+
+
+@torch.no_grad()
+def controlnet_case(ref, name, cfg, B, L, Lc, seed):
+    cn = synth.CONTROLNET
+    sd = weights.synthetic_state_dict(weights.dit_param_shapes(cfg), seed)
+    sd_cn = weights.synthetic_state_dict(weights.controlnet_param_shapes(cfg, cn), seed + 1)
+    m = refimport.build(ref.MaskDiT, sd, **cfg)
+    c = refimport.build(ref.DiTControlNet, sd_cn, **cfg, **cn)
+    x = synth.synth_latents(B, L)
+    ctx, mask = synth.synth_context(B, Lc, cfg["context_dim"])
+    cond = torch.rand(B, 1, 2 * L, generator=torch.Generator().manual_seed(9))
+    t = torch.tensor(499)
+    x257, _ = m(x, t, ctx, context_mask=mask, forward_model=False)
+    skips = c(x257, t, ctx, context_mask=mask, condition=cond, conditioning_scale=0.8)
+    out = m.model(x257, t, ctx, context_mask=mask, controlnet_skips=list(skips))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), out=out.numpy(), skip0=skips[0].numpy(),
+                        skip_last=skips[-1].numpy(), sd_checksum=checksum(sd) + checksum(sd_cn), seed=seed,
+                        B=B, L=L, Lc=Lc)
+    print(name, tuple(out.shape), float(out.std()), float(skips[-1].std()))
+
+
+@torch.no_grad()
+def vae_case(ref, name, dcfg, B, L, seed):
+    sd = weights.synthetic_state_dict(weights.vae_decoder_param_shapes(dcfg), seed)
+    m = refimport.build(ref.OobleckDecoder, {k[len("decoder."):]: v for k, v in sd.items()}, **dcfg)
+    z = synth.synth_latents(B, L, dcfg["latent_dim"], seed=31)
+    wav = m(z)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), out=wav.numpy(), sd_checksum=checksum(sd), seed=seed, B=B, L=L)
+    print(name, tuple(wav.shape), float(wav.std()), float(wav.abs().max()))
+
+
+def main():
+    ref = refimport.import_reference()
+    assert ref is not None, "reference tree not found"
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(os.cpu_count())
+    only = set(sys.argv[1:])
+    global dit_case, controlnet_case, vae_case
+    if only:
+        def filt(f):
+            return lambda ref, name, *a, **k: f(ref, name, *a, **k) if name in only else None
+        dit_case, controlnet_case, vae_case = filt(dit_case), filt(controlnet_case), filt(vae_case)
+    dit_case(ref, "dit_tiny72", synth.tiny_model(72), B=2, L=40, Lc=12, seed=3, inpaint=False, tscalar=999)
+    dit_case(ref, "dit_tiny72_inpaint", synth.tiny_model(72), B=3, L=52, Lc=12, seed=3, inpaint=True, tvec=[999, 500, 19])
+    dit_case(ref, "dit_tiny64", synth.tiny_model(64, heads=4, depth=2), B=2, L=130, Lc=100, seed=4, inpaint=False, tscalar=259)
+    controlnet_case(ref, "controlnet_tiny72", synth.tiny_model(72), B=2, L=40, Lc=12, seed=5)
+    vae_case(ref, "vae_tiny", synth.tiny_vae(16), B=2, L=9, seed=6)
+    vae_case(ref, "vae_full", synth.VAE_DECODER, B=1, L=12, seed=6)
+    dit_case(ref, "dit_L_c1", synth.model_cfg("l"), B=1, L=256, Lc=100, seed=1, inpaint=False, tscalar=999)  # BASELINE config 1
+    dit_case(ref, "dit_XL", synth.model_cfg("xl"), B=2, L=500, Lc=100, seed=2, inpaint=False, tscalar=479)
+
+
+if __name__ == "__main__":
+    main()

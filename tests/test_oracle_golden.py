@@ -1,0 +1,88 @@
+"""Pins oracle/ezaudio_oracle.py (CPU restatement) against golden outputs of the UNMODIFIED
+reference modules (tests/golden/*.npz, made by oracle/gen_golden.py).  fp32 both sides: the
+only difference is reduction order, so the tolerance is fp32 round-off (2e-4 abs on O(1)
+outputs after 29 blocks; measured ~1e-5)."""
+import numpy as np
+import pytest
+import torch
+
+from ezaudio_b200 import synth, weights
+from oracle import ezaudio_oracle as O
+from tests import helpers
+
+TOL = 2e-4
+
+
+@pytest.mark.parametrize("name", ["dit_tiny72", "dit_tiny72_inpaint", "dit_tiny64", "dit_L_c1",
+                                  pytest.param("dit_XL", marks=pytest.mark.slow)])
+def test_dit_oracle_matches_reference_golden(name):
+    cfg, sd, inp, g = helpers.dit_case_inputs(name)
+    with torch.no_grad():
+        out, _ = O.maskdit_forward(sd, cfg, inp["x"], inp["t"], inp["ctx"], inp["mask"], inp["gt"], inp["gt_mask"])
+    err = float((out - torch.from_numpy(g["out"])).abs().max())
+    assert err < TOL, err
+
+
+def test_controlnet_oracle_matches_reference_golden():
+    cfg, cn = synth.tiny_model(72), synth.CONTROLNET
+    g = helpers.load_golden("controlnet_tiny72")
+    sd = weights.synthetic_state_dict(weights.dit_param_shapes(cfg), 5)
+    sd_cn = weights.synthetic_state_dict(weights.controlnet_param_shapes(cfg, cn), 6)
+    x = synth.synth_latents(2, 40)
+    ctx, mask = synth.synth_context(2, 12, cfg["context_dim"])
+    cond = torch.rand(2, 1, 80, generator=torch.Generator().manual_seed(9))
+    t = torch.tensor(499)
+    with torch.no_grad():
+        x257, _ = O.maskdit_forward(sd, cfg, x, t, ctx, mask, forward_model=False)
+        skips = O.controlnet_forward(sd_cn, cfg, x257, t, ctx, mask, cond, 0.8)
+        out = O.udit_forward(sd, cfg, x257, t, ctx, mask, controlnet_skips=skips)
+    assert float((skips[0] - torch.from_numpy(g["skip0"])).abs().max()) < TOL
+    assert float((skips[-1] - torch.from_numpy(g["skip_last"])).abs().max()) < TOL
+    assert float((out - torch.from_numpy(g["out"])).abs().max()) < TOL
+
+
+@pytest.mark.parametrize("name,dcfg,B,L", [("vae_tiny", synth.tiny_vae(16), 2, 9), ("vae_full", synth.VAE_DECODER, 1, 12)])
+def test_vae_oracle_matches_reference_golden(name, dcfg, B, L):
+    g = helpers.load_golden(name)
+    sd = weights.synthetic_state_dict(weights.vae_decoder_param_shapes(dcfg), 6)
+    z = synth.synth_latents(B, L, dcfg["latent_dim"], seed=31)
+    with torch.no_grad():
+        wav = O.vae_decode(sd, z, strides=tuple(dcfg["strides"]))
+    ref = torch.from_numpy(g["out"])
+    assert wav.shape == ref.shape == (B, 1, 480 * L)
+    assert float((wav - ref).abs().max()) < 1e-5 + 1e-4 * float(ref.abs().max())
+
+
+def test_ddim_invariants():
+    """diffusers is absent (parity unpinned): closed-form checks from SURVEY Appendix B."""
+    s = O.DDIM()
+    ts = s.set_timesteps(50)
+    assert ts.tolist() == list(range(999, 0, -20))
+    assert s.set_timesteps(100).tolist() == list(range(999, 0, -10))
+    assert float(s.alphas_cumprod[999]) == 0.0
+    assert abs(float(s.alphas_cumprod[979]) - 8.5788e-5) < 1e-8
+    assert abs(float(s.alphas_cumprod[0]) - 0.99915) < 1e-5
+    s.set_timesteps(50)
+    x = torch.randn(2, 128, 16, generator=torch.Generator().manual_seed(0))
+    v = torch.randn(2, 128, 16, generator=torch.Generator().manual_seed(1))
+    # at t=999: a=0 -> x0 = -v, eps = x ; eta=0 -> prev = sqrt(ap)*(-v) + sqrt(1-ap)*x
+    ap = s.alphas_cumprod[979]
+    assert torch.allclose(s.step(v, 999, x, 0.0), ap.sqrt() * (-v) + (1 - ap).sqrt() * x, atol=1e-6)
+    # eta=1: radicand stays >= 0 on every step of the 50- and 100-step schedules
+    for n in (50, 100):
+        for t in s.set_timesteps(n).tolist():
+            a, ap, b, sig = s.coeffs(t, 1.0)
+            assert float(1 - ap - sig ** 2) >= 0.0
+    # last step lands on final_alpha_cumprod = 1 -> returns x0 when eta = 0
+    s.set_timesteps(50)
+    a = s.alphas_cumprod[19]
+    assert torch.allclose(s.step(v, 19, x, 0.0), a.sqrt() * x - (1 - a).sqrt() * v, atol=1e-6)
+
+
+def test_cfg_rescale_matches_formula():
+    g = torch.Generator().manual_seed(0)
+    t, u = torch.randn(3, 128, 20, generator=g), torch.randn(3, 128, 20, generator=g)
+    out = O.cfg_combine(t, u, 5.0, 0.75)
+    c = u + 5.0 * (t - u)
+    want = 0.75 * c * (t.flatten(1).std(1) / c.flatten(1).std(1)).view(-1, 1, 1) + 0.25 * c
+    assert torch.allclose(out, want, atol=1e-6)
