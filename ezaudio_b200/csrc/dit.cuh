@@ -1,0 +1,602 @@
+// DiT / ControlNet instance: packed weights, workspace, step-invariant caches and the per-step launch sequence.
+// Reference: src/models/udit.py:281-362 (UDiT.forward), src/models/blocks.py:120-160 (DiTBlock._forward),
+// src/models/conditioners.py:156-183 (MaskDiT.forward), src/models/controlnet.py:252-315 (DiTControlNet.forward).
+#pragma once
+#include <functional>
+#include <set>
+#include <vector>
+
+#include "attention_simt.cuh"
+#include "attention_tc.cuh"
+#include "host.cuh"
+
+namespace ezb {
+
+typedef __nv_bfloat16 bf16;
+
+struct BlockW {
+  bf16 *qkv = nullptr, *proj = nullptr, *cq = nullptr, *ckv = nullptr, *cproj = nullptr, *mlp1 = nullptr, *mlp2 = nullptr, *skip = nullptr;
+  float *b_proj = nullptr, *b_cproj = nullptr, *b_mlp1 = nullptr, *b_mlp2 = nullptr, *b_skip = nullptr;
+  float *n1w = nullptr, *n1b = nullptr, *n2w = nullptr, *n2b = nullptr, *n3w = nullptr, *n3b = nullptr, *ncw = nullptr, *ncb = nullptr, *snw = nullptr,
+        *snb = nullptr;
+  float *nqw = nullptr, *nqb = nullptr, *nkw = nullptr, *nkb = nullptr, *cnqw = nullptr, *cnqb = nullptr, *cnkw = nullptr, *cnkb = nullptr;
+  float *table = nullptr, *lora_a = nullptr, *lora_b = nullptr, *inv_freq = nullptr;
+  bf16* zero_w = nullptr;
+  float* zero_b = nullptr;
+  // per-clip cross-attention K / V^T caches
+  float *kc32 = nullptr, *vc32 = nullptr;
+  bf16 *kc16 = nullptr, *vtc16 = nullptr;
+};
+
+struct WeightSpec {
+  std::vector<int64_t> shape;
+  std::function<int(const float*, cudaStream_t)> load;
+  bool loaded = false;
+};
+
+constexpr int GEGLU_BN = 128;
+constexpr int KP_PATCH_ALIGN = 8;
+
+struct Dit {
+  ezb_dit_desc d;
+  Device* dev = nullptr;
+  int D, H, dh, inner, r, C, nblk, half, kmul, Kp;
+  int DHP, DVP;  // tensor-core attention paddings: q/k row pitch, v^T rows
+  bool use_tc_attention = true;
+  std::vector<void*> allocs;
+  std::map<std::string, WeightSpec> specs;
+  bool finalized = false;
+  std::vector<BlockW> blk;
+  // trunk weights
+  bf16 *w_patch = nullptr, *w_ce0 = nullptr, *w_ce2 = nullptr, *w_final = nullptr;
+  float *b_patch = nullptr, *b_ce0 = nullptr, *b_ce2 = nullptr, *b_final = nullptr;
+  float *te_w0 = nullptr, *te_b0 = nullptr, *te_w2 = nullptr, *te_b2 = nullptr, *ta_w = nullptr, *ta_b = nullptr, *taf_w = nullptr, *taf_b = nullptr;
+  float *fn_w = nullptr, *fn_b = nullptr, *fc_w = nullptr, *fc_b = nullptr, *mask_embed = nullptr;
+  // controlnet stem (fp32, tiny)
+  float *cs_in_w = nullptr, *cs_in_b = nullptr, *cs_me = nullptr, *cs_c0_w = nullptr, *cs_c0_b = nullptr, *cs_c1_w = nullptr, *cs_c1_b = nullptr,
+        *cs_out_w = nullptr, *cs_out_b = nullptr;
+  // workspace
+  float *x0 = nullptr, *xa = nullptr, *xb = nullptr, *ybuf = nullptr, *ctx_emb = nullptr, *cond_emb = nullptr, *cs_t0 = nullptr, *cs_t1 = nullptr, *cs_t2 = nullptr;
+  std::vector<float*> skips;
+  bf16 *act = nullptr, *a_patch = nullptr, *attn_out = nullptr, *mid = nullptr;
+  void* qkv = nullptr;  // bf16 (fast) or fp32 (parity) [M, 3D]
+  float *q32 = nullptr, *k32 = nullptr, *v32 = nullptr;
+  bf16 *q16 = nullptr, *k16 = nullptr, *vt16 = nullptr;
+  uint8_t* ctx_mask = nullptr;
+  float *t_vals = nullptr, *t_emb = nullptr, *t_h = nullptr, *t_tok = nullptr, *t_ada = nullptr, *t_lora = nullptr, *mod = nullptr, *mod_final = nullptr,
+        *mod_b = nullptr, *modf_b = nullptr;
+  int n_timesteps = 0, ctx_Be = 0, ctx_Lc = 0, ctx_Lpad = 0;
+
+  ~Dit() {
+    for (void* p : allocs) cudaFree(p);
+  }
+  template <typename T>
+  int alloc(T** out, size_t count) {
+    void* p = nullptr;
+    const size_t bytes = ((count * sizeof(T)) + 255) & ~size_t(255);
+    EZB_CUDA(cudaMalloc(&p, bytes));
+    EZB_CUDA(cudaMemset(p, 0, bytes));
+    allocs.push_back(p);
+    *out = reinterpret_cast<T*>(p);
+    return EZB_OK;
+  }
+
+  // ---------------------------------------------------------------- weight registry
+  void reg(const std::string& key, std::vector<int64_t> shape, std::function<int(const float*, cudaStream_t)> fn) {
+    WeightSpec s;
+    s.shape = std::move(shape);
+    s.load = std::move(fn);
+    specs[key] = std::move(s);
+  }
+  int reg_f32(const std::string& key, std::vector<int64_t> shape, float** dst) {
+    size_t n = 1;
+    for (auto v : shape) n *= v;
+    EZB_TRY(alloc(dst, n));
+    float* p = *dst;
+    reg(key, shape, [p, n](const float* src, cudaStream_t st) -> int {
+      EZB_CUDA(cudaMemcpyAsync(p, src, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      return EZB_OK;
+    });
+    return EZB_OK;
+  }
+  // fp32 [N, K] -> rows [row_off, row_off+N) of bf16 dst [Ntot, kmul*Kpad]
+  void reg_linear(const std::string& key, int N, int K, bf16* dst, int Kpad, int row_off, int geglu_inner = 0, std::vector<int64_t> shape = {}) {
+    const int km = kmul;
+    if (shape.empty()) shape = {N, K};
+    reg(key, shape, [=](const float* src, cudaStream_t st) -> int {
+      const size_t n = (size_t)N * Kpad;
+      pack_weight_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, N, K, dst, Kpad, km, row_off, geglu_inner, GEGLU_BN / 2);
+      EZB_CUDA(cudaGetLastError());
+      return EZB_OK;
+    });
+  }
+  int alloc_w(bf16** dst, int N, int Kpad) { return alloc(dst, (size_t)N * kmul * Kpad); }
+
+  int init(const ezb_dit_desc& desc, Device* device) {
+    d = desc;
+    dev = device;
+    D = d.embed_dim; H = d.num_heads; inner = d.inner_dim; r = d.ada_rank; C = d.latent_chans;
+    if (D <= 0 || H <= 0 || D % H) return fail(EZB_ERR_UNSUPPORTED, "embed_dim %d / num_heads %d", D, H);
+    dh = D / H;
+    half = d.depth / 2;
+    nblk = d.is_controlnet ? half : d.depth + 1;
+    kmul = d.precision == 1 ? 3 : 1;
+    if (d.precision != 0 && d.precision != 1) return fail(EZB_ERR_UNSUPPORTED, "precision %d", d.precision);
+    if (dh > 96 || dh % 8 || D % 16 || inner % (GEGLU_BN / 2) || d.context_dim % 8 || d.depth % 2)
+      return fail(EZB_ERR_UNSUPPORTED, "unsupported dims: D %d dh %d inner %d ctx %d depth %d", D, dh, inner, d.context_dim, d.depth);
+    if (d.max_batch < 1 || d.max_batch > 256 || d.max_len < 1 || d.max_ctx_len < 1 || d.max_timesteps < 1) return fail(EZB_ERR_ARG, "workspace bounds");
+    Kp = (2 * C + 1 + KP_PATCH_ALIGN - 1) / KP_PATCH_ALIGN * KP_PATCH_ALIGN;
+    DHP = (dh + 63) / 64 * 64;
+    DVP = (dh + 15) / 16 * 16;
+    use_tc_attention = (d.precision == 0);
+    blk.resize(nblk);
+    const std::string pre = d.is_controlnet ? "" : "model.";
+    // ---- trunk
+    EZB_TRY(reg_f32("mask_embed", {C}, &mask_embed));  // controlnet handles take the MaskDiT's mask_embed too (x257 is built from it)
+    EZB_TRY(alloc_w(&w_patch, D, Kp));
+    reg_linear(pre + "patch_embed.proj.weight", D, 2 * C + 1, w_patch, Kp, 0, 0, {D, 2 * C + 1, 1});
+    EZB_TRY(reg_f32(pre + "patch_embed.proj.bias", {D}, &b_patch));
+    EZB_TRY(reg_f32(pre + "time_embed.mlp.0.weight", {D, 256}, &te_w0));
+    EZB_TRY(reg_f32(pre + "time_embed.mlp.0.bias", {D}, &te_b0));
+    EZB_TRY(reg_f32(pre + "time_embed.mlp.2.weight", {D, D}, &te_w2));
+    EZB_TRY(reg_f32(pre + "time_embed.mlp.2.bias", {D}, &te_b2));
+    EZB_TRY(reg_f32(pre + "time_ada.weight", {6 * D, D}, &ta_w));
+    EZB_TRY(reg_f32(pre + "time_ada.bias", {6 * D}, &ta_b));
+    if (!d.is_controlnet) {
+      EZB_TRY(reg_f32(pre + "time_ada_final.weight", {2 * D, D}, &taf_w));
+      EZB_TRY(reg_f32(pre + "time_ada_final.bias", {2 * D}, &taf_b));
+    }
+    EZB_TRY(alloc_w(&w_ce0, D, d.context_dim));
+    reg_linear(pre + "context_embed.0.weight", D, d.context_dim, w_ce0, d.context_dim, 0);
+    EZB_TRY(reg_f32(pre + "context_embed.0.bias", {D}, &b_ce0));
+    EZB_TRY(alloc_w(&w_ce2, D, D));
+    reg_linear(pre + "context_embed.2.weight", D, D, w_ce2, D, 0);
+    EZB_TRY(reg_f32(pre + "context_embed.2.bias", {D}, &b_ce2));
+    // ---- blocks
+    for (int i = 0; i < nblk; ++i) {
+      BlockW& w = blk[i];
+      std::string p;
+      const bool is_out = !d.is_controlnet && i > half;
+      if (d.is_controlnet || i < half) p = pre + "in_blocks." + std::to_string(i);
+      else if (i == half) p = pre + "mid_block";
+      else p = pre + "out_blocks." + std::to_string(i - half - 1);
+      EZB_TRY(reg_f32(p + ".norm1.weight", {D}, &w.n1w)); EZB_TRY(reg_f32(p + ".norm1.bias", {D}, &w.n1b));
+      EZB_TRY(reg_f32(p + ".norm2.weight", {D}, &w.n2w)); EZB_TRY(reg_f32(p + ".norm2.bias", {D}, &w.n2b));
+      EZB_TRY(reg_f32(p + ".norm3.weight", {D}, &w.n3w)); EZB_TRY(reg_f32(p + ".norm3.bias", {D}, &w.n3b));
+      EZB_TRY(reg_f32(p + ".norm_context.weight", {D}, &w.ncw)); EZB_TRY(reg_f32(p + ".norm_context.bias", {D}, &w.ncb));
+      EZB_TRY(alloc_w(&w.qkv, 3 * D, D));
+      reg_linear(p + ".attn.to_q.weight", D, D, w.qkv, D, 0);
+      reg_linear(p + ".attn.to_k.weight", D, D, w.qkv, D, D);
+      reg_linear(p + ".attn.to_v.weight", D, D, w.qkv, D, 2 * D);
+      EZB_TRY(reg_f32(p + ".attn.norm_q.weight", {dh}, &w.nqw)); EZB_TRY(reg_f32(p + ".attn.norm_q.bias", {dh}, &w.nqb));
+      EZB_TRY(reg_f32(p + ".attn.norm_k.weight", {dh}, &w.nkw)); EZB_TRY(reg_f32(p + ".attn.norm_k.bias", {dh}, &w.nkb));
+      EZB_TRY(alloc_w(&w.proj, D, D));
+      reg_linear(p + ".attn.proj.weight", D, D, w.proj, D, 0);
+      EZB_TRY(reg_f32(p + ".attn.proj.bias", {D}, &w.b_proj));
+      EZB_TRY(reg_f32(p + ".attn.rotary.inv_freq", {dh / 2}, &w.inv_freq));
+      EZB_TRY(alloc_w(&w.cq, D, D));
+      reg_linear(p + ".cross_attn.to_q.weight", D, D, w.cq, D, 0);
+      EZB_TRY(alloc_w(&w.ckv, 2 * D, D));
+      reg_linear(p + ".cross_attn.to_k.weight", D, D, w.ckv, D, 0);
+      reg_linear(p + ".cross_attn.to_v.weight", D, D, w.ckv, D, D);
+      EZB_TRY(reg_f32(p + ".cross_attn.norm_q.weight", {dh}, &w.cnqw)); EZB_TRY(reg_f32(p + ".cross_attn.norm_q.bias", {dh}, &w.cnqb));
+      EZB_TRY(reg_f32(p + ".cross_attn.norm_k.weight", {dh}, &w.cnkw)); EZB_TRY(reg_f32(p + ".cross_attn.norm_k.bias", {dh}, &w.cnkb));
+      EZB_TRY(alloc_w(&w.cproj, D, D));
+      reg_linear(p + ".cross_attn.proj.weight", D, D, w.cproj, D, 0);
+      EZB_TRY(reg_f32(p + ".cross_attn.proj.bias", {D}, &w.b_cproj));
+      EZB_TRY(alloc_w(&w.mlp1, 2 * inner, D));
+      reg_linear(p + ".mlp.net.0.proj.weight", 2 * inner, D, w.mlp1, D, 0, inner);
+      EZB_TRY(alloc(&w.b_mlp1, (size_t)2 * inner));
+      {
+        float* dst = w.b_mlp1;
+        const int in_ = inner;
+        reg(p + ".mlp.net.0.proj.bias", {2 * inner}, [dst, in_](const float* src, cudaStream_t st) -> int {
+          pack_geglu_bias_kernel<<<(2 * in_ + 255) / 256, 256, 0, st>>>(src, dst, in_, GEGLU_BN / 2);
+          EZB_CUDA(cudaGetLastError());
+          return EZB_OK;
+        });
+      }
+      EZB_TRY(alloc_w(&w.mlp2, D, inner));
+      reg_linear(p + ".mlp.net.2.weight", D, inner, w.mlp2, inner, 0);
+      EZB_TRY(reg_f32(p + ".mlp.net.2.bias", {D}, &w.b_mlp2));
+      EZB_TRY(reg_f32(p + ".adaln.scale_shift_table", {6, D}, &w.table));
+      EZB_TRY(reg_f32(p + ".adaln.lora_a.weight", {6 * r, D}, &w.lora_a));
+      EZB_TRY(reg_f32(p + ".adaln.lora_b.weight", {6 * D, 6 * r}, &w.lora_b));
+      if (is_out) {
+        EZB_TRY(reg_f32(p + ".skip_norm.weight", {2 * D}, &w.snw)); EZB_TRY(reg_f32(p + ".skip_norm.bias", {2 * D}, &w.snb));
+        EZB_TRY(alloc_w(&w.skip, D, 2 * D));
+        reg_linear(p + ".skip_linear.weight", D, 2 * D, w.skip, 2 * D, 0);
+        EZB_TRY(reg_f32(p + ".skip_linear.bias", {D}, &w.b_skip));
+      }
+      if (d.is_controlnet) {
+        EZB_TRY(alloc_w(&w.zero_w, D, D));
+        reg_linear("controlnet_zero_blocks." + std::to_string(i) + ".weight", D, D, w.zero_w, D, 0);
+        EZB_TRY(reg_f32("controlnet_zero_blocks." + std::to_string(i) + ".bias", {D}, &w.zero_b));
+      }
+    }
+    if (!d.is_controlnet) {
+      EZB_TRY(reg_f32("model.final_block.norm.weight", {D}, &fn_w)); EZB_TRY(reg_f32("model.final_block.norm.bias", {D}, &fn_b));
+      EZB_TRY(alloc_w(&w_final, C, D));
+      reg_linear("model.final_block.linear.weight", C, D, w_final, D, 0);
+      EZB_TRY(reg_f32("model.final_block.linear.bias", {C}, &b_final));
+      EZB_TRY(alloc(&fc_w, (size_t)3 * C * C));
+      {
+        float* dst = fc_w;
+        const int c = C;
+        reg("model.final_block.final_layer.weight", {C, C, 3}, [dst, c](const float* src, cudaStream_t st) -> int {
+          // [co][ci][k] -> [k][ci][co]
+          permute3_kernel<<<(3 * c * c + 255) / 256, 256, 0, st>>>(src, dst, 3, c, c, 1, 3, 3 * c);
+          EZB_CUDA(cudaGetLastError());
+          return EZB_OK;
+        });
+      }
+      EZB_TRY(reg_f32("model.final_block.final_layer.bias", {C}, &fc_b));
+    } else {
+      const int c0 = d.cond_c0, c1 = d.cond_c1;
+      EZB_TRY(reg_f32("controlnet_pre.conv_in.weight", {c0, 1, 1}, &cs_in_w)); EZB_TRY(reg_f32("controlnet_pre.conv_in.bias", {c0}, &cs_in_b));
+      EZB_TRY(reg_f32("controlnet_pre.mask_embed", {c0}, &cs_me));
+      EZB_TRY(reg_f32("controlnet_pre.blocks.0.0.weight", {c0 + 1, c0 + 1, 3}, &cs_c0_w)); EZB_TRY(reg_f32("controlnet_pre.blocks.0.0.bias", {c0 + 1}, &cs_c0_b));
+      EZB_TRY(reg_f32("controlnet_pre.blocks.0.2.weight", {c1, c0 + 1, 3}, &cs_c1_w)); EZB_TRY(reg_f32("controlnet_pre.blocks.0.2.bias", {c1}, &cs_c1_b));
+      EZB_TRY(reg_f32("controlnet_pre.conv_out.weight", {D, c1, 1}, &cs_out_w)); EZB_TRY(reg_f32("controlnet_pre.conv_out.bias", {D}, &cs_out_b));
+    }
+    // ---- workspace
+    const size_t Mx = (size_t)d.max_batch * d.max_len, Mc = (size_t)d.max_batch * d.max_ctx_len;
+    const size_t Mmax = Mx > Mc ? Mx : Mc;
+    EZB_TRY(alloc(&x0, Mx * D)); EZB_TRY(alloc(&xa, Mx * D)); EZB_TRY(alloc(&xb, Mx * D));
+    skips.resize(half);
+    for (int i = 0; i < half; ++i) EZB_TRY(alloc(&skips[i], Mx * D));
+    const size_t act_cols = (size_t)kmul * (2 * D > d.context_dim ? 2 * D : d.context_dim);
+    EZB_TRY(alloc(&act, Mmax * act_cols));
+    EZB_TRY(alloc(&a_patch, Mx * kmul * Kp));
+    EZB_TRY(alloc(&attn_out, Mmax * kmul * D));
+    EZB_TRY(alloc(&mid, Mx * kmul * inner));
+    {
+      float* q4 = nullptr;
+      EZB_TRY(alloc(&q4, Mmax * 3 * D));
+      qkv = q4;
+    }
+    if (!use_tc_attention) {
+      EZB_TRY(alloc(&q32, Mx * D)); EZB_TRY(alloc(&k32, Mx * D)); EZB_TRY(alloc(&v32, Mx * D));
+    } else {
+      const size_t Lp = ((size_t)d.max_len + 7) / 8 * 8;
+      EZB_TRY(alloc(&q16, Mx * H * DHP)); EZB_TRY(alloc(&k16, Mx * H * DHP));
+      EZB_TRY(alloc(&vt16, (size_t)d.max_batch * H * DVP * Lp));
+    }
+    EZB_TRY(alloc(&ctx_emb, Mc * D));
+    EZB_TRY(alloc(&ctx_mask, Mc));
+    const size_t Lcp = ((size_t)d.max_ctx_len + 7) / 8 * 8;
+    for (int i = 0; i < nblk; ++i) {
+      if (!use_tc_attention) {
+        EZB_TRY(alloc(&blk[i].kc32, Mc * D)); EZB_TRY(alloc(&blk[i].vc32, Mc * D));
+      } else {
+        EZB_TRY(alloc(&blk[i].kc16, Mc * H * DHP));
+        EZB_TRY(alloc(&blk[i].vtc16, (size_t)d.max_batch * H * DVP * Lcp));
+      }
+    }
+    const size_t T = d.max_timesteps;
+    EZB_TRY(alloc(&t_vals, T)); EZB_TRY(alloc(&t_emb, T * 256)); EZB_TRY(alloc(&t_h, T * D)); EZB_TRY(alloc(&t_tok, T * D));
+    EZB_TRY(alloc(&t_ada, T * 6 * D)); EZB_TRY(alloc(&t_lora, T * 6 * r));
+    EZB_TRY(alloc(&mod, T * nblk * 6 * D));
+    EZB_TRY(alloc(&mod_b, (size_t)d.max_batch * nblk * 6 * D));
+    if (!d.is_controlnet) {
+      EZB_TRY(alloc(&mod_final, T * 2 * D));
+      EZB_TRY(alloc(&modf_b, (size_t)d.max_batch * 2 * D));
+      EZB_TRY(alloc(&ybuf, Mx * C));
+    } else {
+      EZB_TRY(alloc(&cond_emb, Mx * D));
+      EZB_TRY(alloc(&cs_t0, (size_t)d.max_batch * (d.cond_c0 + 1) * 2 * d.max_len));
+      EZB_TRY(alloc(&cs_t1, (size_t)d.max_batch * (d.cond_c0 + 1) * 2 * d.max_len));
+      EZB_TRY(alloc(&cs_t2, (size_t)d.max_batch * d.cond_c1 * d.max_len));
+    }
+    return EZB_OK;
+  }
+
+  int load_weight(const char* key, const float* data, const int64_t* shape, int ndim, cudaStream_t st) {
+    auto it = specs.find(key);
+    if (it == specs.end()) return fail(EZB_ERR_WEIGHT, "unexpected state-dict key '%s'", key);
+    WeightSpec& s = it->second;
+    bool ok = (int)s.shape.size() == ndim;
+    for (int i = 0; ok && i < ndim; ++i) ok = s.shape[i] == shape[i];
+    if (!ok) return fail(EZB_ERR_WEIGHT, "shape mismatch for '%s'", key);
+    EZB_TRY(s.load(data, st));
+    s.loaded = true;
+    return EZB_OK;
+  }
+  int finalize() {
+    for (auto& kv : specs)
+      if (!kv.second.loaded) return fail(EZB_ERR_WEIGHT, "missing state-dict key '%s'", kv.first.c_str());
+    finalized = true;
+    return EZB_OK;
+  }
+
+  // ---------------------------------------------------------------- launch helpers
+  int ln(cudaStream_t st, const float* x, int D1, const float* x2, const float* x3, int D2, const float* w, const float* b, const float* shift,
+         const float* scale, int mod_bstride, int rows_per_batch, bf16* out, int M) {
+    LnParams p;
+    p.x = x; p.x2 = x2; p.x3 = x3; p.D1 = D1; p.D2 = D2; p.w = w; p.b = b; p.shift = shift; p.scale = scale; p.mod_bstride = mod_bstride;
+    p.rows_per_batch = rows_per_batch; p.out = out; p.kmul = kmul; p.M = M;
+    ln_mod_cast_kernel<<<(M + 7) / 8, 256, 0, st>>>(p);
+    EZB_CUDA(cudaGetLastError());
+    return EZB_OK;
+  }
+  EpiLinearParams epi() {
+    EpiLinearParams e;
+    memset(&e, 0, sizeof e);
+    return e;
+  }
+  int lin(cudaStream_t st, const bf16* A, int K, const bf16* W, int M, int N, const EpiLinearParams& e) {
+    return gemm<128, EpiLinear<128>>(*dev, st, A, kmul * K, W, kmul * K, M, N, kmul * K, e);
+  }
+  int small_lin(cudaStream_t st, const float* in, int ld_in, const float* W, const float* bias, const float* add, int ld_add, float* out, int ld_out, int R,
+                int N, int K, int act, float scale) {
+    small_linear_kernel<<<(N + 7) / 8, 256, 0, st>>>(in, ld_in, W, bias, add, ld_add, out, ld_out, R, N, K, act, scale);
+    EZB_CUDA(cudaGetLastError());
+    return EZB_OK;
+  }
+  // head layout for attention from a GEMM output holding `nsec` sections
+  int qk_prep(cudaStream_t st, int ld_in, int nsec, const int* col_off, const int* kinds, const float* nqw_, const float* nqb_, const float* nkw_,
+              const float* nkb_, const float* inv_freq, int B, int L, float* const* f32o, bf16* const* bfo, int Lpad) {
+    const int total = B * L * H * nsec;
+    auto fill = [&](auto& p) {
+      p.ld_in = ld_in; p.n_sections = nsec;
+      for (int i = 0; i < 3; ++i) { p.col_off[i] = i < nsec ? col_off[i] : 0; p.sec_kind[i] = i < nsec ? kinds[i] : 0; p.f32_out[i] = i < nsec ? f32o[i] : nullptr; p.bf_out[i] = i < nsec ? bfo[i] : nullptr; }
+      p.nw[0] = nqw_; p.nb[0] = nqb_; p.nw[1] = nkw_; p.nb[1] = nkb_; p.use_rope = inv_freq != nullptr; p.inv_freq = inv_freq;
+      p.B = B; p.L = L; p.H = H; p.dh = dh; p.ld_qk = DHP; p.Lpad = Lpad; p.dv_pad = DVP;
+    };
+    if (kmul == 3) {
+      QkPrepParams<float> p; p.in = reinterpret_cast<const float*>(qkv); fill(p);
+      qk_prep_kernel<float><<<(total + 7) / 8, 256, 0, st>>>(p);
+    } else {
+      QkPrepParams<bf16> p; p.in = reinterpret_cast<const bf16*>(qkv); fill(p);
+      qk_prep_kernel<bf16><<<(total + 7) / 8, 256, 0, st>>>(p);
+    }
+    EZB_CUDA(cudaGetLastError());
+    return EZB_OK;
+  }
+  // GEMM whose output feeds qk_prep: bf16 [M,N] in fast mode, fp32 in parity mode
+  int lin_to_qkv(cudaStream_t st, const bf16* A, int K, const bf16* W, int M, int N) {
+    EpiLinearParams e = epi();
+    if (kmul == 3) { e.out_f32 = reinterpret_cast<float*>(qkv); e.ld32 = N; }
+    else { e.out_bf16 = reinterpret_cast<bf16*>(qkv); e.ld16 = N; }
+    return lin(st, A, K, W, M, N, e);
+  }
+  int attention(cudaStream_t st, const float* q32_, const float* k32_, const float* v32_, const bf16* q16_, const bf16* k16_, const bf16* vt16_,
+                const uint8_t* mask, int B, int Lq, int Lk, int Lkpad) {
+    const float scale = 1.0f / sqrtf((float)dh);
+    if (!use_tc_attention) {
+      const size_t smem = attn_simt_smem(dh);
+      static bool set = false;
+      if (!set) { EZB_CUDA(cudaFuncSetAttribute(attn_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); set = true; }
+      dim3 grid((Lq + SA_WARPS * SA_QW - 1) / (SA_WARPS * SA_QW), B * H);
+      attn_simt_kernel<<<grid, SA_WARPS * 32, smem, st>>>(q32_, k32_, v32_, mask, attn_out, H, Lq, Lk, dh, scale, kmul);
+      EZB_CUDA(cudaGetLastError());
+      return EZB_OK;
+    }
+    return attention_tc(*dev, st, q16_, k16_, vt16_, mask, attn_out, B, H, Lq, Lk, Lkpad, dh, DHP, DVP, scale);
+  }
+
+  // ---------------------------------------------------------------- step-invariant precompute
+  int set_context(const float* ctx, const uint8_t* mask, int Be, int Lc, cudaStream_t st) {
+    if (!finalized) return fail(EZB_ERR_STATE, "weights not finalized");
+    if (Be < 1 || Be > d.max_batch || Lc < 1 || Lc > d.max_ctx_len) return fail(EZB_ERR_SHAPE, "set_context: Be %d Lc %d exceed workspace", Be, Lc);
+    const int Mc = Be * Lc, cd = d.context_dim;
+    ctx_Be = Be; ctx_Lc = Lc; ctx_Lpad = (Lc + 7) / 8 * 8;
+    EZB_CUDA(cudaMemcpyAsync(ctx_mask, mask, (size_t)Mc, cudaMemcpyDeviceToDevice, st));
+    EZB_TRY(ln(st, ctx, cd, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0, 1, act, Mc));  // cast only
+    EpiLinearParams e = epi();
+    e.bias = b_ce0; e.out_bf16 = attn_out; e.ld16 = kmul * D; e.split_stride = kmul == 3 ? D : 0; e.act = ACT_SILU;
+    EZB_TRY(lin(st, act, cd, w_ce0, Mc, D, e));
+    e = epi();
+    e.bias = b_ce2; e.out_f32 = ctx_emb; e.ld32 = D;
+    EZB_TRY(lin(st, attn_out, D, w_ce2, Mc, D, e));
+    for (int i = 0; i < nblk; ++i) {
+      BlockW& w = blk[i];
+      EZB_TRY(ln(st, ctx_emb, D, nullptr, nullptr, 0, w.ncw, w.ncb, nullptr, nullptr, 0, 1, act, Mc));
+      EZB_TRY(lin_to_qkv(st, act, D, w.ckv, Mc, 2 * D));
+      const int off[2] = {0, D}, kinds[2] = {1, 2};
+      float* f32o[2] = {w.kc32, w.vc32};
+      bf16* bfo[2] = {w.kc16, w.vtc16};
+      if (use_tc_attention) EZB_CUDA(cudaMemsetAsync(w.vtc16, 0, (size_t)Be * H * DVP * ctx_Lpad * sizeof(bf16), st));
+      EZB_TRY(qk_prep(st, 2 * D, 2, off, kinds, nullptr, nullptr, w.cnkw, w.cnkb, nullptr, Be, Lc, f32o, bfo, ctx_Lpad));
+    }
+    return EZB_OK;
+  }
+
+  int set_timesteps(const int64_t* ts, int n, cudaStream_t st) {
+    if (!finalized) return fail(EZB_ERR_STATE, "weights not finalized");
+    if (n < 1 || n > d.max_timesteps) return fail(EZB_ERR_SHAPE, "set_timesteps: n %d exceeds max_timesteps %d", n, d.max_timesteps);
+    std::vector<float> tf(n);
+    for (int i = 0; i < n; ++i) tf[i] = (float)ts[i];
+    EZB_CUDA(cudaMemcpyAsync(t_vals, tf.data(), n * sizeof(float), cudaMemcpyHostToDevice, st));
+    EZB_CUDA(cudaStreamSynchronize(st));  // tf is a stack-owned staging buffer
+    timestep_embed_kernel<<<(n * 128 + 255) / 256, 256, 0, st>>>(t_vals, t_emb, n);
+    EZB_TRY(small_lin(st, t_emb, 256, te_w0, te_b0, nullptr, 0, t_h, D, n, D, 256, 1, 1.f));
+    EZB_TRY(small_lin(st, t_h, D, te_w2, te_b2, nullptr, 0, t_tok, D, n, D, D, 1, 1.f));  // time_act SiLU folded (udit.py:313)
+    EZB_TRY(small_lin(st, t_tok, D, ta_w, ta_b, nullptr, 0, t_ada, 6 * D, n, 6 * D, D, 0, 1.f));
+    if (!d.is_controlnet) EZB_TRY(small_lin(st, t_tok, D, taf_w, taf_b, nullptr, 0, mod_final, 2 * D, n, 2 * D, D, 0, 1.f));
+    const int ldm = nblk * 6 * D;
+    for (int i = 0; i < nblk; ++i) {
+      BlockW& w = blk[i];
+      EZB_TRY(small_lin(st, t_tok, D, w.lora_a, nullptr, nullptr, 0, t_lora, 6 * r, n, 6 * r, D, 0, 1.f));
+      EZB_TRY(small_lin(st, t_lora, 6 * r, w.lora_b, nullptr, t_ada, 6 * D, mod + (size_t)i * 6 * D, ldm, n, 6 * D, 6 * r, 0, d.ada_scaling));
+      add_rowvec_kernel<<<(unsigned)(((size_t)n * 6 * D + 255) / 256), 256, 0, st>>>(mod + (size_t)i * 6 * D, ldm, w.table, n, 6 * D);
+    }
+    EZB_CUDA(cudaGetLastError());
+    n_timesteps = n;
+    return EZB_OK;
+  }
+
+  // modulation rows for this call: uniform timestep -> point into the table (batch stride 0); else gather per sample
+  int select_mod(cudaStream_t st, const int32_t* tidx, int tall, int Be, const float** mod_rows, const float** modf_rows, int* bstride, int* bstride_f) {
+    const int ldm = nblk * 6 * D;
+    bool uniform = true;
+    int t0 = tidx ? tidx[0] : tall;
+    for (int i = 0; tidx && i < Be; ++i) {
+      if (tidx[i] < 0 || tidx[i] >= n_timesteps) return fail(EZB_ERR_ARG, "t_index %d out of range (n=%d)", tidx[i], n_timesteps);
+      uniform = uniform && tidx[i] == t0;
+    }
+    if (t0 < 0 || t0 >= n_timesteps) return fail(EZB_ERR_ARG, "t_index %d out of range (n=%d); call ezb_dit_set_timesteps first", t0, n_timesteps);
+    if (uniform) {
+      *mod_rows = mod + (size_t)t0 * ldm; *bstride = 0;
+      *modf_rows = mod_final ? mod_final + (size_t)t0 * 2 * D : nullptr; *bstride_f = 0;
+    } else {
+      for (int i = 0; i < Be; ++i) {
+        EZB_CUDA(cudaMemcpyAsync(mod_b + (size_t)i * ldm, mod + (size_t)tidx[i] * ldm, (size_t)ldm * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        if (mod_final) EZB_CUDA(cudaMemcpyAsync(modf_b + (size_t)i * 2 * D, mod_final + (size_t)tidx[i] * 2 * D, (size_t)2 * D * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      }
+      *mod_rows = mod_b; *bstride = ldm; *modf_rows = modf_b; *bstride_f = 2 * D;
+    }
+    return EZB_OK;
+  }
+
+  // ---------------------------------------------------------------- one DiT block (blocks.py:120-160)
+  // x_in: residual stream entering; x_out: buffer the block's first residual write goes to (later ops update it in place).
+  int block(cudaStream_t st, int i, const float* x_in, float* x_out, const float* skip, const float* cskip, const float* modr, int mbs, int Be, int L) {
+    BlockW& w = blk[i];
+    const int M = Be * L;
+    const float* m = modr + (size_t)i * 6 * D;  // shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp (blocks.py:132-133)
+    if (skip) {  // out-blocks: x = skip_linear(LN_2D(cat[x, skip (+ controlnet skip)]))  (blocks.py:124-128, udit.py:345-348)
+      EZB_TRY(ln(st, x_in, D, skip, cskip, D, w.snw, w.snb, nullptr, nullptr, 0, L, act, M));
+      EpiLinearParams e = epi();
+      e.bias = w.b_skip; e.out_f32 = x_out; e.ld32 = D;
+      EZB_TRY(lin(st, act, 2 * D, w.skip, M, D, e));
+      x_in = x_out;
+    }
+    // --- self-attention (blocks.py:137-141)
+    EZB_TRY(ln(st, x_in, D, nullptr, nullptr, 0, w.n1w, w.n1b, m + 0 * D, m + 1 * D, mbs, L, act, M));
+    EZB_TRY(lin_to_qkv(st, act, D, w.qkv, M, 3 * D));
+    {
+      const int off[3] = {0, D, 2 * D}, kinds[3] = {0, 1, 2};
+      float* f32o[3] = {q32, k32, v32};
+      bf16* bfo[3] = {q16, k16, vt16};
+      const int Lp = (L + 7) / 8 * 8;
+      EZB_TRY(qk_prep(st, 3 * D, 3, off, kinds, w.nqw, w.nqb, w.nkw, w.nkb, w.inv_freq, Be, L, f32o, bfo, Lp));
+      EZB_TRY(attention(st, q32, k32, v32, q16, k16, vt16, nullptr, Be, L, L, Lp));
+    }
+    {
+      EpiLinearParams e = epi();
+      e.bias = w.b_proj; e.resid = x_in; e.ldr = D; e.gate = m + 2 * D; e.gate_bstride = mbs; e.rows_per_batch = L; e.out_f32 = x_out; e.ld32 = D;
+      EZB_TRY(lin(st, attn_out, D, w.proj, M, D, e));
+    }
+    // --- cross-attention (blocks.py:147-151): no modulation, no gate
+    EZB_TRY(ln(st, x_out, D, nullptr, nullptr, 0, w.n2w, w.n2b, nullptr, nullptr, 0, L, act, M));
+    EZB_TRY(lin_to_qkv(st, act, D, w.cq, M, D));
+    {
+      const int off[1] = {0}, kinds[1] = {0};
+      float* f32o[1] = {q32};
+      bf16* bfo[1] = {q16};
+      EZB_TRY(qk_prep(st, D, 1, off, kinds, w.cnqw, w.cnqb, nullptr, nullptr, nullptr, Be, L, f32o, bfo, 0));
+      EZB_TRY(attention(st, q32, w.kc32, w.vc32, q16, w.kc16, w.vtc16, ctx_mask, Be, L, ctx_Lc, ctx_Lpad));
+    }
+    {
+      EpiLinearParams e = epi();
+      e.bias = w.b_cproj; e.resid = x_out; e.ldr = D; e.out_f32 = x_out; e.ld32 = D;
+      EZB_TRY(lin(st, attn_out, D, w.cproj, M, D, e));
+    }
+    // --- GEGLU MLP (blocks.py:155-156; modules.py:263-277,366)
+    EZB_TRY(ln(st, x_out, D, nullptr, nullptr, 0, w.n3w, w.n3b, m + 3 * D, m + 4 * D, mbs, L, act, M));
+    {
+      EpiGegluParams g;
+      g.bias = w.b_mlp1; g.out_bf16 = mid; g.ld16 = kmul * inner; g.split_stride = kmul == 3 ? inner : 0;
+      EZB_TRY((gemm<GEGLU_BN, EpiGeglu<GEGLU_BN>>(*dev, st, act, kmul * D, w.mlp1, kmul * D, M, 2 * inner, kmul * D, g)));
+      EpiLinearParams e = epi();
+      e.bias = w.b_mlp2; e.resid = x_out; e.ldr = D; e.gate = m + 5 * D; e.gate_bstride = mbs; e.rows_per_batch = L; e.out_f32 = x_out; e.ld32 = D;
+      EZB_TRY(lin(st, mid, inner, w.mlp2, M, D, e));
+    }
+    return EZB_OK;
+  }
+
+  int embed(cudaStream_t st, const float* x, const float* gt, const uint8_t* gt_mask, const float* resid, int Be, int L) {
+    dim3 grid((L + 31) / 32, (2 * C) / 32, Be), blockd(32, 8);
+    if ((2 * C) % 32) return fail(EZB_ERR_UNSUPPORTED, "latent_chans must be a multiple of 16");
+    patch_pack_kernel<<<grid, blockd, 0, st>>>(x, gt, gt_mask, mask_embed, a_patch, Be, C, L, Kp, kmul);
+    EZB_CUDA(cudaGetLastError());
+    EpiLinearParams e = epi();
+    e.bias = b_patch; e.out_f32 = x0; e.ld32 = D; e.resid = resid; e.ldr = D;
+    return lin(st, a_patch, Kp, w_patch, Be * L, D, e);
+  }
+
+  int check_call(int Be, int L) {
+    if (!finalized) return fail(EZB_ERR_STATE, "weights not finalized");
+    if (Be < 1 || Be > d.max_batch || L < 1 || L > d.max_len) return fail(EZB_ERR_SHAPE, "Be %d / L %d exceed workspace (%d, %d)", Be, L, d.max_batch, d.max_len);
+    if (Be != ctx_Be) return fail(EZB_ERR_STATE, "batch %d differs from the context set by ezb_dit_set_context (%d)", Be, ctx_Be);
+    return EZB_OK;
+  }
+
+  int forward(const float* x, const float* gt, const uint8_t* gt_mask, const int32_t* tidx, int tall, const float* const* cskips, float* out, int Be, int L,
+              cudaStream_t st) {
+    if (d.is_controlnet) return fail(EZB_ERR_STATE, "ezb_dit_forward called on a controlnet handle");
+    EZB_TRY(check_call(Be, L));
+    const float *modr, *modf;
+    int mbs, mbsf;
+    EZB_TRY(select_mod(st, tidx, tall, Be, &modr, &modf, &mbs, &mbsf));
+    EZB_TRY(embed(st, x, gt, gt_mask, nullptr, Be, L));
+    const float* xc = x0;
+    for (int i = 0; i < half; ++i) {
+      EZB_TRY(block(st, i, xc, skips[i], nullptr, nullptr, modr, mbs, Be, L));
+      xc = skips[i];
+    }
+    EZB_TRY(block(st, half, xc, xa, nullptr, nullptr, modr, mbs, Be, L));
+    xc = xa;
+    for (int j = 0; j < half; ++j) {
+      const int si = half - 1 - j;  // skips.pop()
+      EZB_TRY(block(st, half + 1 + j, xc, xb, skips[si], cskips ? cskips[si] : nullptr, modr, mbs, Be, L));
+      xc = xb;
+    }
+    // FinalBlock (blocks.py:199-211): shift, scale = time_ada_final.chunk(2)
+    const int M = Be * L;
+    EZB_TRY(ln(st, xc, D, nullptr, nullptr, 0, fn_w, fn_b, modf, modf + D, mbsf, L, act, M));
+    EpiLinearParams e = epi();
+    e.bias = b_final; e.out_f32 = ybuf; e.ld32 = C;
+    EZB_TRY(lin(st, act, D, w_final, M, C, e));
+    dim3 grid((L + 31) / 32, Be);
+    const size_t smem = (size_t)34 * C * sizeof(float);
+    final_conv_kernel<<<grid, 128, smem, st>>>(ybuf, fc_w, fc_b, out, Be, C, L);
+    EZB_CUDA(cudaGetLastError());
+    return EZB_OK;
+  }
+
+  int controlnet_forward(const float* x, const float* gt, const uint8_t* gt_mask, const int32_t* tidx, int tall, const float* cond, float cscale,
+                         float* const* skips_out, int Be, int L, cudaStream_t st);
+};
+
+}  // namespace ezb
+
+namespace ezb {
+// DiTControlNet.forward (controlnet.py:252-315) with the eval-time stem (controlnet.py:65-84: cond_mask_infer = zeros,
+// so mask_embed is never written and the appended mask channel is all-zero).
+inline int Dit::controlnet_forward(const float* x, const float* gt, const uint8_t* gt_mask, const int32_t* tidx, int tall, const float* cond, float cscale,
+                                   float* const* skips_out, int Be, int L, cudaStream_t st) {
+  if (!d.is_controlnet) return fail(EZB_ERR_STATE, "ezb_controlnet_forward called on a DiT handle");
+  EZB_TRY(check_call(Be, L));
+  const float *modr, *modf;
+  int mbs, mbsf;
+  EZB_TRY(select_mod(st, tidx, tall, Be, &modr, &modf, &mbs, &mbsf));
+  const int c0 = d.cond_c0, c1 = d.cond_c1, T = 2 * L;
+  auto conv = [&](const float* in, const float* w, const float* b, float* out, int Cin, int cin_real, int Tin, int Cout, int Tout, int K, int stride, int pad,
+                  int act, int tr) -> int {
+    const size_t n = (size_t)Be * Cout * Tout;
+    conv1d_direct_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, w, b, out, Be, Cin, cin_real, Tin, Cout, Tout, K, stride, pad, act, tr);
+    EZB_CUDA(cudaGetLastError());
+    return EZB_OK;
+  };
+  EZB_TRY(conv(cond, cs_in_w, cs_in_b, cs_t0, 1, 1, T, c0, T, 1, 1, 0, 0, 0));              // conv_in
+  EZB_TRY(conv(cs_t0, cs_c0_w, cs_c0_b, cs_t1, c0 + 1, c0, T, c0 + 1, T, 3, 1, 1, 1, 0));    // conv3 + SiLU (mask channel == 0)
+  EZB_TRY(conv(cs_t1, cs_c1_w, cs_c1_b, cs_t2, c0 + 1, c0 + 1, T, c1, L, 3, 2, 1, 1, 0));    // conv3 stride 2 + SiLU
+  EZB_TRY(conv(cs_t2, cs_out_w, cs_out_b, cond_emb, c1, c1, L, D, L, 1, 1, 0, 0, 1));        // conv_out -> (B,L,D)
+  EZB_TRY(embed(st, x, gt, gt_mask, cond_emb, Be, L));                                       // x = patch_embed(x) + condition
+  const float* xc = x0;
+  const int M = Be * L;
+  for (int i = 0; i < half; ++i) {
+    EZB_TRY(block(st, i, xc, skips[i], nullptr, nullptr, modr, mbs, Be, L));
+    xc = skips[i];
+  }
+  for (int i = 0; i < half; ++i) {  // zero-linears * conditioning_scale (controlnet.py:311-313)
+    EZB_TRY(ln(st, skips[i], D, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0, L, act, M));
+    EpiLinearParams e = epi();
+    e.bias = blk[i].zero_b; e.out_scale = cscale; e.out_f32 = skips_out[i]; e.ld32 = D;
+    EZB_TRY(lin(st, act, D, blk[i].zero_w, M, D, e));
+  }
+  return EZB_OK;
+}
+}  // namespace ezb

@@ -1,0 +1,140 @@
+// C-ABI entry points of libezb200.so (declared in include/ezb200.h).
+#include "../../include/ezb200.h"
+
+#include "dit.cuh"
+#include "host.cuh"
+
+using namespace ezb;
+
+namespace {
+Device& device_ctx(int device) {
+  static Device devs[16];
+  Device& d = devs[device & 15];
+  if (d.num_sms == 148 && d.id == 0 && device >= 0) {
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) d.num_sms = sms;
+    d.id = device;
+  }
+  return d;
+}
+EpiLinearParams to_epi(const ezb_test_epilogue* e) {
+  EpiLinearParams p;
+  p.bias = e->bias; p.bias_mod = e->bias_mod; p.resid = e->resid; p.ldr = e->ldr; p.gate = e->gate;
+  p.gate_bstride = e->gate_bstride; p.rows_per_batch = e->rows_per_batch; p.out_f32 = e->out_f32; p.ld32 = e->ld32;
+  p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(e->out_bf16); p.ld16 = e->ld16; p.split_stride = e->split_stride;
+  p.act = e->act; p.act_a = e->act_a; p.act_b = e->act_b; p.out_scale = 0.f;
+  return p;
+}
+}  // namespace
+
+extern "C" {
+
+__attribute__((visibility("default"))) int ezb_version(void) { return 1; }
+__attribute__((visibility("default"))) const char* ezb_last_error(void) { return last_error().c_str(); }
+
+__attribute__((visibility("default"))) int ezb_test_gemm(int device, const void* A, int lda, const void* W, int ldw, int M, int N, int K, int bn, int epi_kind,
+                  const ezb_test_epilogue* e, int conv_taps, int conv_center, int conv_dil, int conv_cin_pad, int conv_T, int conv_B,
+                  void* stream) {
+  if (!A || !W || !e) return fail(EZB_ERR_ARG, "ezb_test_gemm: null pointer");
+  EZB_CUDA(cudaSetDevice(device));
+  Device& dev = device_ctx(device);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const __nv_bfloat16* a = reinterpret_cast<const __nv_bfloat16*>(A);
+  const __nv_bfloat16* w = reinterpret_cast<const __nv_bfloat16*>(W);
+  ConvAddr conv;
+  conv.taps = conv_taps; conv.center = conv_center; conv.dilation = conv_dil; conv.cin_pad = conv_cin_pad; conv.T = conv_T; conv.B = conv_B;
+  const ConvAddr* cp = conv_taps > 0 ? &conv : nullptr;
+  if (epi_kind == 0) {
+    EpiLinearParams p = to_epi(e);
+    if (bn == 64) return gemm<64, EpiLinear<64>>(dev, st, a, lda, w, ldw, M, N, K, p, cp);
+    if (bn == 128) return gemm<128, EpiLinear<128>>(dev, st, a, lda, w, ldw, M, N, K, p, cp);
+    if (bn == 256) return gemm<256, EpiLinear<256>>(dev, st, a, lda, w, ldw, M, N, K, p, cp);
+  } else if (epi_kind == 1) {
+    EpiGegluParams p;
+    p.bias = e->bias; p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(e->out_bf16); p.ld16 = e->ld16; p.split_stride = e->split_stride;
+    if (bn == 128) return gemm<128, EpiGeglu<128>>(dev, st, a, lda, w, ldw, M, N, K, p, cp);
+    if (bn == 256) return gemm<256, EpiGeglu<256>>(dev, st, a, lda, w, ldw, M, N, K, p, cp);
+  }
+  return fail(EZB_ERR_UNSUPPORTED, "ezb_test_gemm: bn=%d epi=%d", bn, epi_kind);
+}
+
+
+#define EZB_API __attribute__((visibility("default")))
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+
+EZB_API int ezb_dit_create(ezb_dit** out, const ezb_dit_desc* desc, int device) {
+  if (!out || !desc) return fail(EZB_ERR_ARG, "ezb_dit_create: null argument");
+  EZB_CUDA(cudaSetDevice(device));
+  Dit* h = new Dit();
+  int rc = h->init(*desc, &device_ctx(device));
+  if (rc != 0) { delete h; return rc; }
+  *out = reinterpret_cast<ezb_dit*>(h);
+  return EZB_OK;
+}
+EZB_API int ezb_dit_destroy(ezb_dit* h) {
+  delete reinterpret_cast<Dit*>(h);
+  return EZB_OK;
+}
+EZB_API int ezb_dit_load_weight(ezb_dit* h, const char* key, const float* data, const int64_t* shape, int ndim, void* stream) {
+  if (!h || !key || !data || !shape) return fail(EZB_ERR_ARG, "ezb_dit_load_weight: null argument");
+  return reinterpret_cast<Dit*>(h)->load_weight(key, data, shape, ndim, ST(stream));
+}
+EZB_API int ezb_dit_finalize_weights(ezb_dit* h, void* stream) {
+  if (!h) return fail(EZB_ERR_ARG, "null handle");
+  (void)stream;
+  return reinterpret_cast<Dit*>(h)->finalize();
+}
+EZB_API int ezb_dit_set_context(ezb_dit* h, const float* ctx, const uint8_t* ctx_mask, int Be, int Lc, void* stream) {
+  if (!h || !ctx || !ctx_mask) return fail(EZB_ERR_ARG, "ezb_dit_set_context: null argument");
+  return reinterpret_cast<Dit*>(h)->set_context(ctx, ctx_mask, Be, Lc, ST(stream));
+}
+EZB_API int ezb_dit_set_timesteps(ezb_dit* h, const int64_t* ts, int n, void* stream) {
+  if (!h || !ts) return fail(EZB_ERR_ARG, "ezb_dit_set_timesteps: null argument");
+  return reinterpret_cast<Dit*>(h)->set_timesteps(ts, n, ST(stream));
+}
+EZB_API int ezb_dit_forward(ezb_dit* h, const float* x, const float* gt, const uint8_t* gt_mask, const int32_t* tidx, int tall,
+                            const float* const* cskips, float* out, int Be, int L, void* stream) {
+  if (!h || !x || !out) return fail(EZB_ERR_ARG, "ezb_dit_forward: null argument");
+  return reinterpret_cast<Dit*>(h)->forward(x, gt, gt_mask, tidx, tall, cskips, out, Be, L, ST(stream));
+}
+EZB_API int ezb_controlnet_forward(ezb_dit* h, const float* x, const float* gt, const uint8_t* gt_mask, const int32_t* tidx, int tall,
+                                   const float* condition, float scale, float* const* skips_out, int Be, int L, void* stream) {
+  if (!h || !x || !condition || !skips_out) return fail(EZB_ERR_ARG, "ezb_controlnet_forward: null argument");
+  return reinterpret_cast<Dit*>(h)->controlnet_forward(x, gt, gt_mask, tidx, tall, condition, scale, skips_out, Be, L, ST(stream));
+}
+EZB_API int ezb_cfg_ddim_step(const float* model_out, float* latents, const float* noise, int B, int C, int L, float gs, float gr,
+                              const float* coef, void* stream) {
+  if (!model_out || !latents || !coef || B < 1) return fail(EZB_ERR_ARG, "ezb_cfg_ddim_step: bad argument");
+  const int n = C * L;
+  const float* uncond = gs != 0.f ? model_out + (size_t)B * n : nullptr;
+  cfg_ddim_kernel<<<B, 1024, 0, ST(stream)>>>(model_out, uncond, latents, coef[4] != 0.f ? noise : nullptr, n, gs, gr, coef[0], coef[1], coef[2],
+                                              coef[3], coef[4]);
+  EZB_CUDA(cudaGetLastError());
+  return EZB_OK;
+}
+EZB_API int ezb_vae_create(ezb_vae**, const ezb_vae_desc*, int) { return fail(EZB_ERR_UNSUPPORTED, "vae: not built yet"); }
+EZB_API int ezb_vae_destroy(ezb_vae*) { return EZB_OK; }
+EZB_API int ezb_vae_load_weight(ezb_vae*, const char*, const float*, const int64_t*, int, void*) { return fail(EZB_ERR_UNSUPPORTED, "vae"); }
+EZB_API int ezb_vae_finalize_weights(ezb_vae*, void*) { return fail(EZB_ERR_UNSUPPORTED, "vae"); }
+EZB_API int ezb_vae_decode(ezb_vae*, const float*, float*, int, int, void*) { return fail(EZB_ERR_UNSUPPORTED, "vae"); }
+// impl 0: fp32 CUDA-core kernel (q,k,v fp32 [B,H,L,dh]); impl 1: tcgen05 kernel (q,k bf16 [B*H,L,DHP], vt bf16 [B*H,DVP,Lkpad])
+EZB_API int ezb_test_attention(int device, const void* q, const void* k, const void* v, const uint8_t* key_mask, void* out, int B, int H, int Lq,
+                               int Lk, int dh, int impl, void* stream) {
+  if (!q || !k || !v || !out) return fail(EZB_ERR_ARG, "ezb_test_attention: null pointer");
+  EZB_CUDA(cudaSetDevice(device));
+  const float scale = 1.0f / sqrtf((float)dh);
+  if (impl == 0) {
+    EZB_CUDA(cudaFuncSetAttribute(attn_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    dim3 grid((Lq + SA_WARPS * SA_QW - 1) / (SA_WARPS * SA_QW), B * H);
+    attn_simt_kernel<<<grid, SA_WARPS * 32, attn_simt_smem(dh), ST(stream)>>>(reinterpret_cast<const float*>(q), reinterpret_cast<const float*>(k),
+                                                                            reinterpret_cast<const float*>(v), key_mask,
+                                                                            reinterpret_cast<__nv_bfloat16*>(out), H, Lq, Lk, dh, scale, 1);
+    EZB_CUDA(cudaGetLastError());
+    return EZB_OK;
+  }
+  const int dhp = (dh + 63) / 64 * 64, dvp = (dh + 15) / 16 * 16, lkpad = (Lk + 7) / 8 * 8;
+  return attention_tc(device_ctx(device), ST(stream), reinterpret_cast<const __nv_bfloat16*>(q), reinterpret_cast<const __nv_bfloat16*>(k),
+                      reinterpret_cast<const __nv_bfloat16*>(v), key_mask, reinterpret_cast<__nv_bfloat16*>(out), B, H, Lq, Lk, lkpad, dh, dhp, dvp, scale);
+}
+
+}  // extern "C"

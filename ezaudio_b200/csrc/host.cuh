@@ -1,0 +1,178 @@
+// Host-side plumbing shared by the C-ABI entry points: error capture, TMA tensor-map encoding (driver entry point
+// fetched through the runtime, so the library links only libcudart), GEMM launch helpers.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <tuple>
+
+#include "../../include/ezb200.h"
+#include "gemm.cuh"
+
+namespace ezb {
+
+
+inline std::string& last_error() {
+  static thread_local std::string e;
+  return e;
+}
+inline int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  last_error() = buf;
+  return code;
+}
+#define EZB_CUDA(expr)                                                                                         \
+  do {                                                                                                         \
+    cudaError_t _e = (expr);                                                                                   \
+    if (_e != cudaSuccess) return ::ezb::fail(EZB_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #expr, \
+                                              cudaGetErrorString(_e));                                          \
+  } while (0)
+#define EZB_TRY(expr)        \
+  do {                       \
+    int _r = (expr);         \
+    if (_r != 0) return _r;  \
+  } while (0)
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+// bf16 tensor, innermost dim first; 128-byte swizzle, zero fill out of bounds.
+inline int make_tmap(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes /*rank-1*/,
+                     const uint32_t* box) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return fail(EZB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+  cuuint64_t gd[5], gs[5];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gd[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    if (i + 1 < rank) gs[i] = strides_bytes[i];
+  }
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) return fail(EZB_ERR_ARG, "TMA base %p not 16-byte aligned", ptr);
+  for (int i = 0; i + 1 < rank; ++i)
+    if (gs[i] % 16) return fail(EZB_ERR_ARG, "TMA stride %llu not a multiple of 16 B", (unsigned long long)gs[i]);
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(EZB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d): rank %d dims %llu,%llu box %u,%u", (int)r, rank,
+                                     (unsigned long long)gd[0], (unsigned long long)gd[1], bx[0], bx[1]);
+  return EZB_OK;
+}
+
+struct TmapCache {
+  typedef std::tuple<const void*, uint64_t, uint64_t, uint64_t, uint64_t, uint32_t, uint32_t> Key;
+  std::map<Key, CUtensorMap> maps;
+  // 2-D [outer, inner] row-major bf16 (ld elements per row), box {64, box_outer}
+  int get2d(const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_outer, const CUtensorMap** out) {
+    Key k(ptr, inner, outer, ld, 0, box_outer, 2);
+    auto it = maps.find(k);
+    if (it == maps.end()) {
+      CUtensorMap m;
+      uint64_t dims[2] = {inner, outer}, str[1] = {ld * 2};
+      uint32_t box[2] = {64, box_outer};
+      EZB_TRY(make_tmap(&m, ptr, 2, dims, str, box));
+      it = maps.emplace(k, m).first;
+    }
+    *out = &it->second;
+    return EZB_OK;
+  }
+  // 3-D [batch, rows, inner] bf16, box {64, box_rows, 1}
+  int get3d(const void* ptr, uint64_t inner, uint64_t rows, uint64_t batch, uint64_t ld_row, uint64_t ld_batch, uint32_t box_rows,
+            const CUtensorMap** out) {
+    Key k(ptr, inner, rows, batch, ld_row * 1000003ull + ld_batch, box_rows, 3);
+    auto it = maps.find(k);
+    if (it == maps.end()) {
+      CUtensorMap m;
+      uint64_t dims[3] = {inner, rows, batch}, str[2] = {ld_row * 2, ld_batch * 2};
+      uint32_t box[3] = {64, box_rows, 1};
+      EZB_TRY(make_tmap(&m, ptr, 3, dims, str, box));
+      it = maps.emplace(k, m).first;
+    }
+    *out = &it->second;
+    return EZB_OK;
+  }
+};
+
+struct Device {
+  int id = 0;
+  int num_sms = 148;
+  TmapCache tmaps;
+};
+
+struct ConvAddr {  // implicit-GEMM addressing of A, see gemm.cuh
+  int taps = 0, center = 0, dilation = 1, cin_pad = 0, T = 0, B = 0;
+};
+
+template <int BN, int STAGES, class Epi>
+int launch_gemm_t(Device& dev, cudaStream_t st, const CUtensorMap* tA, const CUtensorMap* tB, const GemmShape& g,
+                  const typename Epi::Params& ep) {
+  auto kern = gemm_tcgen05_kernel<BN, STAGES, Epi>;
+  constexpr int smem = GemmSmem<BN, STAGES>::BYTES;
+  static bool attr_set[16] = {};
+  if (!attr_set[dev.id & 15]) {
+    EZB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set[dev.id & 15] = true;
+  }
+  const int tiles = g.num_m_tiles * g.num_n_tiles;
+  const int grid = tiles < dev.num_sms ? tiles : dev.num_sms;
+  kern<<<grid, GEMM_THREADS, smem, st>>>(*tA, *tB, g, ep);
+  EZB_CUDA(cudaGetLastError());
+  return EZB_OK;
+}
+
+// A: [M, K] bf16 row-major (lda), W: [N, K] bf16 row-major (ldw).  K, lda, ldw multiples of 8.
+template <int BN, class Epi>
+int gemm(Device& dev, cudaStream_t st, const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, int M, int N, int K,
+         const typename Epi::Params& ep, const ConvAddr* conv = nullptr) {
+  if (M <= 0 || N <= 0 || K <= 0) return fail(EZB_ERR_SHAPE, "gemm: empty problem %d %d %d", M, N, K);
+  if ((K % 8) || (lda % 8) || (ldw % 8) || (N % 8)) return fail(EZB_ERR_SHAPE, "gemm: K/ld/N must be multiples of 8 (M%d N%d K%d)", M, N, K);
+  GemmShape g;
+  memset(&g, 0, sizeof g);
+  g.M = M;
+  g.N = N;
+  g.num_n_tiles = (N + BN - 1) / BN;
+  const CUtensorMap *tA, *tB;
+  if (conv && conv->taps > 0) {
+    g.taps = conv->taps;
+    g.center = conv->center;
+    g.dilation = conv->dilation;
+    g.cin_blocks = conv->cin_pad / GEMM_BK;
+    g.T = conv->T;
+    g.tiles_per_batch = (conv->T + GEMM_BM - 1) / GEMM_BM;
+    g.num_m_tiles = g.tiles_per_batch * conv->B;
+    g.num_k_blocks = conv->taps * g.cin_blocks;
+    // A viewed as [B, T, lda]; channels beyond lda zero-fill (K here = real channel count)
+    EZB_TRY(dev.tmaps.get3d(A, (uint64_t)K, (uint64_t)conv->T, (uint64_t)conv->B, (uint64_t)lda, (uint64_t)lda * conv->T, GEMM_BM, &tA));
+    EZB_TRY(dev.tmaps.get2d(W, (uint64_t)conv->taps * conv->cin_pad, (uint64_t)N, (uint64_t)ldw, BN, &tB));
+  } else {
+    g.num_m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
+    g.num_k_blocks = (K + GEMM_BK - 1) / GEMM_BK;
+    EZB_TRY(dev.tmaps.get2d(A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, GEMM_BM, &tA));
+    EZB_TRY(dev.tmaps.get2d(W, (uint64_t)K, (uint64_t)N, (uint64_t)ldw, BN, &tB));
+  }
+  constexpr int STAGES = (BN <= 128) ? 6 : 4;
+  return launch_gemm_t<BN, STAGES, Epi>(dev, st, tA, tB, g, ep);
+}
+
+}  // namespace ezb
