@@ -1,7 +1,9 @@
 // C-ABI entry points of libezb200.so (declared in include/ezb200.h).
 #include "../../include/ezb200.h"
 
+#include <algorithm>
 #include "dit.cuh"
+#include "vae.cuh"
 #include "host.cuh"
 
 using namespace ezb;
@@ -22,7 +24,7 @@ EpiLinearParams to_epi(const ezb_test_epilogue* e) {
   p.bias = e->bias; p.bias_mod = e->bias_mod; p.resid = e->resid; p.ldr = e->ldr; p.gate = e->gate;
   p.gate_bstride = e->gate_bstride; p.rows_per_batch = e->rows_per_batch; p.out_f32 = e->out_f32; p.ld32 = e->ld32;
   p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(e->out_bf16); p.ld16 = e->ld16; p.split_stride = e->split_stride;
-  p.act = e->act; p.act_a = e->act_a; p.act_b = e->act_b; p.out_scale = 0.f;
+  p.act = e->act; p.act_a = e->act_a; p.act_b = e->act_b; p.out_scale = 0.f; p.phase_cols = 0; p.phase_ld16 = 0;
   return p;
 }
 }  // namespace
@@ -112,11 +114,31 @@ EZB_API int ezb_cfg_ddim_step(const float* model_out, float* latents, const floa
   EZB_CUDA(cudaGetLastError());
   return EZB_OK;
 }
-EZB_API int ezb_vae_create(ezb_vae**, const ezb_vae_desc*, int) { return fail(EZB_ERR_UNSUPPORTED, "vae: not built yet"); }
-EZB_API int ezb_vae_destroy(ezb_vae*) { return EZB_OK; }
-EZB_API int ezb_vae_load_weight(ezb_vae*, const char*, const float*, const int64_t*, int, void*) { return fail(EZB_ERR_UNSUPPORTED, "vae"); }
-EZB_API int ezb_vae_finalize_weights(ezb_vae*, void*) { return fail(EZB_ERR_UNSUPPORTED, "vae"); }
-EZB_API int ezb_vae_decode(ezb_vae*, const float*, float*, int, int, void*) { return fail(EZB_ERR_UNSUPPORTED, "vae"); }
+EZB_API int ezb_vae_create(ezb_vae** out, const ezb_vae_desc* desc, int device) {
+  if (!out || !desc) return fail(EZB_ERR_ARG, "ezb_vae_create: null argument");
+  EZB_CUDA(cudaSetDevice(device));
+  Vae* h = new Vae();
+  int rc = h->init(*desc, &device_ctx(device));
+  if (rc != 0) { delete h; return rc; }
+  *out = reinterpret_cast<ezb_vae*>(h);
+  return EZB_OK;
+}
+EZB_API int ezb_vae_destroy(ezb_vae* h) {
+  delete reinterpret_cast<Vae*>(h);
+  return EZB_OK;
+}
+EZB_API int ezb_vae_load_weight(ezb_vae* h, const char* key, const float* data, const int64_t* shape, int ndim, void* stream) {
+  if (!h || !key || !data || !shape) return fail(EZB_ERR_ARG, "ezb_vae_load_weight: null argument");
+  return reinterpret_cast<Vae*>(h)->load_weight(key, data, shape, ndim, ST(stream));
+}
+EZB_API int ezb_vae_finalize_weights(ezb_vae* h, void* stream) {
+  if (!h) return fail(EZB_ERR_ARG, "null handle");
+  return reinterpret_cast<Vae*>(h)->finalize(ST(stream));
+}
+EZB_API int ezb_vae_decode(ezb_vae* h, const float* z, float* wav, int B, int L, void* stream) {
+  if (!h || !z || !wav) return fail(EZB_ERR_ARG, "ezb_vae_decode: null argument");
+  return reinterpret_cast<Vae*>(h)->decode(z, wav, B, L, ST(stream));
+}
 // impl 0: fp32 CUDA-core kernel (q,k,v fp32 [B,H,L,dh]); impl 1: tcgen05 kernel (q,k bf16 [B*H,L,DHP], vt bf16 [B*H,DVP,Lkpad])
 EZB_API int ezb_test_attention(int device, const void* q, const void* k, const void* v, const uint8_t* key_mask, void* out, int B, int H, int Lq,
                                int Lk, int dh, int impl, void* stream) {

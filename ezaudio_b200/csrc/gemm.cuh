@@ -50,6 +50,8 @@ struct EpiLinearParams {
   const float* act_a;      // snake: exp(alpha)[c], c = col % bias_mod (or col)
   const float* act_b;      // snake: 1 / (exp(beta)[c] + 1e-9)
   float out_scale;         // v = (acc + bias) * out_scale (before residual); 0 is treated as 1
+  int phase_cols;          // >0 (conv-transpose): bf16 column = (col / phase_cols) * phase_ld16 + col % phase_cols
+  int phase_ld16;
 };
 
 __device__ __forceinline__ void store_bf16x4(__nv_bfloat16* p, int split_stride, float a, float b, float c, float d) {
@@ -117,7 +119,8 @@ struct EpiLinear {
               v[e] = v[e] + ep.act_b[ch] * s * s;
             }
           }
-          store_bf16x4(ep.out_bf16 + (size_t)row * ep.ld16 + col, ep.split_stride, v[0], v[1], v[2], v[3]);
+          const int c16 = ep.phase_cols > 0 ? (col / ep.phase_cols) * ep.phase_ld16 + col % ep.phase_cols : col;
+          store_bf16x4(ep.out_bf16 + (size_t)row * ep.ld16 + c16, ep.split_stride, v[0], v[1], v[2], v[3]);
         }
       }
     }

@@ -1,0 +1,325 @@
+// Oobleck VAE decoder (stable_vae/models/autoencoders.py:149-190; DecoderBlock :82-113; ResidualUnit :38-61;
+// SnakeBeta stable_vae/models/blocks.py:317-359; weight_norm stable_vae/models/nn/layers.py:9-14).
+// Activations live channels-last ([B, T, C], bf16 tensor-core operands + an fp32 residual stream); every Conv1d /
+// ConvTranspose1d is an implicit GEMM on the tcgen05 kernel (gemm.cuh, conv addressing) with bias, residual add and the
+// NEXT layer's SnakeBeta fused into the epilogue.  Weight-norm is folded once at load time.
+#pragma once
+#include <map>
+#include <string>
+#include <vector>
+
+#include "elementwise.cuh"
+#include "host.cuh"
+
+namespace ezb {
+
+// ||v[row, :]|| for weight_norm (norm over all dims except 0)
+__global__ void wn_norm_kernel(const float* __restrict__ v, int cols, float* __restrict__ norms) {
+  __shared__ float red[32];
+  const float* r = v + (size_t)blockIdx.x * cols;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < cols; i += blockDim.x) s += r[i] * r[i];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    s = warp_sum(s);
+    if (threadIdx.x == 0) norms[blockIdx.x] = sqrtf(s);
+  }
+}
+__device__ __forceinline__ void store_w_split(__nv_bfloat16* tap_base, int c, int C, int kmul, float val) {
+  const __nv_bfloat16 hi = __float2bfloat16_rn(val);
+  tap_base[c] = hi;
+  if (kmul == 3) {
+    tap_base[C + c] = hi;
+    tap_base[2 * C + c] = __float2bfloat16_rn(val - __bfloat162float(hi));
+  }
+}
+// Conv1d: v [Cout, Cin, K], g [Cout] -> dst [Cout, K taps * cin_pad], per tap [hi(Cin) | hi | lo | 0-pad]
+__global__ void pack_conv_w_kernel(const float* __restrict__ v, const float* __restrict__ g, const float* __restrict__ norms, __nv_bfloat16* __restrict__ dst,
+                                   int Cout, int Cin, int K, int cin_pad, int kmul) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)Cout * K * Cin) return;
+  const int ci = i % Cin, tap = (i / Cin) % K, co = i / ((size_t)Cin * K);
+  const float val = g[co] * v[((size_t)co * Cin + ci) * K + tap] / norms[co];
+  store_w_split(dst + ((size_t)co * K + tap) * cin_pad, ci, Cin, kmul, val);
+}
+// ConvTranspose1d (kernel 2s, stride s, padding p): v [Cin, Cout, 2s], g [Cin] -> dst [s*Cout, 3 taps * cin_pad]
+//   out[co, q*s + r] = sum_ci sum_delta x[ci, q + delta] * w[ci, co, r + p - delta*s],  delta = tap - 1
+__global__ void pack_convT_w_kernel(const float* __restrict__ v, const float* __restrict__ g, const float* __restrict__ norms, __nv_bfloat16* __restrict__ dst,
+                                    int Cin, int Cout, int s, int pad, int cin_pad, int kmul) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)s * Cout * 3 * Cin) return;
+  const int ci = i % Cin, tap = (i / Cin) % 3;
+  const int n = i / ((size_t)Cin * 3), r = n / Cout, co = n - r * Cout;
+  const int k = r + pad - (tap - 1) * s;
+  const float val = (k >= 0 && k < 2 * s) ? g[ci] * v[((size_t)ci * Cout + co) * (2 * s) + k] / norms[ci] : 0.f;
+  store_w_split(dst + ((size_t)n * 3 + tap) * cin_pad, ci, Cin, kmul, val);
+}
+__global__ void snake_prep_kernel(const float* __restrict__ alpha, const float* __restrict__ beta, float* __restrict__ a, float* __restrict__ binv, int C) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < C) { a[i] = expf(alpha[i]); binv[i] = 1.0f / (expf(beta[i]) + 1e-9f); }
+}
+// z (B, C, L) fp32 -> channels-last bf16 [B, L, kmul*C]
+__global__ void latent_pack_kernel(const float* __restrict__ z, __nv_bfloat16* __restrict__ out, int C, int L, int kmul) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, l0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int c = c0 + i, l = l0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && l < L) ? z[((size_t)b * C + c) * L + l] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int l = l0 + i, c = c0 + threadIdx.x;
+    if (l < L && c < C) store_act(out + ((size_t)b * L + l) * kmul * C, c, C, kmul, tile[threadIdx.x][i]);
+  }
+}
+// last layer: Conv1d(C -> 1, k=7, pad 3, no bias) on the snake-activated channels-last tensor; w folded fp32 [7][C]
+__global__ void __launch_bounds__(128) wave_out_kernel(const __nv_bfloat16* __restrict__ act, const float* __restrict__ w, float* __restrict__ wav, int C, int T,
+                                                       int kmul) {
+  extern __shared__ float sa[];  // [(TT + 6)][C]
+  constexpr int TT = 64;
+  const int b = blockIdx.y, t0 = blockIdx.x * TT;
+  const __nv_bfloat16* ab = act + (size_t)b * T * kmul * C;
+  for (int i = threadIdx.x; i < (TT + 6) * C; i += blockDim.x) {
+    const int rr = i / C, c = i - rr * C, t = t0 + rr - 3;
+    float v = 0.f;
+    if (t >= 0 && t < T) {
+      const __nv_bfloat16* row = ab + (size_t)t * kmul * C;
+      v = __bfloat162float(row[c]);
+      if (kmul == 3) v += __bfloat162float(row[C + c]);
+    }
+    sa[i] = v;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int tt = warp; tt < TT; tt += 4) {
+    float s = 0.f;
+    for (int k = 0; k < 7; ++k)
+      for (int c = lane; c < C; c += 32) s = fmaf(w[k * C + c], sa[(tt + k) * C + c], s);
+    s = warp_sum(s);
+    if (lane == 0 && t0 + tt < T) wav[(size_t)b * T + t0 + tt] = s;
+  }
+}
+__global__ void fold_wave_w_kernel(const float* __restrict__ v, const float* __restrict__ g, const float* __restrict__ norms, float* __restrict__ w, int C) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // v [1, C, 7] -> w [7][C]
+  if (i < 7 * C) { const int k = i / C, c = i - k * C; w[i] = g[0] * v[c * 7 + k] / norms[0]; }
+}
+
+struct VaeConv {  // one packed conv / conv-transpose
+  __nv_bfloat16* w = nullptr;
+  float* bias = nullptr;
+  int cin = 0, cout = 0, taps = 0, center = 0, dil = 1, cin_pad = 0, N = 0, stride = 0;
+};
+struct VaeSnake { float *a = nullptr, *binv = nullptr; };
+
+struct Vae {
+  ezb_vae_desc d;
+  Device* dev = nullptr;
+  int kmul = 1, nst = 0;
+  std::vector<void*> allocs;
+  std::map<std::string, std::pair<float*, std::vector<int64_t>>> raw;  // staged fp32 copies until finalize
+  std::vector<std::string> expected;
+  bool finalized = false;
+  VaeConv conv_in;
+  std::vector<VaeConv> up;                 // per stage conv-transpose
+  std::vector<VaeSnake> up_snake;          // per stage input snake
+  std::vector<VaeConv> res7, res1;         // [stage*3 + unit]
+  std::vector<VaeSnake> res_s0, res_s2;
+  VaeSnake out_snake;
+  float* out_w = nullptr;                  // [7][C0]
+  std::vector<int> cin_s, cout_s, stride_s;
+  __nv_bfloat16 *actA = nullptr, *actB = nullptr;
+  float* resid = nullptr;
+  size_t elems_per_clip = 0;
+
+  ~Vae() { for (void* p : allocs) cudaFree(p); }
+  template <typename T>
+  int alloc(T** out, size_t count) {
+    void* p = nullptr;
+    const size_t bytes = ((count * sizeof(T)) + 255) & ~size_t(255);
+    EZB_CUDA(cudaMalloc(&p, bytes));
+    EZB_CUDA(cudaMemset(p, 0, bytes));
+    allocs.push_back(p);
+    *out = reinterpret_cast<T*>(p);
+    return EZB_OK;
+  }
+  void expect_wn(const std::string& k, bool bias) { expected.push_back(k + ".weight_g"); expected.push_back(k + ".weight_v"); if (bias) expected.push_back(k + ".bias"); }
+  void expect_snake(const std::string& k) { expected.push_back(k + ".alpha"); expected.push_back(k + ".beta"); }
+
+  int init(const ezb_vae_desc& desc, Device* device) {
+    d = desc; dev = device;
+    kmul = d.precision == 1 ? 3 : 1;
+    nst = d.n_stages;
+    if (nst < 1 || nst > 8 || d.out_channels != 1 || d.latent_dim % 32 || d.channels % 8) return fail(EZB_ERR_UNSUPPORTED, "vae config");
+    std::vector<int> mults(1, 1);
+    for (int i = 0; i < nst; ++i) mults.push_back(d.c_mults[i]);
+    for (int i = nst; i >= 1; --i) { cin_s.push_back(mults[i] * d.channels); cout_s.push_back(mults[i - 1] * d.channels); stride_s.push_back(d.strides[i - 1]); }
+    const std::string p = "decoder.layers.";
+    expect_wn(p + "0", true);
+    for (int j = 0; j < nst; ++j) {
+      const std::string q = p + std::to_string(j + 1) + ".layers.";
+      expect_snake(q + "0"); expect_wn(q + "1", true);
+      for (int u = 0; u < 3; ++u) {
+        const std::string ru = q + std::to_string(u + 2) + ".layers.";
+        expect_snake(ru + "0"); expect_wn(ru + "1", true); expect_snake(ru + "2"); expect_wn(ru + "3", true);
+      }
+    }
+    expect_snake(p + std::to_string(nst + 1));
+    expect_wn(p + std::to_string(nst + 2), false);
+    // workspace: largest channels-last activation per clip
+    size_t T = d.max_latent_len, mx = (size_t)T * cin_s[0];
+    for (int j = 0; j < nst; ++j) { T *= stride_s[j]; mx = std::max(mx, T * (size_t)cout_s[j]); }
+    mx = std::max(mx, (size_t)d.max_latent_len * d.latent_dim);
+    elems_per_clip = mx;
+    EZB_TRY(alloc(&actA, mx * d.max_batch * kmul)); EZB_TRY(alloc(&actB, mx * d.max_batch * kmul));
+    EZB_TRY(alloc(&resid, mx * d.max_batch));
+    return EZB_OK;
+  }
+  int load_weight(const char* key, const float* data, const int64_t* shape, int ndim, cudaStream_t st) {
+    std::string k(key);
+    if (std::find(expected.begin(), expected.end(), k) == expected.end()) return fail(EZB_ERR_WEIGHT, "unexpected VAE key '%s'", key);
+    size_t n = 1;
+    std::vector<int64_t> shp(shape, shape + ndim);
+    for (auto v : shp) n *= v;
+    float* p = nullptr;
+    EZB_TRY(alloc(&p, n));
+    EZB_CUDA(cudaMemcpyAsync(p, data, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    raw[k] = std::make_pair(p, shp);
+    return EZB_OK;
+  }
+  int need(const std::string& k, std::vector<int64_t> shape, float** out) {
+    auto it = raw.find(k);
+    if (it == raw.end()) return fail(EZB_ERR_WEIGHT, "missing VAE key '%s'", k.c_str());
+    if (it->second.second != shape) return fail(EZB_ERR_WEIGHT, "shape mismatch for VAE key '%s'", k.c_str());
+    *out = it->second.first;
+    return EZB_OK;
+  }
+  int pack_conv(const std::string& k, int cout, int cin, int K, int dil, bool bias, VaeConv* c, cudaStream_t st) {
+    float *g, *v, *b = nullptr, *norms;
+    EZB_TRY(need(k + ".weight_g", {cout, 1, 1}, &g));
+    EZB_TRY(need(k + ".weight_v", {cout, cin, K}, &v));
+    if (bias) EZB_TRY(need(k + ".bias", {cout}, &b));
+    EZB_TRY(alloc(&norms, (size_t)cout));
+    wn_norm_kernel<<<cout, 256, 0, st>>>(v, cin * K, norms);
+    c->cin = cin; c->cout = cout; c->N = cout; c->taps = K; c->center = (K - 1) / 2; c->dil = dil; c->bias = b;
+    c->cin_pad = (kmul * cin + 63) / 64 * 64;
+    EZB_TRY(alloc(&c->w, (size_t)cout * K * c->cin_pad));
+    const size_t n = (size_t)cout * K * cin;
+    pack_conv_w_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(v, g, norms, c->w, cout, cin, K, c->cin_pad, kmul);
+    EZB_CUDA(cudaGetLastError());
+    return EZB_OK;
+  }
+  int pack_convT(const std::string& k, int cin, int cout, int s, VaeConv* c, cudaStream_t st) {
+    float *g, *v, *b, *norms;
+    EZB_TRY(need(k + ".weight_g", {cin, 1, 1}, &g));
+    EZB_TRY(need(k + ".weight_v", {cin, cout, 2 * s}, &v));
+    EZB_TRY(need(k + ".bias", {cout}, &b));
+    EZB_TRY(alloc(&norms, (size_t)cin));
+    wn_norm_kernel<<<cin, 256, 0, st>>>(v, cout * 2 * s, norms);
+    c->cin = cin; c->cout = cout; c->N = s * cout; c->taps = 3; c->center = 1; c->dil = 1; c->bias = b; c->stride = s;
+    c->cin_pad = (kmul * cin + 63) / 64 * 64;
+    EZB_TRY(alloc(&c->w, (size_t)c->N * 3 * c->cin_pad));
+    const size_t n = (size_t)c->N * 3 * cin;
+    pack_convT_w_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(v, g, norms, c->w, cin, cout, s, (s + 1) / 2, c->cin_pad, kmul);
+    EZB_CUDA(cudaGetLastError());
+    return EZB_OK;
+  }
+  int prep_snake(const std::string& k, int C, VaeSnake* s, cudaStream_t st) {
+    float *al, *be;
+    EZB_TRY(need(k + ".alpha", {C}, &al)); EZB_TRY(need(k + ".beta", {C}, &be));
+    EZB_TRY(alloc(&s->a, (size_t)C)); EZB_TRY(alloc(&s->binv, (size_t)C));
+    snake_prep_kernel<<<(C + 255) / 256, 256, 0, st>>>(al, be, s->a, s->binv, C);
+    EZB_CUDA(cudaGetLastError());
+    return EZB_OK;
+  }
+  int finalize(cudaStream_t st) {
+    const std::string p = "decoder.layers.";
+    EZB_TRY(pack_conv(p + "0", cin_s[0], d.latent_dim, 7, 1, true, &conv_in, st));
+    up.resize(nst); up_snake.resize(nst); res7.resize(3 * nst); res1.resize(3 * nst); res_s0.resize(3 * nst); res_s2.resize(3 * nst);
+    const int dils[3] = {1, 3, 9};
+    for (int j = 0; j < nst; ++j) {
+      const std::string q = p + std::to_string(j + 1) + ".layers.";
+      EZB_TRY(prep_snake(q + "0", cin_s[j], &up_snake[j], st));
+      EZB_TRY(pack_convT(q + "1", cin_s[j], cout_s[j], stride_s[j], &up[j], st));
+      for (int u = 0; u < 3; ++u) {
+        const std::string ru = q + std::to_string(u + 2) + ".layers.";
+        EZB_TRY(prep_snake(ru + "0", cout_s[j], &res_s0[3 * j + u], st));
+        EZB_TRY(pack_conv(ru + "1", cout_s[j], cout_s[j], 7, dils[u], true, &res7[3 * j + u], st));
+        EZB_TRY(prep_snake(ru + "2", cout_s[j], &res_s2[3 * j + u], st));
+        EZB_TRY(pack_conv(ru + "3", cout_s[j], cout_s[j], 1, 1, true, &res1[3 * j + u], st));
+      }
+    }
+    const int C0 = cout_s[nst - 1];
+    EZB_TRY(prep_snake(p + std::to_string(nst + 1), C0, &out_snake, st));
+    {
+      float *g, *v, *norms;
+      const std::string k = p + std::to_string(nst + 2);
+      EZB_TRY(need(k + ".weight_g", {1, 1, 1}, &g)); EZB_TRY(need(k + ".weight_v", {1, C0, 7}, &v));
+      EZB_TRY(alloc(&norms, (size_t)1)); EZB_TRY(alloc(&out_w, (size_t)7 * C0));
+      wn_norm_kernel<<<1, 256, 0, st>>>(v, C0 * 7, norms);
+      fold_wave_w_kernel<<<(7 * C0 + 255) / 256, 256, 0, st>>>(v, g, norms, out_w, C0);
+      EZB_CUDA(cudaGetLastError());
+    }
+    EZB_CUDA(cudaStreamSynchronize(st));
+    finalized = true;
+    return EZB_OK;
+  }
+
+  // one implicit-GEMM conv: A [B, T, kmul*cin] -> epilogue
+  int run_conv(cudaStream_t st, const VaeConv& c, const __nv_bfloat16* A, int B, int T, const float* resid_in, float* raw_out, __nv_bfloat16* act_out,
+               const VaeSnake* snake) {
+    EpiLinearParams e;
+    memset(&e, 0, sizeof e);
+    e.bias = c.bias;
+    e.bias_mod = c.cout;
+    e.resid = resid_in; e.ldr = c.N;
+    e.out_f32 = raw_out; e.ld32 = c.N;
+    e.out_bf16 = act_out;
+    const int phases = c.N / c.cout;
+    e.ld16 = phases * kmul * c.cout;
+    e.split_stride = kmul == 3 ? c.cout : 0;
+    e.phase_cols = phases > 1 ? c.cout : 0;
+    e.phase_ld16 = kmul * c.cout;
+    if (snake) { e.act = ACT_SNAKE; e.act_a = snake->a; e.act_b = snake->binv; }
+    ConvAddr ca;
+    ca.taps = c.taps; ca.center = c.center; ca.dilation = c.dil; ca.cin_pad = c.cin_pad; ca.T = T; ca.B = B;
+    const int ld = c.taps * c.cin_pad;
+    return gemm<128, EpiLinear<128>>(*dev, st, A, kmul * c.cin, c.w, ld, B * T, c.N, kmul * c.cin, e, &ca);
+  }
+
+  int decode(const float* z, float* wav, int B, int L, cudaStream_t st) {
+    if (!finalized) return fail(EZB_ERR_STATE, "VAE weights not finalized");
+    if (B < 1 || B > d.max_batch || L < 1 || L > d.max_latent_len) return fail(EZB_ERR_SHAPE, "vae_decode: B %d L %d exceed workspace", B, L);
+    dim3 grid((L + 31) / 32, (d.latent_dim + 31) / 32, B), blk(32, 8);
+    latent_pack_kernel<<<grid, blk, 0, st>>>(z, actA, d.latent_dim, L, kmul);
+    EZB_CUDA(cudaGetLastError());
+    __nv_bfloat16 *cur = actA, *oth = actB;
+    int T = L;
+    EZB_TRY(run_conv(st, conv_in, cur, B, T, nullptr, nullptr, oth, &up_snake[0]));
+    std::swap(cur, oth);
+    for (int j = 0; j < nst; ++j) {
+      // conv-transpose: writes the fp32 residual stream [B, T*s, cout] and the first unit's snake input
+      EZB_TRY(run_conv(st, up[j], cur, B, T, nullptr, resid, oth, &res_s0[3 * j]));
+      std::swap(cur, oth);
+      T *= stride_s[j];
+      for (int u = 0; u < 3; ++u) {
+        EZB_TRY(run_conv(st, res7[3 * j + u], cur, B, T, nullptr, nullptr, oth, &res_s2[3 * j + u]));
+        const bool last = u == 2;
+        const VaeSnake* nxt = !last ? &res_s0[3 * j + u + 1] : (j + 1 < nst ? &up_snake[j + 1] : &out_snake);
+        EZB_TRY(run_conv(st, res1[3 * j + u], oth, B, T, resid, last ? nullptr : resid, cur, nxt));
+      }
+    }
+    const int C0 = cout_s[nst - 1];
+    const size_t smem = (size_t)(64 + 6) * C0 * sizeof(float);
+    static bool set = false;
+    if (!set) { EZB_CUDA(cudaFuncSetAttribute(wave_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); set = true; }
+    dim3 g2((T + 63) / 64, B);
+    wave_out_kernel<<<g2, 128, smem, st>>>(cur, out_w, wav, C0, T, kmul);
+    EZB_CUDA(cudaGetLastError());
+    return EZB_OK;
+  }
+};
+
+}  // namespace ezb

@@ -1,0 +1,55 @@
+"""Attention kernels vs a plain PyTorch fp32 reference of the same op (softmax(q k^T/sqrt(dh) + key mask) v).
+impl 0 = fp32 CUDA-core kernel (parity mode): tolerance 2e-2 is the bf16 rounding of the OUTPUT only (values O(1));
+impl 1 = tcgen05 kernel: q, k, v and P are bf16 operands -> tolerance 3e-2 abs on O(1) outputs."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(q, k, v, mask):
+    s = (q @ k.transpose(-1, -2)) / math.sqrt(q.shape[-1])
+    if mask is not None:
+        s = s.masked_fill(~mask[:, None, None, :].bool(), float("-inf"))
+    o = s.softmax(-1) @ v
+    return o.permute(0, 2, 1, 3).reshape(q.shape[0], q.shape[2], -1)
+
+
+@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("B,H,Lq,Lk,dh,masked", [(2, 4, 500, 500, 72, False), (2, 3, 256, 256, 64, False), (3, 2, 500, 100, 72, True),
+                                                 (2, 2, 40, 12, 72, True), (1, 2, 130, 130, 64, False), (1, 16, 1500, 1500, 72, False),
+                                                 (2, 2, 37, 100, 64, True)])
+def test_attention(impl, B, H, Lq, Lk, dh, masked):
+    from ezaudio_b200 import _lib
+    g = torch.Generator(device="cuda").manual_seed(Lq * 7 + Lk + dh)
+    q = torch.randn(B, H, Lq, dh, device="cuda", generator=g) * 1.5
+    k = torch.randn(B, H, Lk, dh, device="cuda", generator=g) * 1.5
+    v = torch.randn(B, H, Lk, dh, device="cuda", generator=g)
+    mask = None
+    if masked:
+        mask = torch.zeros(B, Lk, dtype=torch.uint8, device="cuda")
+        for i in range(B):
+            mask[i, : (1 if i == B - 1 else min(Lk, 8 + 5 * i))] = 1
+    out = torch.zeros(B, Lq, H * dh, device="cuda", dtype=torch.bfloat16)
+    L = _lib.lib()
+    if impl == 0:
+        args = (q.contiguous(), k.contiguous(), v.contiguous())
+        ref = _ref(q, k, v, mask)
+    else:
+        dhp, dvp, lkp = (dh + 63) // 64 * 64, (dh + 15) // 16 * 16, (Lk + 7) // 8 * 8
+        qb = torch.zeros(B * H, Lq, dhp, device="cuda", dtype=torch.bfloat16)
+        kb = torch.zeros(B * H, Lk, dhp, device="cuda", dtype=torch.bfloat16)
+        vt = torch.zeros(B * H, dvp, lkp, device="cuda", dtype=torch.bfloat16)
+        qb[:, :, :dh] = q.reshape(B * H, Lq, dh)
+        kb[:, :, :dh] = k.reshape(B * H, Lk, dh)
+        vt[:, :dh, :Lk] = v.reshape(B * H, Lk, dh).transpose(1, 2)
+        vt[:, :, Lk:] = 7.0  # beyond the true length: must never be read
+        args = (qb, kb, vt)
+        ref = _ref(q.bfloat16().float(), k.bfloat16().float(), v.bfloat16().float(), mask)
+    _lib.check(L.ezb_test_attention(0, _lib.ptr(args[0]), _lib.ptr(args[1]), _lib.ptr(args[2]), _lib.ptr(mask), _lib.ptr(out), B, H, Lq, Lk, dh, impl,
+                                    _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    err = (out.float() - ref).abs().max().item()
+    assert math.isfinite(err) and err < (2e-2 if impl == 0 else 3e-2), err
