@@ -1,0 +1,257 @@
+"""Public API -- same classes, method signatures, defaults and return types as the reference
+(api/ezaudio.py:31-207 `EzAudio`, api/controlnet.py:31-161 `EzAudio_ControlNet`), hosted on the CUDA library.
+
+Extensions (all optional, keyword-only): `text` may be a list of prompts (batched; returns a list of waveforms);
+`text_encoder=` injects a callable `(list[str]) -> (emb (B,Lc,ctx) , mask (B,Lc))` standing in for flan-T5 (the image has no
+network, so T5 weights cannot be fetched -- BASELINE configs use cached embeddings); `ckpt_path="synthetic:<seed>"` builds
+the deterministic random checkpoint of `weights.synthetic_state_dict` instead of reading a file.
+"""
+from __future__ import annotations
+
+import os
+import random
+from typing import Callable, List, Optional, Sequence, Union
+
+import numpy as np
+import torch
+
+from . import config, weights
+from .dit import DiTControlNet, MaskDiT
+from .inference import inference
+from .scheduler import DDIMScheduler
+from .vae import Autoencoder, OobleckDecoder
+
+MAX_SEED = np.iinfo(np.int32).max
+
+
+class SyntheticTextEncoder:
+    """Cached-T5 stand-in: deterministic N(0,1) embeddings keyed by the prompt string; "" -> only the first
+    (EOS) token is valid, like the tokenizer's output for the empty negative prompt."""
+
+    def __init__(self, ctx_dim: int, max_length: int = 100):
+        self.ctx_dim, self.max_length = ctx_dim, max_length
+
+    def __call__(self, prompts: Sequence[str]):
+        embs, masks = [], []
+        for p in prompts:
+            seed = int.from_bytes(p.encode()[:8].ljust(8, b"\0"), "little") % (2 ** 31) + 7 * len(p)
+            g = torch.Generator().manual_seed(seed)
+            embs.append(torch.randn(1, self.max_length, self.ctx_dim, generator=g))
+            n = 1 if p == "" else min(self.max_length, 2 + len(p.split()) + len(p) // 6)
+            m = torch.zeros(1, self.max_length, dtype=torch.bool)
+            m[0, :n] = True
+            masks.append(m)
+        return torch.cat(embs, 0), torch.cat(masks, 0)
+
+
+def _load_audio(path: str, sr: int) -> np.ndarray:
+    """librosa.load(path, sr=sr) stand-in (mono float32 resampled), api/ezaudio.py:146."""
+    import torchaudio
+    wav, fs = torchaudio.load(path)
+    wav = wav.mean(0)
+    if fs != sr:
+        wav = torchaudio.functional.resample(wav, fs, sr)
+    return wav.numpy().astype(np.float32)
+
+
+def _load_t5(name: str, device):
+    try:
+        from transformers import T5EncoderModel, T5Tokenizer
+        tok = T5Tokenizer.from_pretrained(name, local_files_only=True)
+        enc = T5EncoderModel.from_pretrained(name, local_files_only=True).to(device).eval()
+        return tok, enc
+    except Exception:
+        return None, None
+
+
+def _state_dict(path, shapes, key):
+    if isinstance(path, str) and path.startswith("synthetic"):
+        seed = int(path.split(":")[1]) if ":" in path else 0
+        return weights.synthetic_state_dict(shapes, seed)
+    if path is None or not os.path.exists(path):
+        raise FileNotFoundError(f"checkpoint {path!r} not found (no network here: pass a local file or 'synthetic:<seed>')")
+    sd = torch.load(path, map_location="cpu")
+    return sd[key] if key in sd else sd
+
+
+class _Base:
+    def _text_embeds(self, prompts: List[str], neg: List[str]):
+        if self.encode_text is None:
+            raise RuntimeError("no text encoder available (flan-T5 weights are not on disk and there is no network); pass "
+                               "text_encoder=<callable> to the constructor, e.g. ezaudio_b200.api.SyntheticTextEncoder")
+        e, m = self.encode_text(prompts)
+        ue, um = self.encode_text(neg)
+        return e, m, ue, um
+
+    def _make_text_encoder(self, text_encoder, params, device):
+        self.tokenizer = self.text_encoder = None
+        if text_encoder is not None:
+            return text_encoder
+        tok, enc = _load_t5(params["text_encoder"]["model"], device)
+        if tok is None:
+            return None
+        self.tokenizer, self.text_encoder = tok, enc
+        ml = params["text_encoder"]["max_length"]
+
+        def run(prompts):
+            tb = tok(list(prompts), max_length=ml, padding="max_length", truncation=True, return_tensors="pt")
+            ids, mask = tb.input_ids.to(device), tb.attention_mask.to(device).bool()
+            with torch.no_grad():
+                return enc(input_ids=ids, attention_mask=mask).last_hidden_state, mask
+        return run
+
+
+class EzAudio(_Base):
+    """api/ezaudio.py:31."""
+
+    def __init__(self, model_name, ckpt_path=None, vae_path=None, device="cuda", *, text_encoder: Optional[Callable] = None,
+                 precision: str = "bf16", max_batch: int = 4, max_length_s: float = 10.0, config_path=None, vae_config_path=None):
+        self.device = device
+        self.params = config.load_params(model_name, config_path)
+        p = self.params
+        latent_sr = p["autoencoder"]["latent_sr"]
+        max_len = int(round(max_length_s * latent_sr))
+        self.noise_scheduler = DDIMScheduler(**p["diff"])
+        self.unet = MaskDiT(precision=precision, max_batch=2 * max_batch, max_len=max_len, max_ctx_len=p["text_encoder"]["max_length"],
+                            max_timesteps=1000, device=device, **p["model"])
+        self.unet.load_state_dict(_state_dict(ckpt_path, weights.dit_param_shapes(p["model"]), "model"))
+        dcfg = config.load_vae_decoder_config(vae_config_path)
+        dec = OobleckDecoder(precision=precision, max_batch=max_batch, max_latent_len=max_len, device=device, **dcfg)
+        vsd = _state_dict(vae_path, weights.vae_decoder_param_shapes(dcfg), "state_dict")
+        vsd = {(k[len("autoencoder."):] if k.startswith("autoencoder.") else k): v for k, v in vsd.items()}  # stable_vae/__init__.py:25-31
+        dec.load_state_dict(vsd)
+        self.autoencoder = Autoencoder(dec)
+        self.encode_text = self._make_text_encoder(text_encoder, p, device)
+
+    def generate_audio(self, text, length=10, guidance_scale=5, guidance_rescale=0.75, ddim_steps=100, eta=1, random_seed=None,
+                       randomize_seed=False):
+        """api/ezaudio.py:101-130.  Returns (sr, float32 waveform); a list of prompts returns (sr, [waveforms])."""
+        batched = not isinstance(text, str)
+        prompts = list(text) if batched else [text]
+        length = length * self.params["autoencoder"]["latent_sr"]
+        if all(t == "" for t in prompts):
+            guidance_scale = None
+            print("empyt input")
+        if randomize_seed:
+            random_seed = random.randint(0, MAX_SEED)
+        embeds = self._text_embeds(prompts, [""])
+        pred = inference(self.autoencoder, self.unet, None, None, None, None, self.params, self.noise_scheduler, prompts, None,
+                         int(length), guidance_scale, guidance_rescale, ddim_steps, eta, random_seed, self.device, text_embeds=embeds)
+        pred = pred.cpu().numpy()
+        sr = self.params["autoencoder"]["sr"]
+        if batched:
+            return sr, [pred[i, 0] for i in range(pred.shape[0])]
+        return sr, pred.squeeze(0).squeeze(0)
+
+    def editing_audio(self, text, boundary, gt_file, mask_start, mask_length, guidance_scale=3.5, guidance_rescale=0, ddim_steps=100,
+                      eta=1, random_seed=None, randomize_seed=False):
+        """api/ezaudio.py:132-207 (crop -> VAE encode -> masked sampling -> paste -> decode -> splice)."""
+        sr = self.params["autoencoder"]["sr"]
+        if text == "":
+            guidance_scale = None
+            print("empyt input")
+        mask_end = mask_start + mask_length
+        gt = _load_audio(gt_file, sr)
+        gt = gt / (np.max(np.abs(gt)) + 1e-9)
+        audio_length = len(gt) / sr
+        mask_start = min(mask_start, audio_length)
+        if mask_end > audio_length:  # outpainting
+            gt = np.pad(gt, (0, round((mask_end - audio_length) * sr)), "constant")
+            audio_length = len(gt) / sr
+        output_audio = gt.copy()
+        gt_t = torch.tensor(gt).unsqueeze(0).unsqueeze(1).to(self.device)
+        boundary = min((mask_end - mask_start) / 2, boundary)
+        start_idx = max(mask_start - boundary, 0)
+        end_idx = min(mask_end + boundary, audio_length)
+        mask_start -= start_idx
+        mask_end -= start_idx
+        gt_t = gt_t[:, :, round(start_idx * sr):round(end_idx * sr)]
+        gt_latent = self.autoencoder(audio=gt_t)  # VAE encode: next SURVEY 8(f) row -- raises until built
+        B, D, L = gt_latent.shape
+        gt_mask = torch.zeros(B, D, L, device=self.device)
+        latent_sr = self.params["autoencoder"]["latent_sr"]
+        gt_mask[:, :, round(mask_start * latent_sr):round(mask_end * latent_sr)] = 1
+        gt_mask = gt_mask.bool()
+        if randomize_seed:
+            random_seed = random.randint(0, MAX_SEED)
+        embeds = self._text_embeds([text], [""])
+        pred = inference(self.autoencoder, self.unet, gt_latent, gt_mask, None, None, self.params, self.noise_scheduler, [text], None, L,
+                         guidance_scale, guidance_rescale, ddim_steps, eta, random_seed, self.device, text_embeds=embeds)
+        pred = pred.cpu().numpy().squeeze(0).squeeze(0)
+        pred = pred[:round((end_idx - start_idx) * sr)]
+        output_audio[round(start_idx * sr):round(end_idx * sr)] = pred
+        return sr, output_audio
+
+
+def energy_condition(audio: torch.Tensor, hop_size=240, window_size=1920, padding="reflect", min_db=-60, norm=True, **unused):
+    """EnergyExtractor + Conditioner (src/models/conditions/energy.py:19-56, condition_wrapper.py:26-42): (B,T) -> (B,1,T/hop)."""
+    import torch.nn.functional as F
+    n_frames = int(audio.size(-1) // hop_size)
+    pad = (window_size - hop_size) // 2
+    sq = F.pad(audio[:, None, :], (pad, pad), mode=padding)[:, 0] ** 2
+    energy = F.unfold(sq[:, None, None, :], (1, window_size), stride=hop_size)[:, :, :n_frames].mean(dim=1)
+    gain_db = 10 * torch.log10(torch.clamp(energy, min=float(np.power(10, min_db / 10))))
+    if norm:
+        mx = gain_db.max(dim=-1, keepdim=True)[0]
+        gain_db = (gain_db - min_db) / (mx - min_db + 1e-8)
+    return gain_db.unsqueeze(1).contiguous()
+
+
+class EzAudio_ControlNet(_Base):
+    """api/controlnet.py:31."""
+
+    def __init__(self, model_name, ckpt_path=None, controlnet_path=None, vae_path=None, device="cuda", *,
+                 text_encoder: Optional[Callable] = None, precision: str = "bf16", max_batch: int = 4, config_path=None,
+                 vae_config_path=None, params: Optional[dict] = None):
+        self.device = device
+        self.params = params if params is not None else config.load_params(model_name, config_path, config.BUILTIN_CONTROLNET)
+        p = self.params
+        max_len = 10 * p["autoencoder"]["latent_sr"]  # the reference ControlNet API is hard-wired to 10 s (api/controlnet.py:131-138)
+        self.noise_scheduler = DDIMScheduler(**p["diff"])
+        kw = dict(precision=precision, max_batch=2 * max_batch, max_len=max_len, max_ctx_len=p["text_encoder"]["max_length"], max_timesteps=1000,
+                  device=device)
+        self.unet = MaskDiT(**kw, **p["model"])
+        sd = _state_dict(ckpt_path, weights.dit_param_shapes(p["model"]), "model")
+        self.unet.load_state_dict(sd)
+        self.controlnet = DiTControlNet(**kw, **p["model"], **p["controlnet"])
+        csd = _state_dict(controlnet_path, weights.controlnet_param_shapes(p["model"], p["controlnet"]), "model")
+        self.controlnet.load_state_dict(csd, mask_embed=sd["mask_embed"])
+        dcfg = config.load_vae_decoder_config(vae_config_path)
+        dec = OobleckDecoder(precision=precision, max_batch=max_batch, max_latent_len=max_len, device=device, **dcfg)
+        vsd = _state_dict(vae_path, weights.vae_decoder_param_shapes(dcfg), "state_dict")
+        vsd = {(k[len("autoencoder."):] if k.startswith("autoencoder.") else k): v for k, v in vsd.items()}
+        dec.load_state_dict(vsd)
+        self.autoencoder = Autoencoder(dec)
+        if p["conditioner"]["condition_type"] != "energy":
+            raise NotImplementedError("only the shipped energy conditioner")
+        self.encode_text = self._make_text_encoder(text_encoder, p, device)
+
+    def generate_audio(self, text, audio_path, surpass_noise=0, guidance_scale=3.5, guidance_rescale=0, ddim_steps=50, eta=1,
+                       conditioning_scale=1, random_seed=None, randomize_seed=False):
+        """api/controlnet.py:113-161.  `audio_path` may also be a float32 numpy waveform at the model sample rate."""
+        sr = self.params["autoencoder"]["sr"]
+        gt = _load_audio(audio_path, sr) if isinstance(audio_path, str) else np.asarray(audio_path, dtype=np.float32)
+        gt = gt / (np.max(np.abs(gt)) + 1e-9)
+        if surpass_noise > 0:
+            gt[np.abs(gt) <= surpass_noise] = 0
+        original_length = len(gt)
+        num_samples = int(10 * sr)
+        audio_frames = round(num_samples / sr * self.params["autoencoder"]["latent_sr"])
+        gt = np.pad(gt, (0, num_samples - len(gt)), "constant") if len(gt) < num_samples else gt[:num_samples]
+        gt_audio = torch.tensor(gt).unsqueeze(0).to(self.device)
+        # the reference encodes gt_audio only to read its latent SHAPE (api/controlnet.py:141-142): (1, 128, audio_frames)
+        cond_kw = {k: v for k, v in self.params["conditioner"].items() if k != "condition_type"}
+        condition = energy_condition(gt_audio, **cond_kw)
+        if randomize_seed:
+            random_seed = random.randint(0, MAX_SEED)
+        batched = not isinstance(text, str)
+        prompts = list(text) if batched else [text]
+        condition = condition.expand(len(prompts), -1, -1)
+        embeds = self._text_embeds(prompts, [""])
+        pred = inference(self.autoencoder, self.unet, None, None, None, None, self.params, self.noise_scheduler, prompts, None, audio_frames,
+                         guidance_scale, guidance_rescale, ddim_steps, eta, random_seed, self.device, text_embeds=embeds,
+                         controlnet=self.controlnet, condition=condition, conditioning_scale=conditioning_scale)
+        pred = pred.cpu().numpy()
+        if batched:
+            return sr, [pred[i, 0][:original_length] for i in range(pred.shape[0])]
+        return sr, pred.squeeze(0).squeeze(0)[:original_length]

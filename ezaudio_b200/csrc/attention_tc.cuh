@@ -234,11 +234,13 @@ inline int attention_tc(Device& dev, cudaStream_t st, const __nv_bfloat16* q, co
     const int smem = AttnSmem<1>::total(dvp);
     static bool set = false;
     if (!set) { EZB_CUDA(cudaFuncSetAttribute(attn_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem<1>::total(80))); set = true; }
+    ++launch_counter();
     attn_tc_kernel<1><<<grid, AT_THREADS, smem, st>>>(*tq, *tk, *tv, p);
   } else {
     const int smem = AttnSmem<2>::total(dvp);
     static bool set = false;
     if (!set) { EZB_CUDA(cudaFuncSetAttribute(attn_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem<2>::total(80))); set = true; }
+    ++launch_counter();
     attn_tc_kernel<2><<<grid, AT_THREADS, smem, st>>>(*tq, *tk, *tv, p);
   }
   EZB_CUDA(cudaGetLastError());

@@ -105,6 +105,7 @@ struct Dit {
     if (shape.empty()) shape = {N, K};
     reg(key, shape, [=](const float* src, cudaStream_t st) -> int {
       const size_t n = (size_t)N * Kpad;
+      ++launch_counter();
       pack_weight_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, N, K, dst, Kpad, km, row_off, geglu_inner, GEGLU_BN / 2);
       EZB_CUDA(cudaGetLastError());
       return EZB_OK;
@@ -191,6 +192,7 @@ struct Dit {
         float* dst = w.b_mlp1;
         const int in_ = inner;
         reg(p + ".mlp.net.0.proj.bias", {2 * inner}, [dst, in_](const float* src, cudaStream_t st) -> int {
+          ++launch_counter();
           pack_geglu_bias_kernel<<<(2 * in_ + 255) / 256, 256, 0, st>>>(src, dst, in_, GEGLU_BN / 2);
           EZB_CUDA(cudaGetLastError());
           return EZB_OK;
@@ -225,6 +227,7 @@ struct Dit {
         const int c = C;
         reg("model.final_block.final_layer.weight", {C, C, 3}, [dst, c](const float* src, cudaStream_t st) -> int {
           // [co][ci][k] -> [k][ci][co]
+          ++launch_counter();
           permute3_kernel<<<(3 * c * c + 255) / 256, 256, 0, st>>>(src, dst, 3, c, c, 1, 3, 3 * c);
           EZB_CUDA(cudaGetLastError());
           return EZB_OK;
@@ -315,6 +318,7 @@ struct Dit {
     LnParams p;
     p.x = x; p.x2 = x2; p.x3 = x3; p.D1 = D1; p.D2 = D2; p.w = w; p.b = b; p.shift = shift; p.scale = scale; p.mod_bstride = mod_bstride;
     p.rows_per_batch = rows_per_batch; p.out = out; p.kmul = kmul; p.M = M;
+    ++launch_counter();
     ln_mod_cast_kernel<<<(M + 7) / 8, 256, 0, st>>>(p);
     EZB_CUDA(cudaGetLastError());
     return EZB_OK;
@@ -329,6 +333,7 @@ struct Dit {
   }
   int small_lin(cudaStream_t st, const float* in, int ld_in, const float* W, const float* bias, const float* add, int ld_add, float* out, int ld_out, int R,
                 int N, int K, int act, float scale) {
+    ++launch_counter();
     small_linear_kernel<<<(N + 7) / 8, 256, 0, st>>>(in, ld_in, W, bias, add, ld_add, out, ld_out, R, N, K, act, scale);
     EZB_CUDA(cudaGetLastError());
     return EZB_OK;
@@ -345,9 +350,11 @@ struct Dit {
     };
     if (kmul == 3) {
       QkPrepParams<float> p; p.in = reinterpret_cast<const float*>(qkv); fill(p);
+      ++launch_counter();
       qk_prep_kernel<float><<<(total + 7) / 8, 256, 0, st>>>(p);
     } else {
       QkPrepParams<bf16> p; p.in = reinterpret_cast<const bf16*>(qkv); fill(p);
+      ++launch_counter();
       qk_prep_kernel<bf16><<<(total + 7) / 8, 256, 0, st>>>(p);
     }
     EZB_CUDA(cudaGetLastError());
@@ -368,6 +375,7 @@ struct Dit {
       static bool set = false;
       if (!set) { EZB_CUDA(cudaFuncSetAttribute(attn_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); set = true; }
       dim3 grid((Lq + SA_WARPS * SA_QW - 1) / (SA_WARPS * SA_QW), B * H);
+      ++launch_counter();
       attn_simt_kernel<<<grid, SA_WARPS * 32, smem, st>>>(q32_, k32_, v32_, mask, attn_out, H, Lq, Lk, dh, scale, kmul);
       EZB_CUDA(cudaGetLastError());
       return EZB_OK;
@@ -409,6 +417,7 @@ struct Dit {
     for (int i = 0; i < n; ++i) tf[i] = (float)ts[i];
     EZB_CUDA(cudaMemcpyAsync(t_vals, tf.data(), n * sizeof(float), cudaMemcpyHostToDevice, st));
     EZB_CUDA(cudaStreamSynchronize(st));  // tf is a stack-owned staging buffer
+    ++launch_counter();
     timestep_embed_kernel<<<(n * 128 + 255) / 256, 256, 0, st>>>(t_vals, t_emb, n);
     EZB_TRY(small_lin(st, t_emb, 256, te_w0, te_b0, nullptr, 0, t_h, D, n, D, 256, 1, 1.f));
     EZB_TRY(small_lin(st, t_h, D, te_w2, te_b2, nullptr, 0, t_tok, D, n, D, D, 1, 1.f));  // time_act SiLU folded (udit.py:313)
@@ -419,6 +428,7 @@ struct Dit {
       BlockW& w = blk[i];
       EZB_TRY(small_lin(st, t_tok, D, w.lora_a, nullptr, nullptr, 0, t_lora, 6 * r, n, 6 * r, D, 0, 1.f));
       EZB_TRY(small_lin(st, t_lora, 6 * r, w.lora_b, nullptr, t_ada, 6 * D, mod + (size_t)i * 6 * D, ldm, n, 6 * D, 6 * r, 0, d.ada_scaling));
+      ++launch_counter();
       add_rowvec_kernel<<<(unsigned)(((size_t)n * 6 * D + 255) / 256), 256, 0, st>>>(mod + (size_t)i * 6 * D, ldm, w.table, n, 6 * D);
     }
     EZB_CUDA(cudaGetLastError());
@@ -509,6 +519,7 @@ struct Dit {
   int embed(cudaStream_t st, const float* x, const float* gt, const uint8_t* gt_mask, const float* resid, int Be, int L) {
     dim3 grid((L + 31) / 32, (2 * C) / 32, Be), blockd(32, 8);
     if ((2 * C) % 32) return fail(EZB_ERR_UNSUPPORTED, "latent_chans must be a multiple of 16");
+    ++launch_counter();
     patch_pack_kernel<<<grid, blockd, 0, st>>>(x, gt, gt_mask, mask_embed, a_patch, Be, C, L, Kp, kmul);
     EZB_CUDA(cudaGetLastError());
     EpiLinearParams e = epi();
@@ -551,6 +562,7 @@ struct Dit {
     EZB_TRY(lin(st, act, D, w_final, M, C, e));
     dim3 grid((L + 31) / 32, Be);
     const size_t smem = (size_t)34 * C * sizeof(float);
+    ++launch_counter();
     final_conv_kernel<<<grid, 128, smem, st>>>(ybuf, fc_w, fc_b, out, Be, C, L);
     EZB_CUDA(cudaGetLastError());
     return EZB_OK;
@@ -576,6 +588,7 @@ inline int Dit::controlnet_forward(const float* x, const float* gt, const uint8_
   auto conv = [&](const float* in, const float* w, const float* b, float* out, int Cin, int cin_real, int Tin, int Cout, int Tout, int K, int stride, int pad,
                   int act, int tr) -> int {
     const size_t n = (size_t)Be * Cout * Tout;
+    ++launch_counter();
     conv1d_direct_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, w, b, out, Be, Cin, cin_real, Tin, Cout, Tout, K, stride, pad, act, tr);
     EZB_CUDA(cudaGetLastError());
     return EZB_OK;

@@ -109,6 +109,7 @@ EZB_API int ezb_cfg_ddim_step(const float* model_out, float* latents, const floa
   if (!model_out || !latents || !coef || B < 1) return fail(EZB_ERR_ARG, "ezb_cfg_ddim_step: bad argument");
   const int n = C * L;
   const float* uncond = gs != 0.f ? model_out + (size_t)B * n : nullptr;
+  ++launch_counter();
   cfg_ddim_kernel<<<B, 1024, 0, ST(stream)>>>(model_out, uncond, latents, coef[4] != 0.f ? noise : nullptr, n, gs, gr, coef[0], coef[1], coef[2],
                                               coef[3], coef[4]);
   EZB_CUDA(cudaGetLastError());
@@ -148,6 +149,7 @@ EZB_API int ezb_test_attention(int device, const void* q, const void* k, const v
   if (impl == 0) {
     EZB_CUDA(cudaFuncSetAttribute(attn_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     dim3 grid((Lq + SA_WARPS * SA_QW - 1) / (SA_WARPS * SA_QW), B * H);
+    ++launch_counter();
     attn_simt_kernel<<<grid, SA_WARPS * 32, attn_simt_smem(dh), ST(stream)>>>(reinterpret_cast<const float*>(q), reinterpret_cast<const float*>(k),
                                                                             reinterpret_cast<const float*>(v), key_mask,
                                                                             reinterpret_cast<__nv_bfloat16*>(out), H, Lq, Lk, dh, scale, 1);
@@ -157,6 +159,32 @@ EZB_API int ezb_test_attention(int device, const void* q, const void* k, const v
   const int dhp = (dh + 63) / 64 * 64, dvp = (dh + 15) / 16 * 16, lkpad = (Lk + 7) / 8 * 8;
   return attention_tc(device_ctx(device), ST(stream), reinterpret_cast<const __nv_bfloat16*>(q), reinterpret_cast<const __nv_bfloat16*>(k),
                       reinterpret_cast<const __nv_bfloat16*>(v), key_mask, reinterpret_cast<__nv_bfloat16*>(out), B, H, Lq, Lk, lkpad, dh, dhp, dvp, scale);
+}
+
+
+// ---- accounting / profiling hooks (bench.py)
+EZB_API unsigned long long ezb_launch_count(void) { return launch_counter(); }
+EZB_API int ezb_prof_gemm_begin(void) {
+  GemmProf& gp = gemm_prof();
+  gp.on = true; gp.used = 0; gp.flops.clear();
+  return EZB_OK;
+}
+// Synchronises the device; returns the number of GEMM launches recorded since begin, their total algorithmic FLOPs and the
+// sum of their CUDA-event durations (ms).
+EZB_API int ezb_prof_gemm_end(int* launches, double* flops, double* ms) {
+  GemmProf& gp = gemm_prof();
+  gp.on = false;
+  EZB_CUDA(cudaDeviceSynchronize());
+  double f = 0, t = 0;
+  for (size_t i = 0; i < gp.flops.size(); ++i) {
+    float m = 0.f;
+    EZB_CUDA(cudaEventElapsedTime(&m, gp.ev[2 * i], gp.ev[2 * i + 1]));
+    f += gp.flops[i]; t += m;
+  }
+  if (launches) *launches = (int)gp.flops.size();
+  if (flops) *flops = f;
+  if (ms) *ms = t;
+  return EZB_OK;
 }
 
 }  // extern "C"

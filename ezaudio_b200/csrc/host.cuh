@@ -10,12 +10,29 @@
 #include <map>
 #include <string>
 #include <tuple>
+#include <vector>
 
 #include "../../include/ezb200.h"
 #include "gemm.cuh"
 
 namespace ezb {
 
+
+// launch accounting (bench.py's gpu_launches) and optional per-GEMM CUDA-event timing (bench.py's roofline leg)
+inline unsigned long long& launch_counter() {
+  static unsigned long long n = 0;
+  return n;
+}
+struct GemmProf {
+  bool on = false;
+  std::vector<cudaEvent_t> ev;   // pairs
+  std::vector<double> flops;
+  size_t used = 0;
+};
+inline GemmProf& gemm_prof() {
+  static GemmProf p;
+  return p;
+}
 
 inline std::string& last_error() {
   static thread_local std::string e;
@@ -136,7 +153,20 @@ int launch_gemm_t(Device& dev, cudaStream_t st, const CUtensorMap* tA, const CUt
   }
   const int tiles = g.num_m_tiles * g.num_n_tiles;
   const int grid = tiles < dev.num_sms ? tiles : dev.num_sms;
+  GemmProf& gp = gemm_prof();
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (gp.on) {
+    if (gp.used + 2 > gp.ev.size()) {
+      for (int i = 0; i < 2; ++i) { cudaEvent_t e; EZB_CUDA(cudaEventCreate(&e)); gp.ev.push_back(e); }
+    }
+    e0 = gp.ev[gp.used]; e1 = gp.ev[gp.used + 1];
+    gp.used += 2;
+    gp.flops.push_back(2.0 * (double)g.M * (double)g.N * (double)g.num_k_blocks * GEMM_BK);
+    EZB_CUDA(cudaEventRecord(e0, st));
+  }
+  ++launch_counter();
   kern<<<grid, GEMM_THREADS, smem, st>>>(*tA, *tB, g, ep);
+  if (gp.on) EZB_CUDA(cudaEventRecord(e1, st));
   EZB_CUDA(cudaGetLastError());
   return EZB_OK;
 }

@@ -202,11 +202,13 @@ struct Vae {
     EZB_TRY(need(k + ".weight_v", {cout, cin, K}, &v));
     if (bias) EZB_TRY(need(k + ".bias", {cout}, &b));
     EZB_TRY(alloc(&norms, (size_t)cout));
+    ++launch_counter();
     wn_norm_kernel<<<cout, 256, 0, st>>>(v, cin * K, norms);
     c->cin = cin; c->cout = cout; c->N = cout; c->taps = K; c->center = (K - 1) / 2; c->dil = dil; c->bias = b;
     c->cin_pad = (kmul * cin + 63) / 64 * 64;
     EZB_TRY(alloc(&c->w, (size_t)cout * K * c->cin_pad));
     const size_t n = (size_t)cout * K * cin;
+    ++launch_counter();
     pack_conv_w_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(v, g, norms, c->w, cout, cin, K, c->cin_pad, kmul);
     EZB_CUDA(cudaGetLastError());
     return EZB_OK;
@@ -217,11 +219,13 @@ struct Vae {
     EZB_TRY(need(k + ".weight_v", {cin, cout, 2 * s}, &v));
     EZB_TRY(need(k + ".bias", {cout}, &b));
     EZB_TRY(alloc(&norms, (size_t)cin));
+    ++launch_counter();
     wn_norm_kernel<<<cin, 256, 0, st>>>(v, cout * 2 * s, norms);
     c->cin = cin; c->cout = cout; c->N = s * cout; c->taps = 3; c->center = 1; c->dil = 1; c->bias = b; c->stride = s;
     c->cin_pad = (kmul * cin + 63) / 64 * 64;
     EZB_TRY(alloc(&c->w, (size_t)c->N * 3 * c->cin_pad));
     const size_t n = (size_t)c->N * 3 * cin;
+    ++launch_counter();
     pack_convT_w_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(v, g, norms, c->w, cin, cout, s, (s + 1) / 2, c->cin_pad, kmul);
     EZB_CUDA(cudaGetLastError());
     return EZB_OK;
@@ -230,6 +234,7 @@ struct Vae {
     float *al, *be;
     EZB_TRY(need(k + ".alpha", {C}, &al)); EZB_TRY(need(k + ".beta", {C}, &be));
     EZB_TRY(alloc(&s->a, (size_t)C)); EZB_TRY(alloc(&s->binv, (size_t)C));
+    ++launch_counter();
     snake_prep_kernel<<<(C + 255) / 256, 256, 0, st>>>(al, be, s->a, s->binv, C);
     EZB_CUDA(cudaGetLastError());
     return EZB_OK;
@@ -258,7 +263,9 @@ struct Vae {
       const std::string k = p + std::to_string(nst + 2);
       EZB_TRY(need(k + ".weight_g", {1, 1, 1}, &g)); EZB_TRY(need(k + ".weight_v", {1, C0, 7}, &v));
       EZB_TRY(alloc(&norms, (size_t)1)); EZB_TRY(alloc(&out_w, (size_t)7 * C0));
+      ++launch_counter();
       wn_norm_kernel<<<1, 256, 0, st>>>(v, C0 * 7, norms);
+      ++launch_counter();
       fold_wave_w_kernel<<<(7 * C0 + 255) / 256, 256, 0, st>>>(v, g, norms, out_w, C0);
       EZB_CUDA(cudaGetLastError());
     }
@@ -293,6 +300,7 @@ struct Vae {
     if (!finalized) return fail(EZB_ERR_STATE, "VAE weights not finalized");
     if (B < 1 || B > d.max_batch || L < 1 || L > d.max_latent_len) return fail(EZB_ERR_SHAPE, "vae_decode: B %d L %d exceed workspace", B, L);
     dim3 grid((L + 31) / 32, (d.latent_dim + 31) / 32, B), blk(32, 8);
+    ++launch_counter();
     latent_pack_kernel<<<grid, blk, 0, st>>>(z, actA, d.latent_dim, L, kmul);
     EZB_CUDA(cudaGetLastError());
     __nv_bfloat16 *cur = actA, *oth = actB;
@@ -316,6 +324,7 @@ struct Vae {
     static bool set = false;
     if (!set) { EZB_CUDA(cudaFuncSetAttribute(wave_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); set = true; }
     dim3 g2((T + 63) / 64, B);
+    ++launch_counter();
     wave_out_kernel<<<g2, 128, smem, st>>>(cur, out_w, wav, C0, T, kmul);
     EZB_CUDA(cudaGetLastError());
     return EZB_OK;

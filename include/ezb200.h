@@ -112,6 +112,11 @@ int ezb_test_gemm(int device, const void* A_bf16, int lda, const void* W_bf16, i
 int ezb_test_attention(int device, const void* q, const void* k, const void* vt, const uint8_t* key_mask, void* out_bf16,
                        int B, int H, int Lq, int Lk, int dh, int impl, void* stream);
 
+/* accounting: kernels launched by this library so far (process-wide); per-GEMM CUDA-event timing for bench.py's roofline leg */
+unsigned long long ezb_launch_count(void);
+int ezb_prof_gemm_begin(void);
+int ezb_prof_gemm_end(int* launches, double* flops, double* ms);
+
 #ifdef __cplusplus
 }
 #endif
