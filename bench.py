@@ -1,0 +1,260 @@
+#!/usr/bin/env python
+"""Benchmark of the EzAudio hot path (BASELINE.json metric: audio-seconds generated per wall-second, EzAudio-XL,
+50 DDIM steps, 10-s prompts).
+
+  python bench.py --gpus N --steps K --warmup W           -> our arm (CUDA library), one JSON line from rank 0
+  python bench.py --impl reference --gpus N --steps K ... -> the reference algorithm's CPU path (oracle port), same JSON
+
+A "step" is one full pass of the hot path over one batch: 4 prompts per GPU x 10 s, 50 DDIM steps with classifier-free
+guidance (effective batch 8; API defaults guidance 5 / rescale 0.75 / eta 1, api/ezaudio.py:102) + VAE decode.
+`value` times the loop with inputs resident in HBM; `e2e` times the public API call (`EzAudio.generate_audio`) with
+host-resident cached T5 embeddings (pinned) copied in and the waveforms copied back out every step.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+PROMPTS_PER_GPU = 4
+SECONDS, STEPS_DDIM, LC = 10, 50, 100
+GF_DIT_XL_L500 = 786.7e9    # algorithmic FLOPs of one XL DiT forward per sample (L=500, Lc=100)
+GF_VAE_10S = 499.4e9        # VAE decode per 10-s clip
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(burst=d["bf16_tflops"], sustained=d["bf16_tflops_sustained"], hbm=d["hbm_gbs"], src="measured (MEASURED_PEAKS.json)")
+    return dict(burst=1590.0, sustained=1400.0, hbm=6650.0, src="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    def __init__(self, idx):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(idx), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return None
+        self.p.terminate()
+        try:
+            out = self.p.communicate(timeout=5)[0]
+        except Exception:
+            return None
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx = max(mx, float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return None
+        busy = [x for x in sm if x > 0.5 * max(sm)] or sm
+        return dict(sm_mhz=statistics.median(busy), sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+
+
+def cpu_reference_leg(threads=None, verbose=False):
+    """The reference algorithm's own CPU path (oracle port: torch fp32, all host threads) on a bounded sample of the same
+    workload: one XL DiT forward at effective batch 2 (one prompt with CFG) and one VAE decode of 2 s, extrapolated to a
+    10-s / 50-step clip (per-step cost does not depend on t)."""
+    from ezaudio_b200 import synth, weights
+    from oracle import ezaudio_oracle as O
+    cores = threads or os.cpu_count()
+    torch.set_num_threads(cores)
+    cfg = synth.model_cfg("xl")
+    sd = weights.synthetic_state_dict(weights.dit_param_shapes(cfg), 2)
+    vsd = weights.synthetic_state_dict(weights.vae_decoder_param_shapes(synth.VAE_DECODER), 6)
+    x = synth.synth_latents(2, 500)
+    ctx, mask = synth.synth_context(2, LC, cfg["context_dim"])
+    t = torch.tensor(479)
+    with torch.no_grad():
+        O.maskdit_forward(sd, cfg, x[:1], t, ctx[:1], mask[:1])  # warm-up
+        t0 = time.perf_counter()
+        O.maskdit_forward(sd, cfg, x, t, ctx, mask)
+        t_fwd = time.perf_counter() - t0
+        z = synth.synth_latents(1, 100, 128, seed=31)
+        t0 = time.perf_counter()
+        O.vae_decode(vsd, z)
+        t_vae = (time.perf_counter() - t0) * (SECONDS * 50 / 100)
+    total = STEPS_DDIM * t_fwd + t_vae
+    return dict(value=SECONDS / total, unit="audio-s/s", cores=cores, kind="port",
+                sample=f"1 XL DiT forward (B_eff=2, L=500) = {t_fwd:.2f}s x{STEPS_DDIM} + VAE decode 2 s x5 = {t_vae:.2f}s; oracle port (torch fp32 CPU)",
+                t_fwd_s=t_fwd, t_vae_10s_s=t_vae)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cfg", action="store_true")
+    a = ap.parse_args()
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    config = dict(workload=f"C2/C3: EzAudio-XL, {STEPS_DDIM}-step DDIM, {SECONDS} s, {PROMPTS_PER_GPU} prompts/GPU, "
+                           f"{'no CFG' if a.no_cfg else 'CFG 5.0 / rescale 0.75 (effective batch 8)'}, eta 1, cached T5 embeddings, + VAE decode",
+                  prompts_per_gpu=PROMPTS_PER_GPU, global_prompts=PROMPTS_PER_GPU * max(world, a.gpus), parallelism=f"prompt-sharded dp{max(world, a.gpus)}",
+                  weights="synthetic random-init (seed 2), all zero-init tensors re-drawn", cache="weights 1.75 GB bf16 streamed per DiT step >> 126 MB L2 (no flush needed)")
+    base = dict(metric="audio-seconds generated per wall-second (EzAudio-XL, 50-step DDIM, 10 s)", unit="audio-s/s", n_gpus=max(world, a.gpus),
+                steps=a.steps, warmup=a.warmup, higher_is_better=True, scaling="weak", vs_baseline=None, data="synthetic", config=config)
+
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        cb = cpu_reference_leg()
+        audio_s = SECONDS
+        line = dict(base, impl="reference", value=cb["value"], ms_per_step=1e3 * audio_s / cb["value"], dtype="f32", cpu_baseline=cb,
+                    e2e=dict(value=cb["value"], unit="audio-s/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0, n_gpus=max(world, a.gpus))
+        print(json.dumps(line))
+        return
+
+    from ezaudio_b200 import _lib, api, synth, weights
+    from ezaudio_b200.inference import sample_latents
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    B = PROMPTS_PER_GPU
+    # public API object (reference-facing): synthetic checkpoint + cached-T5 stand-in returning PINNED HOST tensors
+    enc = api.SyntheticTextEncoder(2048, LC)
+
+    def host_encoder(prompts):
+        e, m = enc(prompts)
+        return e.pin_memory(), m.pin_memory()
+
+    ez = api.EzAudio("s3_xl", ckpt_path="synthetic:2", vae_path="synthetic:6", device=dev, text_encoder=host_encoder, precision=a.precision, max_batch=B,
+                     max_length_s=SECONDS)
+    prompts = [f"synthetic prompt number {rank * B + i} with a dog barking and rain" for i in range(B)]
+    gs, gr = (None, 0.0) if a.no_cfg else (5, 0.75)
+    L = SECONDS * 50
+    te, tm = enc(prompts)
+    ue, um = enc([""])
+    te, tm, ue, um = te.to(dev), tm.to(dev), ue.to(dev), um.to(dev)
+
+    def step_resident():
+        lat = sample_latents(ez.unet, ez.noise_scheduler, te, tm, ue, um, None, None, L, gs, gr, STEPS_DDIM, 1, 2024 + rank * B, device=dev)
+        return ez.autoencoder(embedding=lat)
+
+    def step_e2e():
+        if a.no_cfg:
+            embeds = ez._text_embeds(prompts, [""])
+            from ezaudio_b200.inference import inference
+            return inference(ez.autoencoder, ez.unet, None, None, None, None, ez.params, ez.noise_scheduler, prompts, None, L, None, 0.0, STEPS_DDIM, 1,
+                             2024, dev, text_embeds=embeds).cpu().numpy()
+        return ez.generate_audio(prompts, length=SECONDS, guidance_scale=5, guidance_rescale=0.75, ddim_steps=STEPS_DDIM, eta=1, random_seed=2024)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(a.warmup):
+        step_resident()
+    sync_all()
+    Lb = _lib.lib()
+    n0 = Lb.ezb_launch_count()
+    clocks = ClockSampler(local)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        wav = step_resident()
+    e1.record()
+    sync_all()
+    ms = e0.elapsed_time(e1)
+    clk = clocks.stop()
+    launches = int(Lb.ezb_launch_count() - n0)
+    assert torch.isfinite(wav).all()
+    # ---- end to end through the public API (host buffers in / out)
+    step_e2e()
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        step_e2e()
+    sync_all()
+    ms_e2e = (time.perf_counter() - t0) * 1e3
+    if dist is not None:
+        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+    n_e = 1 if a.no_cfg else 2
+    h2d = (B + 1) * LC * 2048 * 4 + (B + 1) * LC
+    d2h = B * L * 480 * 4
+    # ---- dominant kernel (tcgen05 GEMM): CUDA-event timed per launch over one instrumented generation on rank 0
+    roof = None
+    pk = peaks()
+    if rank == 0:
+        _lib.check(Lb.ezb_prof_gemm_begin())
+        step_resident()
+        nl, fl, tms = C.c_int(), C.c_double(), C.c_double()
+        _lib.check(Lb.ezb_prof_gemm_end(C.byref(nl), C.byref(fl), C.byref(tms)))
+        ach = fl.value / (tms.value * 1e-3) / 1e12
+        roof = dict(bound="tensor", kernel="gemm_tcgen05_kernel", achieved=ach, peak=pk["sustained"], unit="TFLOP/s", frac=ach / pk["sustained"],
+                    peak_source=pk["src"] + ", sustained figure (kernel timed inside a long step)", traffic=None,
+                    launches=nl.value, flops_per_launch=fl.value / max(1, nl.value), ms_per_launch=tms.value / max(1, nl.value),
+                    gemm_share_of_step=tms.value / (ms / a.steps),
+                    how="CUDA events around every GEMM launch on the launch stream during one extra instrumented generation")
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    total_audio = SECONDS * B * max(world, 1)
+    value = total_audio * a.steps / (ms * 1e-3)
+    job_flops = (STEPS_DDIM * n_e * B * GF_DIT_XL_L500 + B * GF_VAE_10S) * max(world, 1)
+    line = dict(base, impl="ours", value=value, ms_per_step=ms / a.steps, dtype=a.precision,
+                dit_step_ms=None, clocks=clk, gpu_launches=launches,
+                e2e=dict(value=total_audio * a.steps / (ms_e2e * 1e-3), unit="audio-s/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
+                         api="EzAudio.generate_audio(list[str]) with pinned host T5 embeddings; waveform .cpu().numpy()"),
+                roofline=roof,
+                job_tensor_roofline_frac=job_flops * a.steps / (ms * 1e-3) / 1e12 / (pk["sustained"] * max(world, 1)),
+                job_algorithmic_tflop_per_step=job_flops / 1e12)
+    # DiT-step ms: one denoiser forward (+CFG/DDIM update) inside the loop
+    ez.unet.set_context(torch.cat([te, ue.expand(B, -1, -1)], 0) if not a.no_cfg else te, torch.cat([tm, um.expand(B, -1)], 0) if not a.no_cfg else tm)
+    ez.unet.set_timesteps([int(t) for t in ez.noise_scheduler.timesteps])
+    xin = torch.randn(B * n_e, 128, L, device=dev)
+    for _ in range(3):
+        ez.unet.forward_step(xin, 0)
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(10):
+        ez.unet.forward_step(xin, i)
+    e1.record()
+    torch.cuda.synchronize()
+    line["dit_step_ms"] = e0.elapsed_time(e1) / 10
+    if not a.no_cpu_baseline and world == 1:
+        line["cpu_baseline"] = cpu_reference_leg()
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

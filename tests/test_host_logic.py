@@ -1,0 +1,122 @@
+"""CPU-only checks: C-ABI exports, scheduler restatement, weight wire format, prompt sharding (gloo, world_size 2)."""
+import ctypes
+import os
+import re
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "ezb200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(ezb_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_builds_loads_and_exports_every_declared_symbol():
+    from ezaudio_b200 import _lib, build
+    build.build()
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    names = _header_functions()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/ezb200.h but not exported"
+    assert set(_lib.EXPORTS) <= set(names)
+    assert _lib.lib().ezb_version() >= 1
+
+
+def test_no_cpu_fallback_without_library(monkeypatch):
+    from ezaudio_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libezb200.so")
+    with pytest.raises(_lib.EzbError):
+        _lib.lib()
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "ezaudio_b200")
+    for f in os.listdir(pkg):
+        if f.endswith(".py"):
+            assert not re.search(r"^\s*(from|import)\s+oracle", open(os.path.join(pkg, f)).read(), flags=re.M), f
+
+
+def test_scheduler_matches_oracle_restatement_and_invariants():
+    from ezaudio_b200.scheduler import DDIMScheduler
+    from oracle import ezaudio_oracle as O
+    s, o = DDIMScheduler(), O.DDIM()
+    assert torch.equal(s.alphas_cumprod, o.alphas_cumprod)
+    assert float(s.alphas_cumprod[-1]) == 0.0
+    for n in (50, 100):
+        s.set_timesteps(n)
+        assert s.timesteps.tolist() == list(range(999, 0, -1000 // n))
+        o.set_timesteps(n)
+        x = torch.randn(2, 8, 5, generator=torch.Generator().manual_seed(n))
+        v = torch.randn(2, 8, 5, generator=torch.Generator().manual_seed(n + 1))
+        z = torch.randn(2, 8, 5, generator=torch.Generator().manual_seed(n + 2))
+        for t in s.timesteps.tolist()[:: max(1, n // 10)]:
+            for eta in (0.0, 1.0):
+                c = s.step_coefficients(t, eta)
+                x0, eps = c[0] * x - c[1] * v, c[0] * v + c[1] * x
+                mine = c[2] * x0 + c[3] * eps + c[4] * z
+                assert torch.allclose(mine, o.step(v, t, x, eta, z), atol=2e-6)
+
+
+def test_weight_wire_format_matches_live_reference():
+    from oracle import refimport
+    ref = refimport.import_reference()
+    if ref is None:
+        pytest.skip("reference tree not present")
+    import contextlib
+    import copy
+    import io
+    from ezaudio_b200 import synth, weights
+    for cfg in (synth.model_cfg("xl"), synth.model_cfg("l")):
+        with torch.device("meta"), contextlib.redirect_stdout(io.StringIO()):
+            m = ref.MaskDiT(**copy.deepcopy(cfg))
+        assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == dict(weights.dit_param_shapes(cfg))
+    cfg = synth.model_cfg("l")
+    with torch.device("meta"), contextlib.redirect_stdout(io.StringIO()):
+        c = ref.DiTControlNet(**copy.deepcopy(cfg), **copy.deepcopy(synth.CONTROLNET))
+    assert {k: tuple(v.shape) for k, v in c.state_dict().items()} == dict(weights.controlnet_param_shapes(cfg, synth.CONTROLNET))
+
+
+def test_shard_range_covers_everything_once():
+    from ezaudio_b200.shard import shard_range
+    for n in (0, 1, 4, 7, 32, 33):
+        for w in (1, 2, 3, 8):
+            spans = [shard_range(n, w, r) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+            assert max(b - a for a, b in spans) - min(b - a for a, b in spans) <= 1
+
+
+def _gloo_worker(rank, world, port, n_total, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from ezaudio_b200.shard import gather_waveforms, shard_prompts, shard_range
+    prompts = [f"p{i}" for i in range(n_total)]
+    mine = shard_prompts(prompts, world, rank)
+    a, b = shard_range(n_total, world, rank)
+    local = torch.stack([torch.full((6,), float(i)) for i in range(a, b)]) if b > a else torch.zeros(0, 6)
+    full = gather_waveforms(local, n_total, dist)
+    q.put((rank, mine, full[:, 0].tolist()))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_total", [4, 5])
+def test_prompt_sharding_two_ranks_gloo(n_total):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000 + n_total
+    ps = [ctx.Process(target=_gloo_worker, args=(r, 2, port, n_total, q)) for r in range(2)]
+    [p.start() for p in ps]
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    [p.join(timeout=60) for p in ps]
+    assert res[0][1] + res[1][1] == [f"p{i}" for i in range(n_total)]
+    for _, _, col in res:
+        assert col == [float(i) for i in range(n_total)]
