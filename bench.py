@@ -82,7 +82,25 @@ def cpu_reference_leg(threads=None, verbose=False):
     10-s / 50-step clip (per-step cost does not depend on t)."""
     from ezaudio_b200 import synth, weights
     from oracle import ezaudio_oracle as O
-    cores = threads or os.cpu_count()
+    avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
+    if threads is None:
+        # "all the host threads it can use": pick the fastest of a few thread counts on a GEMM probe (oversubscribing a
+        # cgroup-limited box makes torch CPU slower, not faster)
+        a_ = torch.randn(2048, 1152)
+        b_ = torch.randn(1152, 4608)
+        best, threads = None, avail
+        for n in sorted({8, 16, 32, 64, avail}):
+            if n > avail:
+                continue
+            torch.set_num_threads(n)
+            a_ @ b_
+            t0 = time.perf_counter()
+            for _ in range(3):
+                a_ @ b_
+            dt = time.perf_counter() - t0
+            if best is None or dt < best:
+                best, threads = dt, n
+    cores = threads
     torch.set_num_threads(cores)
     cfg = synth.model_cfg("xl")
     sd = weights.synthetic_state_dict(weights.dit_param_shapes(cfg), 2)
