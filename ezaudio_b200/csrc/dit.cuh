@@ -34,7 +34,6 @@ struct WeightSpec {
   bool loaded = false;
 };
 
-constexpr int GEGLU_BN = 128;
 constexpr int KP_PATCH_ALIGN = 8;
 
 struct Dit {
@@ -66,6 +65,10 @@ struct Dit {
   float *t_vals = nullptr, *t_emb = nullptr, *t_h = nullptr, *t_tok = nullptr, *t_ada = nullptr, *t_lora = nullptr, *mod = nullptr, *mod_final = nullptr,
         *mod_b = nullptr, *modf_b = nullptr;
   int n_timesteps = 0, ctx_Be = 0, ctx_Lc = 0, ctx_Lpad = 0;
+  float2* rope_cs = nullptr;
+  bool fused_heads = false;
+  bool pair = true;       // CTA-pair (cta_group::2) GEMMs
+  int geglu_bn = 128;     // N-tile of the GEGLU GEMM: packing group = geglu_bn / 2
 
   ~Dit() {
     for (void* p : allocs) cudaFree(p);
@@ -101,12 +104,12 @@ struct Dit {
   }
   // fp32 [N, K] -> rows [row_off, row_off+N) of bf16 dst [Ntot, kmul*Kpad]
   void reg_linear(const std::string& key, int N, int K, bf16* dst, int Kpad, int row_off, int geglu_inner = 0, std::vector<int64_t> shape = {}) {
-    const int km = kmul;
+    const int km = kmul, gh = geglu_bn / 2;
     if (shape.empty()) shape = {N, K};
     reg(key, shape, [=](const float* src, cudaStream_t st) -> int {
       const size_t n = (size_t)N * Kpad;
       ++launch_counter();
-      pack_weight_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, N, K, dst, Kpad, km, row_off, geglu_inner, GEGLU_BN / 2);
+      pack_weight_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, N, K, dst, Kpad, km, row_off, geglu_inner, gh);
       EZB_CUDA(cudaGetLastError());
       return EZB_OK;
     });
@@ -123,7 +126,9 @@ struct Dit {
     nblk = d.is_controlnet ? half : d.depth + 1;
     kmul = d.precision == 1 ? 3 : 1;
     if (d.precision != 0 && d.precision != 1) return fail(EZB_ERR_UNSUPPORTED, "precision %d", d.precision);
-    if (dh > 96 || dh % 8 || D % 16 || inner % (GEGLU_BN / 2) || d.context_dim % 8 || d.depth % 2)
+    pair = opt_pair_gemm() != 0;
+    geglu_bn = (pair && inner % 128 == 0) ? 256 : 128;
+    if (dh > 96 || dh % 8 || D % 16 || inner % 64 || d.context_dim % 8 || d.depth % 2)
       return fail(EZB_ERR_UNSUPPORTED, "unsupported dims: D %d dh %d inner %d ctx %d depth %d", D, dh, inner, d.context_dim, d.depth);
     if (d.max_batch < 1 || d.max_batch > 256 || d.max_len < 1 || d.max_ctx_len < 1 || d.max_timesteps < 1) return fail(EZB_ERR_ARG, "workspace bounds");
     Kp = (2 * C + 1 + KP_PATCH_ALIGN - 1) / KP_PATCH_ALIGN * KP_PATCH_ALIGN;
@@ -190,10 +195,10 @@ struct Dit {
       EZB_TRY(alloc(&w.b_mlp1, (size_t)2 * inner));
       {
         float* dst = w.b_mlp1;
-        const int in_ = inner;
-        reg(p + ".mlp.net.0.proj.bias", {2 * inner}, [dst, in_](const float* src, cudaStream_t st) -> int {
+        const int in_ = inner, gh = geglu_bn / 2;
+        reg(p + ".mlp.net.0.proj.bias", {2 * inner}, [dst, in_, gh](const float* src, cudaStream_t st) -> int {
           ++launch_counter();
-          pack_geglu_bias_kernel<<<(2 * in_ + 255) / 256, 256, 0, st>>>(src, dst, in_, GEGLU_BN / 2);
+          pack_geglu_bias_kernel<<<(2 * in_ + 255) / 256, 256, 0, st>>>(src, dst, in_, gh);
           EZB_CUDA(cudaGetLastError());
           return EZB_OK;
         });
@@ -265,6 +270,8 @@ struct Dit {
       EZB_TRY(alloc(&q16, Mx * H * DHP)); EZB_TRY(alloc(&k16, Mx * H * DHP));
       EZB_TRY(alloc(&vt16, (size_t)d.max_batch * H * DVP * Lp));
     }
+    EZB_TRY(alloc(&rope_cs, (size_t)d.max_len * (dh / 2)));
+    fused_heads = use_tc_attention && (dh == 64 || dh == 72) && (H % 2 == 0);
     EZB_TRY(alloc(&ctx_emb, Mc * D));
     EZB_TRY(alloc(&ctx_mask, Mc));
     const size_t Lcp = ((size_t)d.max_ctx_len + 7) / 8 * 8;
@@ -308,6 +315,13 @@ struct Dit {
   int finalize() {
     for (auto& kv : specs)
       if (!kv.second.loaded) return fail(EZB_ERR_WEIGHT, "missing state-dict key '%s'", kv.first.c_str());
+    {
+      const int n = d.max_len * (dh / 2);
+      ++launch_counter();
+      rope_table_kernel<<<(n + 255) / 256, 256>>>(blk[0].inv_freq, rope_cs, d.max_len, dh / 2);
+      EZB_CUDA(cudaGetLastError());
+      EZB_CUDA(cudaDeviceSynchronize());
+    }
     finalized = true;
     return EZB_OK;
   }
@@ -329,6 +343,7 @@ struct Dit {
     return e;
   }
   int lin(cudaStream_t st, const bf16* A, int K, const bf16* W, int M, int N, const EpiLinearParams& e) {
+    if (pair) return gemm2<128, EpiLinear<128>>(*dev, st, A, kmul * K, W, kmul * K, M, N, kmul * K, e);
     return gemm<128, EpiLinear<128>>(*dev, st, A, kmul * K, W, kmul * K, M, N, kmul * K, e);
   }
   int small_lin(cudaStream_t st, const float* in, int ld_in, const float* W, const float* bias, const float* add, int ld_add, float* out, int ld_out, int R,
@@ -359,6 +374,24 @@ struct Dit {
     }
     EZB_CUDA(cudaGetLastError());
     return EZB_OK;
+  }
+  // Q/K/V projection with the fused per-head LN + RoPE + attention-layout epilogue (fast mode)
+  int lin_heads(cudaStream_t st, const bf16* A, const bf16* W, int M, int N, const int* kinds, const float* nqw_, const float* nqb_, const float* nkw_,
+                const float* nkb_, bool rope, int L, bf16* qo, bf16* ko, bf16* vto, int Lpad) {
+    EpiHeadsParams e;
+    memset(&e, 0, sizeof e);
+    e.D = D; e.H = H; e.L = L;
+    for (int i = 0; i < 3; ++i) e.kind[i] = i < N / D ? kinds[i] : 0;
+    e.nw[0] = nqw_; e.nb[0] = nqb_; e.nw[1] = nkw_; e.nb[1] = nkb_;
+    e.rope = rope ? rope_cs : nullptr; e.rope_kinds = 3;
+    e.out[0] = qo; e.out[1] = ko; e.out[2] = vto;
+    e.ld_qk = DHP; e.dvp = DVP; e.Lpad = Lpad;
+    if (pair) {
+      if (dh == 72) return gemm2<144, EpiHeads<72>>(*dev, st, A, D, W, D, M, N, D, e);
+      return gemm2<128, EpiHeads<64>>(*dev, st, A, D, W, D, M, N, D, e);
+    }
+    if (dh == 72) return gemm<144, EpiHeads<72>>(*dev, st, A, D, W, D, M, N, D, e);
+    return gemm<128, EpiHeads<64>>(*dev, st, A, D, W, D, M, N, D, e);
   }
   // GEMM whose output feeds qk_prep: bf16 [M,N] in fast mode, fp32 in parity mode
   int lin_to_qkv(cudaStream_t st, const bf16* A, int K, const bf16* W, int M, int N) {
@@ -400,8 +433,12 @@ struct Dit {
     for (int i = 0; i < nblk; ++i) {
       BlockW& w = blk[i];
       EZB_TRY(ln(st, ctx_emb, D, nullptr, nullptr, 0, w.ncw, w.ncb, nullptr, nullptr, 0, 1, act, Mc));
-      EZB_TRY(lin_to_qkv(st, act, D, w.ckv, Mc, 2 * D));
       const int off[2] = {0, D}, kinds[2] = {1, 2};
+      if (fused_heads) {
+        EZB_TRY(lin_heads(st, act, w.ckv, Mc, 2 * D, kinds, nullptr, nullptr, w.cnkw, w.cnkb, false, Lc, nullptr, w.kc16, w.vtc16, ctx_Lpad));
+        continue;
+      }
+      EZB_TRY(lin_to_qkv(st, act, D, w.ckv, Mc, 2 * D));
       float* f32o[2] = {w.kc32, w.vc32};
       bf16* bfo[2] = {w.kc16, w.vtc16};
       if (use_tc_attention) EZB_CUDA(cudaMemsetAsync(w.vtc16, 0, (size_t)Be * H * DVP * ctx_Lpad * sizeof(bf16), st));
@@ -474,8 +511,13 @@ struct Dit {
     }
     // --- self-attention (blocks.py:137-141)
     EZB_TRY(ln(st, x_in, D, nullptr, nullptr, 0, w.n1w, w.n1b, m + 0 * D, m + 1 * D, mbs, L, act, M));
-    EZB_TRY(lin_to_qkv(st, act, D, w.qkv, M, 3 * D));
-    {
+    if (fused_heads) {
+      const int kinds[3] = {0, 1, 2};
+      const int Lp = (L + 7) / 8 * 8;
+      EZB_TRY(lin_heads(st, act, w.qkv, M, 3 * D, kinds, w.nqw, w.nqb, w.nkw, w.nkb, true, L, q16, k16, vt16, Lp));
+      EZB_TRY(attention(st, q32, k32, v32, q16, k16, vt16, nullptr, Be, L, L, Lp));
+    } else {
+      EZB_TRY(lin_to_qkv(st, act, D, w.qkv, M, 3 * D));
       const int off[3] = {0, D, 2 * D}, kinds[3] = {0, 1, 2};
       float* f32o[3] = {q32, k32, v32};
       bf16* bfo[3] = {q16, k16, vt16};
@@ -490,8 +532,12 @@ struct Dit {
     }
     // --- cross-attention (blocks.py:147-151): no modulation, no gate
     EZB_TRY(ln(st, x_out, D, nullptr, nullptr, 0, w.n2w, w.n2b, nullptr, nullptr, 0, L, act, M));
-    EZB_TRY(lin_to_qkv(st, act, D, w.cq, M, D));
-    {
+    if (fused_heads) {
+      const int kinds[1] = {0};
+      EZB_TRY(lin_heads(st, act, w.cq, M, D, kinds, w.cnqw, w.cnqb, nullptr, nullptr, false, L, q16, nullptr, nullptr, 0));
+      EZB_TRY(attention(st, q32, w.kc32, w.vc32, q16, w.kc16, w.vtc16, ctx_mask, Be, L, ctx_Lc, ctx_Lpad));
+    } else {
+      EZB_TRY(lin_to_qkv(st, act, D, w.cq, M, D));
       const int off[1] = {0}, kinds[1] = {0};
       float* f32o[1] = {q32};
       bf16* bfo[1] = {q16};
@@ -508,7 +554,8 @@ struct Dit {
     {
       EpiGegluParams g;
       g.bias = w.b_mlp1; g.out_bf16 = mid; g.ld16 = kmul * inner; g.split_stride = kmul == 3 ? inner : 0;
-      EZB_TRY((gemm<GEGLU_BN, EpiGeglu<GEGLU_BN>>(*dev, st, act, kmul * D, w.mlp1, kmul * D, M, 2 * inner, kmul * D, g)));
+      if (geglu_bn == 256) EZB_TRY((gemm2<256, EpiGeglu<256>>(*dev, st, act, kmul * D, w.mlp1, kmul * D, M, 2 * inner, kmul * D, g)));
+      else EZB_TRY((gemm<128, EpiGeglu<128>>(*dev, st, act, kmul * D, w.mlp1, kmul * D, M, 2 * inner, kmul * D, g)));
       EpiLinearParams e = epi();
       e.bias = w.b_mlp2; e.resid = x_out; e.ldr = D; e.gate = m + 5 * D; e.gate_bstride = mbs; e.rows_per_batch = L; e.out_f32 = x_out; e.ld32 = D;
       EZB_TRY(lin(st, mid, inner, w.mlp2, M, D, e));

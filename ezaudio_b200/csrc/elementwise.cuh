@@ -287,6 +287,15 @@ __global__ void __launch_bounds__(256) small_linear_kernel(const float* __restri
   }
 }
 
+// RoPE table (rotary.py:48-70): cs[l][i] = (cos, sin)(l * inv_freq[i]), fp32, i < dh/2
+__global__ void rope_table_kernel(const float* __restrict__ inv_freq, float2* __restrict__ cs, int L, int half) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= L * half) return;
+  const int l = i / half, f = i - l * half;
+  float s, c;
+  sincosf((float)l * inv_freq[f], &s, &c);
+  cs[i] = make_float2(c, s);
+}
 // timestep_embedding (modules.py:19-39): [cos(t f_i) | sin(t f_i)], f_i = exp(-ln(1e4) i / 128), dim 256
 __global__ void timestep_embed_kernel(const float* __restrict__ t, float* __restrict__ out, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;

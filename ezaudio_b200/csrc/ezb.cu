@@ -46,6 +46,19 @@ __attribute__((visibility("default"))) int ezb_test_gemm(int device, const void*
   ConvAddr conv;
   conv.taps = conv_taps; conv.center = conv_center; conv.dilation = conv_dil; conv.cin_pad = conv_cin_pad; conv.T = conv_T; conv.B = conv_B;
   const ConvAddr* cp = conv_taps > 0 ? &conv : nullptr;
+  if (epi_kind == 10 || epi_kind == 11) {  // CTA-pair kernel (bn is the pair tile's N)
+    if (cp) return fail(EZB_ERR_UNSUPPORTED, "pair GEMM has no conv addressing");
+    if (epi_kind == 10) {
+      EpiLinearParams p = to_epi(e);
+      if (bn == 128) return gemm2<128, EpiLinear<128>>(dev, st, a, lda, w, ldw, M, N, K, p);
+      if (bn == 256) return gemm2<256, EpiLinear<256>>(dev, st, a, lda, w, ldw, M, N, K, p);
+    } else {
+      EpiGegluParams p;
+      p.bias = e->bias; p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(e->out_bf16); p.ld16 = e->ld16; p.split_stride = e->split_stride;
+      if (bn == 256) return gemm2<256, EpiGeglu<256>>(dev, st, a, lda, w, ldw, M, N, K, p);
+    }
+    return fail(EZB_ERR_UNSUPPORTED, "ezb_test_gemm pair: bn=%d", bn);
+  }
   if (epi_kind == 0) {
     EpiLinearParams p = to_epi(e);
     if (bn == 64) return gemm<64, EpiLinear<64>>(dev, st, a, lda, w, ldw, M, N, K, p, cp);
@@ -162,6 +175,11 @@ EZB_API int ezb_test_attention(int device, const void* q, const void* k, const v
 }
 
 
+// runtime switches (A/B testing): "pair_gemm" 0/1 -- read when a handle is created
+EZB_API int ezb_set_option(const char* name, int value) {
+  if (name && !strcmp(name, "pair_gemm")) { opt_pair_gemm() = value; return EZB_OK; }
+  return fail(EZB_ERR_ARG, "unknown option");
+}
 // ---- accounting / profiling hooks (bench.py)
 EZB_API unsigned long long ezb_launch_count(void) { return launch_counter(); }
 EZB_API int ezb_prof_gemm_begin(void) {

@@ -54,73 +54,100 @@ struct EpiLinearParams {
   int phase_ld16;
 };
 
-__device__ __forceinline__ void store_bf16x4(__nv_bfloat16* p, int split_stride, float a, float b, float c, float d) {
-  uint2 hi = make_uint2(pack_bf16(a, b), pack_bf16(c, d));
-  *reinterpret_cast<uint2*>(p) = hi;
+// ---------------------------------------------------------------------------------------------------------------
+// Epilogue staging: a warp reads its 32 accumulator rows from TMEM (thread == row), transposes 64-column chunks through
+// a private 8 KB smem tile (XOR-swizzled 8-byte granules: conflict-free both ways) and then works with lane == column
+// pair, so every global access is a fully coalesced 128/256-byte row segment.
+constexpr int EPI_STAGE_FLOATS = 32 * 64;
+
+__device__ __forceinline__ void stage_put(float* st, int r, int g, float a, float b) {
+  *reinterpret_cast<float2*>(st + r * 64 + 2 * (g ^ r)) = make_float2(a, b);
+}
+__device__ __forceinline__ float2 stage_get(const float* st, int rr, int lane) {
+  return *reinterpret_cast<const float2*>(st + rr * 64 + 2 * (lane ^ rr));
+}
+__device__ __forceinline__ void store_bf16x2(__nv_bfloat16* p, int split_stride, float a, float b) {
+  const uint32_t hi = pack_bf16(a, b);
+  *reinterpret_cast<uint32_t*>(p) = hi;
   if (split_stride > 0) {
-    const __nv_bfloat162 h0 = *reinterpret_cast<__nv_bfloat162*>(&hi.x), h1 = *reinterpret_cast<__nv_bfloat162*>(&hi.y);
-    uint2 lo = make_uint2(pack_bf16(a - __low2float(h0), b - __high2float(h0)), pack_bf16(c - __low2float(h1), d - __high2float(h1)));
-    *reinterpret_cast<uint2*>(p + split_stride) = lo;
-    *reinterpret_cast<uint2*>(p + 2 * split_stride) = hi;
+    const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&hi);
+    *reinterpret_cast<uint32_t*>(p + split_stride) = pack_bf16(a - __low2float(h), b - __high2float(h));
+    *reinterpret_cast<uint32_t*>(p + 2 * split_stride) = hi;
   }
 }
 
 template <int BN>
 struct EpiLinear {
   using Params = EpiLinearParams;
-  static __device__ __forceinline__ void run(const Params& ep, uint32_t taddr_row, int row, int M, int n0, int N) {
-    const bool row_ok = row < M;
-    const int b = (ep.gate != nullptr && row_ok) ? row / ep.rows_per_batch : 0;
+  // row0: global row of this warp's first accumulator row; nvalid: rows of the 32 that exist (<= 0: none)
+  static __device__ __forceinline__ void run(const Params& ep, float* st, uint32_t taddr_row, int row0, int nvalid, int n0, int N, int lane) {
 #pragma unroll 1
-    for (int c = 0; c < BN; c += 32) {
+    for (int c = 0; c < BN; c += 64) {
       if (n0 + c >= N) break;  // warp-uniform
-      uint32_t r[32];
+      uint32_t r[64];
       __syncwarp();
       tmem_ld_32x32(taddr_row + c, r);
+      tmem_ld_32x32(taddr_row + c + 32, r + 32);
       tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const int col = n0 + c + j;
-        if (col >= N || !row_ok) break;
-        float v[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) v[e] = __uint_as_float(r[j + e]);
-        if (ep.bias != nullptr) {
-#pragma unroll
-          for (int e = 0; e < 4; ++e) v[e] += ep.bias[ep.bias_mod > 0 ? (col + e) % ep.bias_mod : col + e];
+      for (int g = 0; g < 32; ++g) stage_put(st, lane, g, __uint_as_float(r[2 * g]), __uint_as_float(r[2 * g + 1]));
+      __syncwarp();
+      const int col = n0 + c + 2 * lane;
+      if (col < N) {
+        float b0 = 0.f, b1 = 0.f, sa0 = 0.f, sa1 = 0.f, sb0 = 0.f, sb1 = 0.f;
+        const int ch = ep.bias_mod > 0 ? col % ep.bias_mod : col;
+        if (ep.bias != nullptr) { b0 = ep.bias[ch]; b1 = ep.bias[ch + 1]; }
+        if (ep.act == ACT_SNAKE) { sa0 = ep.act_a[ch]; sa1 = ep.act_a[ch + 1]; sb0 = ep.act_b[ch]; sb1 = ep.act_b[ch + 1]; }
+        const float osc = ep.out_scale != 0.f ? ep.out_scale : 1.f;
+        const int c16 = ep.phase_cols > 0 ? (col / ep.phase_cols) * ep.phase_ld16 + col % ep.phase_cols : col;
+        // gate rows: the warp's 32 rows touch at most two batch items -> preload both gate vectors once per chunk
+        float2 g0 = make_float2(0.f, 0.f), g1 = g0;
+        int brow = 0x7fffffff;  // first row belonging to the second batch item
+        if (ep.gate != nullptr) {
+          const int b0i = row0 / ep.rows_per_batch;
+          brow = (b0i + 1) * ep.rows_per_batch;
+          g0 = *reinterpret_cast<const float2*>(ep.gate + (size_t)b0i * ep.gate_bstride + col);
+          if (brow < row0 + 32 && brow < row0 + nvalid) g1 = *reinterpret_cast<const float2*>(ep.gate + (size_t)(b0i + 1) * ep.gate_bstride + col);
+          g0.x = 1.0f - g0.x; g0.y = 1.0f - g0.y; g1.x = 1.0f - g1.x; g1.y = 1.0f - g1.y;
         }
-        if (ep.out_scale != 0.f) {
+        const int nv = nvalid < 32 ? nvalid : 32;
+#pragma unroll 1
+        for (int r0 = 0; r0 < nv; r0 += 8) {
+          float2 x[8];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) v[e] *= ep.out_scale;
-        }
-        if (ep.resid != nullptr) {
-          const float4 x = *reinterpret_cast<const float4*>(ep.resid + (size_t)row * ep.ldr + col);
-          if (ep.gate != nullptr) {
-            const float4 g = *reinterpret_cast<const float4*>(ep.gate + (size_t)b * ep.gate_bstride + col);
-            v[0] = x.x + (1.0f - g.x) * v[0];
-            v[1] = x.y + (1.0f - g.y) * v[1];
-            v[2] = x.z + (1.0f - g.z) * v[2];
-            v[3] = x.w + (1.0f - g.w) * v[3];
-          } else {
-            v[0] += x.x; v[1] += x.y; v[2] += x.z; v[3] += x.w;
+          for (int i = 0; i < 8; ++i) {
+            x[i] = make_float2(0.f, 0.f);
+            if (ep.resid != nullptr && r0 + i < nv) x[i] = *reinterpret_cast<const float2*>(ep.resid + (size_t)(row0 + r0 + i) * ep.ldr + col);
           }
-        }
-        if (ep.out_f32 != nullptr)
-          *reinterpret_cast<float4*>(ep.out_f32 + (size_t)row * ep.ld32 + col) = make_float4(v[0], v[1], v[2], v[3]);
-        if (ep.out_bf16 != nullptr) {
-          if (ep.act == ACT_SILU) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) v[e] = silu(v[e]);
-          } else if (ep.act == ACT_SNAKE) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int ch = ep.bias_mod > 0 ? (col + e) % ep.bias_mod : col + e;
-              const float s = sinf(v[e] * ep.act_a[ch]);
-              v[e] = v[e] + ep.act_b[ch] * s * s;
+          for (int i = 0; i < 8; ++i) {
+            const int rr = r0 + i, row = row0 + rr;
+            if (rr >= nv) break;
+            const float2 acc = stage_get(st, rr, lane);
+            float v0 = (acc.x + b0) * osc, v1 = (acc.y + b1) * osc;
+            if (ep.resid != nullptr) {
+              if (ep.gate != nullptr) {
+                const float2 g = row >= brow ? g1 : g0;
+                v0 = x[i].x + g.x * v0;
+                v1 = x[i].y + g.y * v1;
+              } else {
+                v0 += x[i].x;
+                v1 += x[i].y;
+              }
+            }
+            if (ep.out_f32 != nullptr) *reinterpret_cast<float2*>(ep.out_f32 + (size_t)row * ep.ld32 + col) = make_float2(v0, v1);
+            if (ep.out_bf16 != nullptr) {
+              if (ep.act == ACT_SILU) {
+                v0 = silu(v0);
+                v1 = silu(v1);
+              } else if (ep.act == ACT_SNAKE) {
+                const float s0 = sinf(v0 * sa0), s1 = sinf(v1 * sa1);
+                v0 = v0 + sb0 * s0 * s0;
+                v1 = v1 + sb1 * s1 * s1;
+              }
+              store_bf16x2(ep.out_bf16 + (size_t)row * ep.ld16 + c16, ep.split_stride, v0, v1);
             }
           }
-          const int c16 = ep.phase_cols > 0 ? (col / ep.phase_cols) * ep.phase_ld16 + col % ep.phase_cols : col;
-          store_bf16x4(ep.out_bf16 + (size_t)row * ep.ld16 + c16, ep.split_stride, v[0], v[1], v[2], v[3]);
         }
       }
     }
@@ -138,29 +165,60 @@ struct EpiGegluParams {
 template <int BN>
 struct EpiGeglu {
   using Params = EpiGegluParams;
-  static __device__ __forceinline__ void run(const Params& ep, uint32_t taddr_row, int row, int M, int n0, int N) {
+  static __device__ __forceinline__ void run(const Params& ep, float* st, uint32_t taddr_row, int row0, int nvalid, int n0, int N, int lane) {
     constexpr int HALF = BN / 2;
-    const bool row_ok = row < M;
 #pragma unroll 1
-    for (int c = 0; c < HALF; c += 16) {
+    for (int c = 0; c < HALF; c += 64) {  // 64 output features per pass, gated in the thread == row layout
       if (n0 + c >= N) break;
-      uint32_t h[16], g[16];
-      __syncwarp();
-      tmem_ld_32x16(taddr_row + c, h);
-      tmem_ld_32x16(taddr_row + HALF + c, g);
-      tmem_ld_wait();
-      __nv_bfloat16* o = ep.out_bf16 + (size_t)row * ep.ld16 + (n0 / 2 + c);
+      uint32_t pk[32];  // 64 bf16 results of this thread's row
 #pragma unroll
-      for (int j = 0; j < 16; j += 4) {
-        if (!row_ok) break;
-        float v[4];
+      for (int q4 = 0; q4 < 2; ++q4) {
+        uint32_t h[32], g[32];
+        __syncwarp();
+        tmem_ld_32x32(taddr_row + c + q4 * 32, h);
+        tmem_ld_32x32(taddr_row + HALF + c + q4 * 32, g);
+        tmem_ld_wait();
+        const float* bh = ep.bias + n0 + c + q4 * 32;
+        const float* bg = ep.bias + n0 + HALF + c + q4 * 32;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float hv = __uint_as_float(h[j + e]) + ep.bias[n0 + c + j + e];
-          const float gv = __uint_as_float(g[j + e]) + ep.bias[n0 + HALF + c + j + e];
-          v[e] = hv * gelu_erf(gv);
+        for (int j = 0; j < 32; j += 2) {
+          const float o0 = (__uint_as_float(h[j]) + __ldg(bh + j)) * gelu_erf(__uint_as_float(g[j]) + __ldg(bg + j));
+          const float o1 = (__uint_as_float(h[j + 1]) + __ldg(bh + j + 1)) * gelu_erf(__uint_as_float(g[j + 1]) + __ldg(bg + j + 1));
+          pk[q4 * 16 + j / 2] = pack_bf16(o0, o1);
         }
-        store_bf16x4(o + j, ep.split_stride, v[0], v[1], v[2], v[3]);
+      }
+      if (ep.split_stride > 0) {  // parity mode keeps full precision: fall back to per-thread row stores of [hi | lo | hi]
+        // (rare path; bf16x3 is the numerics mode, not the throughput mode)
+        __syncwarp();
+        uint32_t h[32], g[32];
+#pragma unroll 1
+        for (int q4 = 0; q4 < 2; ++q4) {
+          tmem_ld_32x32(taddr_row + c + q4 * 32, h);
+          tmem_ld_32x32(taddr_row + HALF + c + q4 * 32, g);
+          tmem_ld_wait();
+          if (lane < nvalid) {
+            __nv_bfloat16* o = ep.out_bf16 + (size_t)(row0 + lane) * ep.ld16 + (n0 / 2 + c + q4 * 32);
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              const float o0 = (__uint_as_float(h[j]) + ep.bias[n0 + c + q4 * 32 + j]) * gelu_erf(__uint_as_float(g[j]) + ep.bias[n0 + HALF + c + q4 * 32 + j]);
+              const float o1 = (__uint_as_float(h[j + 1]) + ep.bias[n0 + c + q4 * 32 + j + 1]) * gelu_erf(__uint_as_float(g[j + 1]) + ep.bias[n0 + HALF + c + q4 * 32 + j + 1]);
+              store_bf16x2(o + j, ep.split_stride, o0, o1);
+            }
+          }
+          __syncwarp();
+        }
+        continue;
+      }
+#pragma unroll
+      for (int gq = 0; gq < 16; ++gq) stage_put(st, lane, gq, __uint_as_float(pk[2 * gq]), __uint_as_float(pk[2 * gq + 1]));
+      __syncwarp();
+      // 16 lanes cover one 128-byte row segment (64 bf16): the two half-warps take alternate rows
+      const int hl = lane & 15, hw = lane >> 4;
+      __nv_bfloat16* obase = ep.out_bf16 + (size_t)row0 * ep.ld16 + (n0 / 2 + c + 4 * hl);
+#pragma unroll 4
+      for (int rp = 0; rp < 16; ++rp) {
+        const int rr = 2 * rp + hw;
+        if (rr < nvalid) *reinterpret_cast<float2*>(obase + (size_t)rr * ep.ld16) = stage_get(st, rr, hl);
       }
     }
   }
@@ -170,21 +228,23 @@ template <int BN, int STAGES>
 struct GemmSmem {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
   static constexpr int B_BYTES = BN * GEMM_BK * 2;
-  static constexpr int BYTES = 1024 /*align slack*/ + STAGES * (A_BYTES + B_BYTES) + (2 * STAGES + 4) * 8 + 16;
+  static constexpr int STAGE_BYTES = 4 * EPI_STAGE_FLOATS * 4;  // one 8 KB transpose tile per epilogue warp
+  static constexpr int BYTES = 1024 /*align slack*/ + STAGES * (A_BYTES + B_BYTES) + STAGE_BYTES + (2 * STAGES + 4) * 8 + 16;
 };
 
 template <int BN, int STAGES, class Epi>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmShape g,
                     const typename Epi::Params ep) {
-  static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN");
+  static_assert(BN % 16 == 0 && BN >= 64 && BN <= 256, "BN");
   using SM = GemmSmem<BN, STAGES>;
   constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * SM::A_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * SM::B_BYTES);
+  float* sStage = reinterpret_cast<float*>(sB + STAGES * SM::B_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * SM::B_BYTES + SM::STAGE_BYTES);
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
@@ -266,18 +326,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint32_t acc = 0, acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int mt = tile % g.num_m_tiles, nt = tile / g.num_m_tiles;
-      int row;
-      int m_limit = g.M;
+      int row0, nvalid;
       if (g.taps == 0) {
-        row = mt * GEMM_BM + lg * 32 + lane;
+        row0 = mt * GEMM_BM + lg * 32;
+        nvalid = g.M - row0;
       } else {  // rows are (batch, t): tiles never straddle clips
-        const int bidx = mt / g.tiles_per_batch, t = (mt - bidx * g.tiles_per_batch) * GEMM_BM + lg * 32 + lane;
-        row = (t < g.T) ? bidx * g.T + t : g.M;
+        const int bidx = mt / g.tiles_per_batch, t0 = (mt - bidx * g.tiles_per_batch) * GEMM_BM + lg * 32;
+        row0 = bidx * g.T + t0;
+        nvalid = g.T - t0;
       }
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr_row = tmem_base + acc * BN + (static_cast<uint32_t>(lg * 32) << 16);
-      Epi::run(ep, taddr_row, row, m_limit, nt * BN, g.N);
+      Epi::run(ep, sStage + (warp - 2) * EPI_STAGE_FLOATS, taddr_row, row0, nvalid, nt * BN, g.N, lane);
       tc_fence_before();
       mbar_arrive(&tempty[acc]);
       acc ^= 1;
@@ -287,6 +348,220 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+}  // namespace ezb
+
+namespace ezb {
+// ---------------------------------------------------------------------------------------------------------------
+// Fused "heads" epilogue for the Q/K/V projections (attention.py:127-129,137-144; rotary.py:6-18,72-84): an N-tile holds two
+// whole heads, a thread owns one token row, so the per-head LayerNorm(dh) and the rotate-half RoPE are in-thread.
+//   kind 0/1 (q/k): LN affine -> RoPE (optional) -> bf16 rows [b*H + h, l, 0..dh) (pitch ld_qk), written 144/128 B-coalesced
+//                   through the staging tile;
+//   kind 2   (v)  : bf16 V^T [b*H + h, d, l] (pitch Lpad): for a fixed d a warp stores 32 consecutive tokens (64 B).
+struct EpiHeadsParams {
+  int D, H, L;                 // model width, heads, tokens per batch item
+  int kind[3];                 // section (n / D) -> 0 q, 1 k, 2 v
+  const float* nw[2];          // LayerNorm(dh) weight for q, k
+  const float* nb[2];
+  const float2* rope;          // [L][dh/2] (cos, sin) or null
+  int rope_kinds;              // bit k set: apply RoPE to kind k
+  __nv_bfloat16* out[3];       // per kind: q rows, k rows, v^T
+  int ld_qk, dvp, Lpad;
+};
+
+template <int DH>
+struct EpiHeads {
+  using Params = EpiHeadsParams;
+  static constexpr int BN = 2 * DH;
+  static __device__ __forceinline__ void run(const Params& ep, float* st, uint32_t taddr_row, int row0, int nvalid, int n0, int N, int lane) {
+    const int row = row0 + lane;
+    const bool row_ok = lane < nvalid;
+    const int b = row_ok ? row / ep.L : 0, l = row_ok ? row - b * ep.L : 0;
+#pragma unroll 1
+    for (int hh = 0; hh < 2; ++hh) {
+      const int n = n0 + hh * DH;
+      if (n >= N) break;
+      const int sec = n / ep.D, kind = ep.kind[sec], head = (n - sec * ep.D) / DH;
+      uint32_t r[DH];
+      __syncwarp();
+      tmem_ld_32x64(taddr_row + hh * DH, r);
+      if constexpr (DH == 72) tmem_ld_32x8(taddr_row + hh * DH + 64, r + 64);
+      tmem_ld_wait();
+      float v[DH];
+#pragma unroll
+      for (int i = 0; i < DH; ++i) v[i] = __uint_as_float(r[i]);
+      const size_t bh = (size_t)b * ep.H + head;
+      if (kind < 2) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < DH; ++i) s += v[i];
+        const float mean = s * (1.0f / DH);
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < DH; ++i) q += (v[i] - mean) * (v[i] - mean);
+        const float rstd = rsqrtf(q * (1.0f / DH) + 1e-5f);
+        const float* w = ep.nw[kind];
+        const float* bb = ep.nb[kind];
+#pragma unroll
+        for (int i = 0; i < DH; ++i) v[i] = (v[i] - mean) * rstd * __ldg(w + i) + __ldg(bb + i);
+        if (ep.rope != nullptr && ((ep.rope_kinds >> kind) & 1)) {
+          const float2* cs = ep.rope + (size_t)l * (DH / 2);
+#pragma unroll
+          for (int i = 0; i < DH / 2; ++i) {
+            const float2 c = __ldg(cs + i);
+            const float a = v[i], bq = v[i + DH / 2];
+            v[i] = a * c.x - bq * c.y;
+            v[i + DH / 2] = bq * c.x + a * c.y;
+          }
+        }
+        // bf16 pairs -> staging granules (4 bf16 each) -> coalesced row stores
+#pragma unroll
+        for (int g = 0; g < DH / 4; ++g)
+          stage_put(st, lane, g, __uint_as_float(pack_bf16(v[4 * g], v[4 * g + 1])), __uint_as_float(pack_bf16(v[4 * g + 2], v[4 * g + 3])));
+        __syncwarp();
+        if (lane < DH / 4) {
+          for (int rr = 0; rr < nvalid && rr < 32; ++rr) {
+            const int rw = row0 + rr, rb = rw / ep.L, rl = rw - rb * ep.L;
+            const float2 pk = stage_get(st, rr, lane);
+            __nv_bfloat16* dst = ep.out[kind] + (((size_t)rb * ep.H + head) * ep.L + rl) * ep.ld_qk + 4 * lane;
+            *reinterpret_cast<float2*>(dst) = pk;
+          }
+        }
+      } else if (row_ok) {
+        __nv_bfloat16* dst = ep.out[2] + bh * ep.dvp * ep.Lpad + l;
+#pragma unroll
+        for (int i = 0; i < DH; ++i) dst[(size_t)i * ep.Lpad] = __float2bfloat16_rn(v[i]);
+        for (int i = DH; i < ep.dvp; ++i) dst[(size_t)i * ep.Lpad] = __float2bfloat16_rn(0.f);
+      }
+    }
+  }
+};
+
+}  // namespace ezb
+
+namespace ezb {
+// ---------------------------------------------------------------------------------------------------------------
+// CTA-pair GEMM (tcgen05 cta_group::2): a cluster of two CTAs on one TPC computes a 256 x BN tile.  CTA r stages its own
+// 128 rows of A and rows [r*BN/2, (r+1)*BN/2) of the W tile; the leader's single MMA thread issues M=256 instructions that
+// read both CTAs' shared memory, so each SM pulls half the operand bytes per flop through L2 (the 128x128 single-CTA tile
+// is L2->smem bound at ~64 flop/B).  Accumulator rows 128r..128r+127 live in CTA r's TMEM; both CTAs run the epilogue.
+template <int BN, int STAGES>
+struct Gemm2Smem {
+  static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
+  static constexpr int B_BYTES = (BN / 2) * GEMM_BK * 2;
+  static constexpr int STAGE_BYTES = 4 * EPI_STAGE_FLOATS * 4;
+  static constexpr int BYTES = 1024 + STAGES * (A_BYTES + B_BYTES) + STAGE_BYTES + (2 * STAGES + 4) * 8 + 16;
+};
+
+template <int BN, int STAGES, class Epi>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmShape g, const typename Epi::Params ep) {
+  static_assert(BN % 16 == 0 && BN >= 64 && BN <= 256, "BN");
+  using SM = Gemm2Smem<BN, STAGES>;
+  constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * SM::A_BYTES;
+  float* sStage = reinterpret_cast<float*>(sB + STAGES * SM::B_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * SM::B_BYTES + SM::STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const int num_tiles = g.num_m_tiles * g.num_n_tiles;  // num_m_tiles counts 256-row tiles here
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 256);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc_pair<TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------ TMA producer (both CTAs; bytes are credited to the leader's barrier)
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const int mt = tile % g.num_m_tiles, nt = tile / g.num_m_tiles;
+        const int m0 = mt * 2 * GEMM_BM + (int)rank * GEMM_BM, n0 = nt * BN + (int)rank * (BN / 2);
+        for (int kb = 0; kb < g.num_k_blocks; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          const uint32_t bar = mapa_u32(smem_u32(&full[stage]), 0);
+          if (leader) mbar_expect_tx(&full[stage], 2 * (SM::A_BYTES + SM::B_BYTES));
+          tma_load_2d_pair(sA + stage * SM::A_BYTES, &tmA, bar, kb * GEMM_BK, m0);
+          tma_load_2d_pair(sB + stage * SM::B_BYTES, &tmB, bar, kb * GEMM_BK, n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------ MMA issuer (leader CTA only)
+    if (leader) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * GEMM_BM, BN);
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < g.num_k_blocks; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint64_t ad = umma_desc_sw128(smem_u32(sA + stage * SM::A_BYTES));
+            const uint64_t bd = umma_desc_sw128(smem_u32(sB + stage * SM::B_BYTES));
+#pragma unroll
+            for (int k = 0; k < GEMM_BK / 16; ++k) umma_bf16_pair(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
+            umma_commit_pair(&empty[stage]);
+            if (kb == g.num_k_blocks - 1) umma_commit_pair(&tfull[acc]);
+          }
+          __syncwarp();
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ------------------------------------------------ epilogue (both CTAs, own 128 accumulator rows)
+    const int lg = warp & 3;
+    uint32_t acc = 0, acc_phase = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      const int mt = tile % g.num_m_tiles, nt = tile / g.num_m_tiles;
+      const int row0 = mt * 2 * GEMM_BM + (int)rank * GEMM_BM + lg * 32;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr_row = tmem_base + acc * BN + (static_cast<uint32_t>(lg * 32) << 16);
+      Epi::run(ep, sStage + (warp - 2) * EPI_STAGE_FLOATS, taddr_row, row0, g.M - row0, nt * BN, g.N, lane);
+      tc_fence_before();
+      mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[acc]), 0));
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc_pair<TMEM_COLS>(tmem_base);
 }
 
 }  // namespace ezb

@@ -23,6 +23,10 @@ inline unsigned long long& launch_counter() {
   static unsigned long long n = 0;
   return n;
 }
+inline int& opt_pair_gemm() {
+  static int v = 1;
+  return v;
+}
 struct GemmProf {
   bool on = false;
   std::vector<cudaEvent_t> ev;   // pairs
@@ -171,6 +175,58 @@ int launch_gemm_t(Device& dev, cudaStream_t st, const CUtensorMap* tA, const CUt
   return EZB_OK;
 }
 
+// CTA-pair GEMM launch: 256 x BN tiles, cluster (2,1,1), one pair per TPC.
+template <int BN, class Epi>
+int gemm2(Device& dev, cudaStream_t st, const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, int M, int N, int K,
+          const typename Epi::Params& ep) {
+  if (M <= 0 || N <= 0 || K <= 0) return fail(EZB_ERR_SHAPE, "gemm2: empty problem %d %d %d", M, N, K);
+  if ((K % 8) || (lda % 8) || (ldw % 8) || (N % 8)) return fail(EZB_ERR_SHAPE, "gemm2: K/ld/N must be multiples of 8 (M%d N%d K%d)", M, N, K);
+  constexpr int STAGES = (BN <= 128) ? 8 : (BN <= 192) ? 7 : 6;
+  GemmShape g;
+  memset(&g, 0, sizeof g);
+  g.M = M; g.N = N;
+  g.num_n_tiles = (N + BN - 1) / BN;
+  g.num_m_tiles = (M + 2 * GEMM_BM - 1) / (2 * GEMM_BM);
+  g.num_k_blocks = (K + GEMM_BK - 1) / GEMM_BK;
+  const CUtensorMap *tA, *tB;
+  EZB_TRY(dev.tmaps.get2d(A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, GEMM_BM, &tA));
+  EZB_TRY(dev.tmaps.get2d(W, (uint64_t)K, (uint64_t)N, (uint64_t)ldw, BN / 2, &tB));
+  auto kern = gemm2_tcgen05_kernel<BN, STAGES, Epi>;
+  constexpr int smem = Gemm2Smem<BN, STAGES>::BYTES;
+  static bool attr_set[16] = {};
+  if (!attr_set[dev.id & 15]) {
+    EZB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set[dev.id & 15] = true;
+  }
+  const int tiles = g.num_m_tiles * g.num_n_tiles, max_pairs = dev.num_sms / 2;
+  const int pairs = tiles < max_pairs ? tiles : max_pairs;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  GemmProf& gp = gemm_prof();
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (gp.on) {
+    if (gp.used + 2 > gp.ev.size()) {
+      for (int i = 0; i < 2; ++i) { cudaEvent_t e; EZB_CUDA(cudaEventCreate(&e)); gp.ev.push_back(e); }
+    }
+    e0 = gp.ev[gp.used]; e1 = gp.ev[gp.used + 1];
+    gp.used += 2;
+    gp.flops.push_back(2.0 * (double)M * (double)N * (double)g.num_k_blocks * GEMM_BK);
+    EZB_CUDA(cudaEventRecord(e0, st));
+  }
+  ++launch_counter();
+  EZB_CUDA(cudaLaunchKernelEx(&cfg, kern, *tA, *tB, g, ep));
+  if (gp.on) EZB_CUDA(cudaEventRecord(e1, st));
+  return EZB_OK;
+}
+
 // A: [M, K] bf16 row-major (lda), W: [N, K] bf16 row-major (ldw).  K, lda, ldw multiples of 8.
 template <int BN, class Epi>
 int gemm(Device& dev, cudaStream_t st, const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, int M, int N, int K,
@@ -201,7 +257,7 @@ int gemm(Device& dev, cudaStream_t st, const __nv_bfloat16* A, int lda, const __
     EZB_TRY(dev.tmaps.get2d(A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, GEMM_BM, &tA));
     EZB_TRY(dev.tmaps.get2d(W, (uint64_t)K, (uint64_t)N, (uint64_t)ldw, BN, &tB));
   }
-  constexpr int STAGES = (BN <= 128) ? 6 : 4;
+  constexpr int STAGES = (BN <= 64) ? 8 : (BN <= 128) ? 6 : (BN <= 144) ? 5 : 4;
   return launch_gemm_t<BN, STAGES, Epi>(dev, st, tA, tB, g, ep);
 }
 

@@ -112,6 +112,8 @@ int ezb_test_gemm(int device, const void* A_bf16, int lda, const void* W_bf16, i
 int ezb_test_attention(int device, const void* q, const void* k, const void* vt, const uint8_t* key_mask, void* out_bf16,
                        int B, int H, int Lq, int Lk, int dh, int impl, void* stream);
 
+/* runtime switch for A/B measurements: "pair_gemm" (1 = cta_group::2 256-row tiles, default; 0 = single-CTA 128x128) */
+int ezb_set_option(const char* name, int value);
 /* accounting: kernels launched by this library so far (process-wide); per-GEMM CUDA-event timing for bench.py's roofline leg */
 unsigned long long ezb_launch_count(void);
 int ezb_prof_gemm_begin(void);

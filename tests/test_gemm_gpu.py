@@ -113,3 +113,34 @@ def test_gemm_conv_addressing(Cin, Cout, taps, dil, T, B):
     assert (raw - ref).abs().max().item() < 3e-3
     sref = ref + binv * torch.sin(ref * a) ** 2
     assert (act.float() - sref).abs().max().item() < 3e-2
+
+
+@pytest.mark.parametrize("M,N,K,bn", [(4000, 1152, 1152, 128), (300, 144, 144, 128), (4000, 1152, 4608, 128), (1000, 3456, 1152, 256), (129, 256, 64, 256),
+                                      (777, 2304, 264, 128)])
+def test_pair_gemm_f32_out(M, N, K, bn):
+    """CTA-pair (tcgen05 cta_group::2) kernel, same oracle as the single-CTA one."""
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    W = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    out = torch.full((M, N), float("nan"), device="cuda")
+    _run(A, W, _epi(out_f32=out, ld32=N, bias=bias), M, N, K, bn, kind=10)
+    ref = A.float() @ W.float().t() + bias
+    err = (out - ref).abs().max().item()
+    assert err < 2e-3 * max(1.0, math.sqrt(K / 1024)), err
+
+
+def test_pair_gemm_geglu():
+    M, D, inner, bn = 900, 1152, 4608, 256
+    g = torch.Generator(device="cuda").manual_seed(3)
+    A = torch.randn(M, D, device="cuda", generator=g).bfloat16()
+    W = (torch.randn(2 * inner, D, device="cuda", generator=g) / math.sqrt(D)).bfloat16()
+    bias = torch.randn(2 * inner, device="cuda", generator=g) * 0.1
+    half = bn // 2
+    Wp = torch.stack([W[:inner].view(inner // half, half, D), W[inner:].view(inner // half, half, D)], 1).reshape(2 * inner, D).contiguous()
+    bp = torch.stack([bias[:inner].view(-1, half), bias[inner:].view(-1, half)], 1).reshape(-1).contiguous()
+    out = torch.zeros(M, inner, device="cuda", dtype=torch.bfloat16)
+    _run(A, Wp, _epi(bias=bp, out_bf16=out, ld16=inner), M, 2 * inner, D, bn, kind=11)
+    u = A.float() @ W.float().t() + bias
+    ref = u[:, :inner] * torch.nn.functional.gelu(u[:, inner:])
+    assert (out.float() - ref).abs().max().item() < 2e-2 * max(1.0, ref.abs().max().item() / 4)
