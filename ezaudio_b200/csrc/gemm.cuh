@@ -20,7 +20,7 @@ namespace ezb {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_SMEM_BUDGET = 227 * 1024 - 2048;  // dynamic smem per CTA minus alignment slack and barriers
 
 struct GemmShape {
   int M, N;
@@ -60,11 +60,13 @@ struct EpiLinearParams {
 // pair, so every global access is a fully coalesced 128/256-byte row segment.
 constexpr int EPI_STAGE_FLOATS = 32 * 64;
 
+template <int PITCH = 64>
 __device__ __forceinline__ void stage_put(float* st, int r, int g, float a, float b) {
-  *reinterpret_cast<float2*>(st + r * 64 + 2 * (g ^ r)) = make_float2(a, b);
+  *reinterpret_cast<float2*>(st + r * PITCH + 2 * (g ^ (r & (PITCH / 2 - 1)))) = make_float2(a, b);
 }
+template <int PITCH = 64>
 __device__ __forceinline__ float2 stage_get(const float* st, int rr, int lane) {
-  return *reinterpret_cast<const float2*>(st + rr * 64 + 2 * (lane ^ rr));
+  return *reinterpret_cast<const float2*>(st + rr * PITCH + 2 * (lane ^ (rr & (PITCH / 2 - 1))));
 }
 __device__ __forceinline__ void store_bf16x2(__nv_bfloat16* p, int split_stride, float a, float b) {
   const uint32_t hi = pack_bf16(a, b);
@@ -79,11 +81,44 @@ __device__ __forceinline__ void store_bf16x2(__nv_bfloat16* p, int split_stride,
 template <int BN>
 struct EpiLinear {
   using Params = EpiLinearParams;
-  // row0: global row of this warp's first accumulator row; nvalid: rows of the 32 that exist (<= 0: none)
-  static __device__ __forceinline__ void run(const Params& ep, float* st, uint32_t taddr_row, int row0, int nvalid, int n0, int N, int lane) {
+  static constexpr int EPI_WARPS = BN >= 128 ? 8 : 4;       // two warps per TMEM lane group split the tile's columns
+  static constexpr int STAGE_FLOATS = EPI_STAGE_FLOATS;
+  // row0: global row of this warp's first accumulator row; nvalid: rows of the 32 that exist (<= 0: none);
+  // [c_begin, c_end): this warp's column range inside the tile; wait(): blocks until the accumulator is complete.
+  template <class Wait>
+  static __device__ __forceinline__ void run(const Params& ep, float* st, uint32_t taddr_row, int row0, int nvalid, int n0, int N, int lane, int c_begin,
+                                             int c_end, Wait wait) {
+    const int nv = nvalid < 32 ? nvalid : 32;
+    bool waited = false;
 #pragma unroll 1
-    for (int c = 0; c < BN; c += 64) {
-      if (n0 + c >= N) break;  // warp-uniform
+    for (int c = c_begin; c < c_end; c += 64) {
+      const int col = n0 + c + 2 * lane;
+      const bool col_ok = (c + 2 * lane < c_end) && col < N;
+      // operands that do not depend on the accumulator are fetched first (and, for the first chunk, before the wait)
+      float2 x[32];
+      if (ep.resid != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          x[i] = make_float2(0.f, 0.f);
+          if (col_ok && i < nv) x[i] = *reinterpret_cast<const float2*>(ep.resid + (size_t)(row0 + i) * ep.ldr + col);
+        }
+      }
+      float b0 = 0.f, b1 = 0.f, sa0 = 0.f, sa1 = 0.f, sb0 = 0.f, sb1 = 0.f;
+      float2 g0 = make_float2(0.f, 0.f), g1 = g0;
+      int brow = 0x7fffffff;  // first row that belongs to the second batch item touched by this warp
+      if (col_ok) {
+        const int ch = ep.bias_mod > 0 ? col % ep.bias_mod : col;
+        if (ep.bias != nullptr) { b0 = ep.bias[ch]; b1 = ep.bias[ch + 1]; }
+        if (ep.act == ACT_SNAKE) { sa0 = ep.act_a[ch]; sa1 = ep.act_a[ch + 1]; sb0 = ep.act_b[ch]; sb1 = ep.act_b[ch + 1]; }
+        if (ep.gate != nullptr && nv > 0) {
+          const int b0i = row0 / ep.rows_per_batch;
+          brow = (b0i + 1) * ep.rows_per_batch;
+          g0 = *reinterpret_cast<const float2*>(ep.gate + (size_t)b0i * ep.gate_bstride + col);
+          if (brow < row0 + nv) g1 = *reinterpret_cast<const float2*>(ep.gate + (size_t)(b0i + 1) * ep.gate_bstride + col);
+          g0.x = 1.0f - g0.x; g0.y = 1.0f - g0.y; g1.x = 1.0f - g1.x; g1.y = 1.0f - g1.y;
+        }
+      }
+      if (!waited) { wait(); waited = true; }
       uint32_t r[64];
       __syncwarp();
       tmem_ld_32x32(taddr_row + c, r);
@@ -92,65 +127,41 @@ struct EpiLinear {
 #pragma unroll
       for (int g = 0; g < 32; ++g) stage_put(st, lane, g, __uint_as_float(r[2 * g]), __uint_as_float(r[2 * g + 1]));
       __syncwarp();
-      const int col = n0 + c + 2 * lane;
-      if (col < N) {
-        float b0 = 0.f, b1 = 0.f, sa0 = 0.f, sa1 = 0.f, sb0 = 0.f, sb1 = 0.f;
-        const int ch = ep.bias_mod > 0 ? col % ep.bias_mod : col;
-        if (ep.bias != nullptr) { b0 = ep.bias[ch]; b1 = ep.bias[ch + 1]; }
-        if (ep.act == ACT_SNAKE) { sa0 = ep.act_a[ch]; sa1 = ep.act_a[ch + 1]; sb0 = ep.act_b[ch]; sb1 = ep.act_b[ch + 1]; }
+      if (col_ok) {
         const float osc = ep.out_scale != 0.f ? ep.out_scale : 1.f;
         const int c16 = ep.phase_cols > 0 ? (col / ep.phase_cols) * ep.phase_ld16 + col % ep.phase_cols : col;
-        // gate rows: the warp's 32 rows touch at most two batch items -> preload both gate vectors once per chunk
-        float2 g0 = make_float2(0.f, 0.f), g1 = g0;
-        int brow = 0x7fffffff;  // first row belonging to the second batch item
-        if (ep.gate != nullptr) {
-          const int b0i = row0 / ep.rows_per_batch;
-          brow = (b0i + 1) * ep.rows_per_batch;
-          g0 = *reinterpret_cast<const float2*>(ep.gate + (size_t)b0i * ep.gate_bstride + col);
-          if (brow < row0 + 32 && brow < row0 + nvalid) g1 = *reinterpret_cast<const float2*>(ep.gate + (size_t)(b0i + 1) * ep.gate_bstride + col);
-          g0.x = 1.0f - g0.x; g0.y = 1.0f - g0.y; g1.x = 1.0f - g1.x; g1.y = 1.0f - g1.y;
-        }
-        const int nv = nvalid < 32 ? nvalid : 32;
-#pragma unroll 1
-        for (int r0 = 0; r0 < nv; r0 += 8) {
-          float2 x[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            x[i] = make_float2(0.f, 0.f);
-            if (ep.resid != nullptr && r0 + i < nv) x[i] = *reinterpret_cast<const float2*>(ep.resid + (size_t)(row0 + r0 + i) * ep.ldr + col);
+        for (int rr = 0; rr < 32; ++rr) {
+          if (rr >= nv) break;
+          const int row = row0 + rr;
+          const float2 acc = stage_get(st, rr, lane);
+          float v0 = (acc.x + b0) * osc, v1 = (acc.y + b1) * osc;
+          if (ep.resid != nullptr) {
+            if (ep.gate != nullptr) {
+              const float2 g = row >= brow ? g1 : g0;
+              v0 = x[rr].x + g.x * v0;
+              v1 = x[rr].y + g.y * v1;
+            } else {
+              v0 += x[rr].x;
+              v1 += x[rr].y;
+            }
           }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int rr = r0 + i, row = row0 + rr;
-            if (rr >= nv) break;
-            const float2 acc = stage_get(st, rr, lane);
-            float v0 = (acc.x + b0) * osc, v1 = (acc.y + b1) * osc;
-            if (ep.resid != nullptr) {
-              if (ep.gate != nullptr) {
-                const float2 g = row >= brow ? g1 : g0;
-                v0 = x[i].x + g.x * v0;
-                v1 = x[i].y + g.y * v1;
-              } else {
-                v0 += x[i].x;
-                v1 += x[i].y;
-              }
+          if (ep.out_f32 != nullptr) *reinterpret_cast<float2*>(ep.out_f32 + (size_t)row * ep.ld32 + col) = make_float2(v0, v1);
+          if (ep.out_bf16 != nullptr) {
+            if (ep.act == ACT_SILU) {
+              v0 = silu(v0);
+              v1 = silu(v1);
+            } else if (ep.act == ACT_SNAKE) {
+              const float s0 = sinf(v0 * sa0), s1 = sinf(v1 * sa1);
+              v0 = v0 + sb0 * s0 * s0;
+              v1 = v1 + sb1 * s1 * s1;
             }
-            if (ep.out_f32 != nullptr) *reinterpret_cast<float2*>(ep.out_f32 + (size_t)row * ep.ld32 + col) = make_float2(v0, v1);
-            if (ep.out_bf16 != nullptr) {
-              if (ep.act == ACT_SILU) {
-                v0 = silu(v0);
-                v1 = silu(v1);
-              } else if (ep.act == ACT_SNAKE) {
-                const float s0 = sinf(v0 * sa0), s1 = sinf(v1 * sa1);
-                v0 = v0 + sb0 * s0 * s0;
-                v1 = v1 + sb1 * s1 * s1;
-              }
-              store_bf16x2(ep.out_bf16 + (size_t)row * ep.ld16 + c16, ep.split_stride, v0, v1);
-            }
+            store_bf16x2(ep.out_bf16 + (size_t)row * ep.ld16 + c16, ep.split_stride, v0, v1);
           }
         }
       }
     }
+    if (!waited) wait();
   }
 };
 
@@ -162,37 +173,40 @@ struct EpiGegluParams {
   int ld16;
   int split_stride;
 };
+// erf with 1.5e-7 absolute error (Abramowitz-Stegun 7.1.26): one rcp, one ex2, 7 FMA -- used by the bf16 throughput path
+// (the bf16 rounding of the result is 4e-3 relative); the bf16x3 parity path calls the exact erff.
+__device__ __forceinline__ float erf_fast(float x) {
+  const float ax = fabsf(x);
+  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float e = exp2f(-1.4426950408889634f * ax * ax);
+  return copysignf(fmaf(-p * t, e, 1.0f), x);
+}
+__device__ __forceinline__ float gelu_fast(float x) { return 0.5f * x * (1.0f + erf_fast(x * 0.70710678118654752440f)); }
+
 template <int BN>
 struct EpiGeglu {
   using Params = EpiGegluParams;
-  static __device__ __forceinline__ void run(const Params& ep, float* st, uint32_t taddr_row, int row0, int nvalid, int n0, int N, int lane) {
-    constexpr int HALF = BN / 2;
+  static constexpr int HALF = BN / 2;
+  static constexpr int EPI_WARPS = BN == 256 ? 8 : 4;   // 8 warps: each takes 64 of the tile's 128 output features
+  static constexpr int STAGE_FLOATS = 32 * 32;          // 64 packed bf16 per row
+  template <class Wait>
+  static __device__ __forceinline__ void run(const Params& ep, float* st, uint32_t taddr_row, int row0, int nvalid, int n0, int N, int lane, int c_begin,
+                                             int c_end, Wait wait) {
+    wait();
+    // c_begin/c_end are expressed in accumulator columns of the whole tile: map them to output-feature ranges
+    const int f_begin = c_begin / 2, f_end = c_end / 2;
 #pragma unroll 1
-    for (int c = 0; c < HALF; c += 64) {  // 64 output features per pass, gated in the thread == row layout
+    for (int c = f_begin; c < f_end; c += 64) {  // 64 output features per pass, gated in the thread == row layout
       if (n0 + c >= N) break;
-      uint32_t pk[32];  // 64 bf16 results of this thread's row
-#pragma unroll
-      for (int q4 = 0; q4 < 2; ++q4) {
-        uint32_t h[32], g[32];
-        __syncwarp();
-        tmem_ld_32x32(taddr_row + c + q4 * 32, h);
-        tmem_ld_32x32(taddr_row + HALF + c + q4 * 32, g);
-        tmem_ld_wait();
-        const float* bh = ep.bias + n0 + c + q4 * 32;
-        const float* bg = ep.bias + n0 + HALF + c + q4 * 32;
-#pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          const float o0 = (__uint_as_float(h[j]) + __ldg(bh + j)) * gelu_erf(__uint_as_float(g[j]) + __ldg(bg + j));
-          const float o1 = (__uint_as_float(h[j + 1]) + __ldg(bh + j + 1)) * gelu_erf(__uint_as_float(g[j + 1]) + __ldg(bg + j + 1));
-          pk[q4 * 16 + j / 2] = pack_bf16(o0, o1);
-        }
-      }
-      if (ep.split_stride > 0) {  // parity mode keeps full precision: fall back to per-thread row stores of [hi | lo | hi]
-        // (rare path; bf16x3 is the numerics mode, not the throughput mode)
-        __syncwarp();
+      if (ep.split_stride > 0) {  // bf16x3 parity mode: exact erf, per-thread row stores of [hi | lo | hi]
         uint32_t h[32], g[32];
 #pragma unroll 1
         for (int q4 = 0; q4 < 2; ++q4) {
+          __syncwarp();
           tmem_ld_32x32(taddr_row + c + q4 * 32, h);
           tmem_ld_32x32(taddr_row + HALF + c + q4 * 32, g);
           tmem_ld_wait();
@@ -205,12 +219,29 @@ struct EpiGeglu {
               store_bf16x2(o + j, ep.split_stride, o0, o1);
             }
           }
-          __syncwarp();
         }
         continue;
       }
+      uint32_t pk[32];  // 64 bf16 results of this thread's row
 #pragma unroll
-      for (int gq = 0; gq < 16; ++gq) stage_put(st, lane, gq, __uint_as_float(pk[2 * gq]), __uint_as_float(pk[2 * gq + 1]));
+      for (int q4 = 0; q4 < 2; ++q4) {
+        uint32_t h[32], g[32];
+        __syncwarp();
+        tmem_ld_32x32(taddr_row + c + q4 * 32, h);
+        tmem_ld_32x32(taddr_row + HALF + c + q4 * 32, g);
+        tmem_ld_wait();
+        const float* bh = ep.bias + n0 + c + q4 * 32;
+        const float* bg = ep.bias + n0 + HALF + c + q4 * 32;
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          const float o0 = (__uint_as_float(h[j]) + __ldg(bh + j)) * gelu_fast(__uint_as_float(g[j]) + __ldg(bg + j));
+          const float o1 = (__uint_as_float(h[j + 1]) + __ldg(bh + j + 1)) * gelu_fast(__uint_as_float(g[j + 1]) + __ldg(bg + j + 1));
+          pk[q4 * 16 + j / 2] = pack_bf16(o0, o1);
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int gq = 0; gq < 16; ++gq) stage_put<32>(st, lane, gq, __uint_as_float(pk[2 * gq]), __uint_as_float(pk[2 * gq + 1]));
       __syncwarp();
       // 16 lanes cover one 128-byte row segment (64 bf16): the two half-warps take alternate rows
       const int hl = lane & 15, hw = lane >> 4;
@@ -218,26 +249,32 @@ struct EpiGeglu {
 #pragma unroll 4
       for (int rp = 0; rp < 16; ++rp) {
         const int rr = 2 * rp + hw;
-        if (rr < nvalid) *reinterpret_cast<float2*>(obase + (size_t)rr * ep.ld16) = stage_get(st, rr, hl);
+        if (rr < nvalid) *reinterpret_cast<float2*>(obase + (size_t)rr * ep.ld16) = stage_get<32>(st, rr, hl);
       }
     }
   }
 };
 
-template <int BN, int STAGES>
-struct GemmSmem {
+template <int BN, class Epi, bool PAIR>
+struct GemmCfg {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
-  static constexpr int B_BYTES = BN * GEMM_BK * 2;
-  static constexpr int STAGE_BYTES = 4 * EPI_STAGE_FLOATS * 4;  // one 8 KB transpose tile per epilogue warp
+  static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * GEMM_BK * 2;
+  static constexpr int EPI_WARPS = Epi::EPI_WARPS;
+  static constexpr int THREADS = 64 + 32 * EPI_WARPS;
+  static constexpr int STAGE_BYTES = EPI_WARPS * Epi::STAGE_FLOATS * 4;   // one transpose tile per epilogue warp
+  static constexpr int FIT = (GEMM_SMEM_BUDGET - STAGE_BYTES) / (A_BYTES + B_BYTES);
+  static constexpr int STAGES = FIT > 8 ? 8 : FIT;
   static constexpr int BYTES = 1024 /*align slack*/ + STAGES * (A_BYTES + B_BYTES) + STAGE_BYTES + (2 * STAGES + 4) * 8 + 16;
+  static_assert(STAGES >= 3, "smem budget");
 };
 
-template <int BN, int STAGES, class Epi>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+template <int BN, class Epi>
+__global__ void __launch_bounds__((GemmCfg<BN, Epi, false>::THREADS), 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmShape g,
                     const typename Epi::Params ep) {
   static_assert(BN % 16 == 0 && BN >= 64 && BN <= 256, "BN");
-  using SM = GemmSmem<BN, STAGES>;
+  using SM = GemmCfg<BN, Epi, false>;
+  constexpr int STAGES = SM::STAGES;
   constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -263,7 +300,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 128);
+      mbar_init(&tempty[i], 32 * SM::EPI_WARPS);
     }
     fence_mbar_init();
   }
@@ -335,10 +372,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         row0 = bidx * g.T + t0;
         nvalid = g.T - t0;
       }
-      mbar_wait(&tfull[acc], acc_phase);
-      tc_fence_after();
       const uint32_t taddr_row = tmem_base + acc * BN + (static_cast<uint32_t>(lg * 32) << 16);
-      Epi::run(ep, sStage + (warp - 2) * EPI_STAGE_FLOATS, taddr_row, row0, nvalid, nt * BN, g.N, lane);
+      constexpr int CW = BN / (SM::EPI_WARPS / 4);  // columns per warp
+      const int ch = (warp - 2) >> 2;
+      uint64_t* tf = &tfull[acc];
+      const uint32_t ph = acc_phase;
+      Epi::run(ep, sStage + (warp - 2) * Epi::STAGE_FLOATS, taddr_row, row0, nvalid, nt * BN, g.N, lane, ch * CW, (ch + 1) * CW, [tf, ph]() {
+        mbar_wait(tf, ph);
+        tc_fence_after();
+      });
       tc_fence_before();
       mbar_arrive(&tempty[acc]);
       acc ^= 1;
@@ -374,12 +416,17 @@ template <int DH>
 struct EpiHeads {
   using Params = EpiHeadsParams;
   static constexpr int BN = 2 * DH;
-  static __device__ __forceinline__ void run(const Params& ep, float* st, uint32_t taddr_row, int row0, int nvalid, int n0, int N, int lane) {
+  static constexpr int EPI_WARPS = 8;   // the two warps of a TMEM lane group take one head each
+  static constexpr int STAGE_FLOATS = EPI_STAGE_FLOATS;
+  template <class Wait>
+  static __device__ __forceinline__ void run(const Params& ep, float* st, uint32_t taddr_row, int row0, int nvalid, int n0, int N, int lane, int c_begin,
+                                             int c_end, Wait wait) {
+    wait();
     const int row = row0 + lane;
     const bool row_ok = lane < nvalid;
     const int b = row_ok ? row / ep.L : 0, l = row_ok ? row - b * ep.L : 0;
 #pragma unroll 1
-    for (int hh = 0; hh < 2; ++hh) {
+    for (int hh = c_begin / DH; hh < c_end / DH; ++hh) {
       const int n = n0 + hh * DH;
       if (n >= N) break;
       const int sec = n / ep.D, kind = ep.kind[sec], head = (n - sec * ep.D) / DH;
@@ -446,19 +493,12 @@ namespace ezb {
 // 128 rows of A and rows [r*BN/2, (r+1)*BN/2) of the W tile; the leader's single MMA thread issues M=256 instructions that
 // read both CTAs' shared memory, so each SM pulls half the operand bytes per flop through L2 (the 128x128 single-CTA tile
 // is L2->smem bound at ~64 flop/B).  Accumulator rows 128r..128r+127 live in CTA r's TMEM; both CTAs run the epilogue.
-template <int BN, int STAGES>
-struct Gemm2Smem {
-  static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
-  static constexpr int B_BYTES = (BN / 2) * GEMM_BK * 2;
-  static constexpr int STAGE_BYTES = 4 * EPI_STAGE_FLOATS * 4;
-  static constexpr int BYTES = 1024 + STAGES * (A_BYTES + B_BYTES) + STAGE_BYTES + (2 * STAGES + 4) * 8 + 16;
-};
-
-template <int BN, int STAGES, class Epi>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+template <int BN, class Epi>
+__global__ void __launch_bounds__((GemmCfg<BN, Epi, true>::THREADS), 1)
 gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmShape g, const typename Epi::Params ep) {
   static_assert(BN % 16 == 0 && BN >= 64 && BN <= 256, "BN");
-  using SM = Gemm2Smem<BN, STAGES>;
+  using SM = GemmCfg<BN, Epi, true>;
+  constexpr int STAGES = SM::STAGES;
   constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -486,7 +526,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 256);
+      mbar_init(&tempty[i], 2 * 32 * SM::EPI_WARPS);
     }
     fence_mbar_init();
   }
@@ -548,10 +588,15 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
       const int mt = tile % g.num_m_tiles, nt = tile / g.num_m_tiles;
       const int row0 = mt * 2 * GEMM_BM + (int)rank * GEMM_BM + lg * 32;
-      mbar_wait(&tfull[acc], acc_phase);
-      tc_fence_after();
       const uint32_t taddr_row = tmem_base + acc * BN + (static_cast<uint32_t>(lg * 32) << 16);
-      Epi::run(ep, sStage + (warp - 2) * EPI_STAGE_FLOATS, taddr_row, row0, g.M - row0, nt * BN, g.N, lane);
+      constexpr int CW = BN / (SM::EPI_WARPS / 4);
+      const int ch = (warp - 2) >> 2;
+      uint64_t* tf = &tfull[acc];
+      const uint32_t ph = acc_phase;
+      Epi::run(ep, sStage + (warp - 2) * Epi::STAGE_FLOATS, taddr_row, row0, g.M - row0, nt * BN, g.N, lane, ch * CW, (ch + 1) * CW, [tf, ph]() {
+        mbar_wait(tf, ph);
+        tc_fence_after();
+      });
       tc_fence_before();
       mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[acc]), 0));
       acc ^= 1;

@@ -145,11 +145,12 @@ struct ConvAddr {  // implicit-GEMM addressing of A, see gemm.cuh
   int taps = 0, center = 0, dilation = 1, cin_pad = 0, T = 0, B = 0;
 };
 
-template <int BN, int STAGES, class Epi>
+template <int BN, class Epi>
 int launch_gemm_t(Device& dev, cudaStream_t st, const CUtensorMap* tA, const CUtensorMap* tB, const GemmShape& g,
                   const typename Epi::Params& ep) {
-  auto kern = gemm_tcgen05_kernel<BN, STAGES, Epi>;
-  constexpr int smem = GemmSmem<BN, STAGES>::BYTES;
+  auto kern = gemm_tcgen05_kernel<BN, Epi>;
+  constexpr int smem = GemmCfg<BN, Epi, false>::BYTES;
+  constexpr int GEMM_THREADS = GemmCfg<BN, Epi, false>::THREADS;
   static bool attr_set[16] = {};
   if (!attr_set[dev.id & 15]) {
     EZB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -181,7 +182,6 @@ int gemm2(Device& dev, cudaStream_t st, const __nv_bfloat16* A, int lda, const _
           const typename Epi::Params& ep) {
   if (M <= 0 || N <= 0 || K <= 0) return fail(EZB_ERR_SHAPE, "gemm2: empty problem %d %d %d", M, N, K);
   if ((K % 8) || (lda % 8) || (ldw % 8) || (N % 8)) return fail(EZB_ERR_SHAPE, "gemm2: K/ld/N must be multiples of 8 (M%d N%d K%d)", M, N, K);
-  constexpr int STAGES = (BN <= 128) ? 8 : (BN <= 192) ? 7 : 6;
   GemmShape g;
   memset(&g, 0, sizeof g);
   g.M = M; g.N = N;
@@ -191,8 +191,9 @@ int gemm2(Device& dev, cudaStream_t st, const __nv_bfloat16* A, int lda, const _
   const CUtensorMap *tA, *tB;
   EZB_TRY(dev.tmaps.get2d(A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, GEMM_BM, &tA));
   EZB_TRY(dev.tmaps.get2d(W, (uint64_t)K, (uint64_t)N, (uint64_t)ldw, BN / 2, &tB));
-  auto kern = gemm2_tcgen05_kernel<BN, STAGES, Epi>;
-  constexpr int smem = Gemm2Smem<BN, STAGES>::BYTES;
+  auto kern = gemm2_tcgen05_kernel<BN, Epi>;
+  constexpr int smem = GemmCfg<BN, Epi, true>::BYTES;
+  constexpr int GEMM_THREADS = GemmCfg<BN, Epi, true>::THREADS;
   static bool attr_set[16] = {};
   if (!attr_set[dev.id & 15]) {
     EZB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -257,8 +258,7 @@ int gemm(Device& dev, cudaStream_t st, const __nv_bfloat16* A, int lda, const __
     EZB_TRY(dev.tmaps.get2d(A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, GEMM_BM, &tA));
     EZB_TRY(dev.tmaps.get2d(W, (uint64_t)K, (uint64_t)N, (uint64_t)ldw, BN, &tB));
   }
-  constexpr int STAGES = (BN <= 64) ? 8 : (BN <= 128) ? 6 : (BN <= 144) ? 5 : 4;
-  return launch_gemm_t<BN, STAGES, Epi>(dev, st, tA, tB, g, ep);
+  return launch_gemm_t<BN, Epi>(dev, st, tA, tB, g, ep);
 }
 
 }  // namespace ezb
