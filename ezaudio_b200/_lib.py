@@ -53,6 +53,7 @@ _SIGS = {
     "ezb_vae_finalize_weights": ([_VP, _VP], _I),
     "ezb_vae_decode": ([_VP, _VP, _VP, _I, _I, _VP], _I),
     "ezb_set_option": ([C.c_char_p, _I], _I),
+    "ezb_debug_read": ([C.POINTER(C.c_ulonglong)], _I),
     "ezb_launch_count": ([], C.c_ulonglong),
     "ezb_prof_gemm_begin": ([], _I),
     "ezb_prof_gemm_end": ([C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double)], _I),

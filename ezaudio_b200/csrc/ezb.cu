@@ -178,7 +178,19 @@ EZB_API int ezb_test_attention(int device, const void* q, const void* k, const v
 // runtime switches (A/B testing): "pair_gemm" 0/1 -- read when a handle is created
 EZB_API int ezb_set_option(const char* name, int value) {
   if (name && !strcmp(name, "pair_gemm")) { opt_pair_gemm() = value; return EZB_OK; }
+  if (name && !strcmp(name, "gemm_debug")) {  // cycle counters of CTA 0 of every pair-GEMM launch (accumulated)
+    if (value && !gemm_dbg_buf()) { EZB_CUDA(cudaMalloc(&gemm_dbg_buf(), 64)); EZB_CUDA(cudaMemset(gemm_dbg_buf(), 0, 64)); }
+    if (!value && gemm_dbg_buf()) { cudaFree(gemm_dbg_buf()); gemm_dbg_buf() = nullptr; }
+    return EZB_OK;
+  }
   return fail(EZB_ERR_ARG, "unknown option");
+}
+EZB_API int ezb_debug_read(unsigned long long* out8) {
+  if (!gemm_dbg_buf() || !out8) return fail(EZB_ERR_STATE, "gemm_debug is off");
+  EZB_CUDA(cudaDeviceSynchronize());
+  EZB_CUDA(cudaMemcpy(out8, gemm_dbg_buf(), 64, cudaMemcpyDeviceToHost));
+  EZB_CUDA(cudaMemset(gemm_dbg_buf(), 0, 64));
+  return EZB_OK;
 }
 // ---- accounting / profiling hooks (bench.py)
 EZB_API unsigned long long ezb_launch_count(void) { return launch_counter(); }

@@ -28,6 +28,8 @@ struct GemmShape {
   int num_m_tiles, num_n_tiles;
   // implicit-conv addressing of A (taps == 0 -> plain 2-D A[M,K])
   int taps, center, dilation, cin_blocks, T, tiles_per_batch;
+  unsigned long long* dbg;  // optional cycle counters (CTA 0): [0] mma wait full, [1] mma wait tempty, [2] producer wait empty,
+                            // [3] epilogue warp 2 wait tfull, [4] epilogue warp 2 busy, [5] total
 };
 
 enum { ACT_NONE = 0, ACT_SILU = 1, ACT_SNAKE = 2 };
@@ -75,6 +77,76 @@ __device__ __forceinline__ void store_bf16x2(__nv_bfloat16* p, int split_stride,
     const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&hi);
     *reinterpret_cast<uint32_t*>(p + split_stride) = pack_bf16(a - __low2float(h), b - __high2float(h));
     *reinterpret_cast<uint32_t*>(p + 2 * split_stride) = hi;
+  }
+}
+
+struct RowCtx {
+  const float* st; int lane, nv, row0, brow;
+  float b0, b1; float2 g0, g1; float sa0, sa1, sb0, sb1;
+  float* o32; int ld32; __nv_bfloat16* o16; int ld16;
+};
+template <bool RESID, bool GATE, bool F32, bool BF16, int ACT>
+__device__ __forceinline__ void rows_t(const RowCtx& c, const float2* x) {
+  float* o32 = c.o32;
+  __nv_bfloat16* o16 = c.o16;
+#pragma unroll
+  for (int rr = 0; rr < 32; ++rr) {
+    if (rr >= c.nv) break;
+    const float2 acc = stage_get(c.st, rr, c.lane);
+    float v0 = acc.x + c.b0, v1 = acc.y + c.b1;
+    if (RESID) {
+      if (GATE) {
+        const bool second = c.row0 + rr >= c.brow;
+        v0 = fmaf(second ? c.g1.x : c.g0.x, v0, x[rr].x);
+        v1 = fmaf(second ? c.g1.y : c.g0.y, v1, x[rr].y);
+      } else {
+        v0 += x[rr].x;
+        v1 += x[rr].y;
+      }
+    }
+    if (F32) { *reinterpret_cast<float2*>(o32) = make_float2(v0, v1); o32 += c.ld32; }
+    if (BF16) {
+      if (ACT == ACT_SILU) { v0 = silu(v0); v1 = silu(v1); }
+      if (ACT == ACT_SNAKE) {
+        const float s0 = sinf(v0 * c.sa0), s1 = sinf(v1 * c.sa1);
+        v0 = fmaf(c.sb0 * s0, s0, v0);
+        v1 = fmaf(c.sb1 * s1, s1, v1);
+      }
+      *reinterpret_cast<uint32_t*>(o16) = pack_bf16(v0, v1);
+      o16 += c.ld16;
+    }
+  }
+}
+__device__ __forceinline__ void rows_generic(const EpiLinearParams& ep, const RowCtx& c, const float2* x, int col, int c16) {
+  const float osc = ep.out_scale != 0.f ? ep.out_scale : 1.f;
+#pragma unroll
+  for (int rr = 0; rr < 32; ++rr) {
+    if (rr >= c.nv) break;
+    const int row = c.row0 + rr;
+    const float2 acc = stage_get(c.st, rr, c.lane);
+    float v0 = (acc.x + c.b0) * osc, v1 = (acc.y + c.b1) * osc;
+    if (ep.resid != nullptr) {
+      if (ep.gate != nullptr) {
+        const float2 g = row >= c.brow ? c.g1 : c.g0;
+        v0 = x[rr].x + g.x * v0;
+        v1 = x[rr].y + g.y * v1;
+      } else {
+        v0 += x[rr].x;
+        v1 += x[rr].y;
+      }
+    }
+    if (ep.out_f32 != nullptr) *reinterpret_cast<float2*>(ep.out_f32 + (size_t)row * ep.ld32 + col) = make_float2(v0, v1);
+    if (ep.out_bf16 != nullptr) {
+      if (ep.act == ACT_SILU) {
+        v0 = silu(v0);
+        v1 = silu(v1);
+      } else if (ep.act == ACT_SNAKE) {
+        const float s0 = sinf(v0 * c.sa0), s1 = sinf(v1 * c.sa1);
+        v0 = v0 + c.sb0 * s0 * s0;
+        v1 = v1 + c.sb1 * s1 * s1;
+      }
+      store_bf16x2(ep.out_bf16 + (size_t)row * ep.ld16 + c16, ep.split_stride, v0, v1);
+    }
   }
 }
 
@@ -128,36 +200,23 @@ struct EpiLinear {
       for (int g = 0; g < 32; ++g) stage_put(st, lane, g, __uint_as_float(r[2 * g]), __uint_as_float(r[2 * g + 1]));
       __syncwarp();
       if (col_ok) {
-        const float osc = ep.out_scale != 0.f ? ep.out_scale : 1.f;
         const int c16 = ep.phase_cols > 0 ? (col / ep.phase_cols) * ep.phase_ld16 + col % ep.phase_cols : col;
-#pragma unroll
-        for (int rr = 0; rr < 32; ++rr) {
-          if (rr >= nv) break;
-          const int row = row0 + rr;
-          const float2 acc = stage_get(st, rr, lane);
-          float v0 = (acc.x + b0) * osc, v1 = (acc.y + b1) * osc;
-          if (ep.resid != nullptr) {
-            if (ep.gate != nullptr) {
-              const float2 g = row >= brow ? g1 : g0;
-              v0 = x[rr].x + g.x * v0;
-              v1 = x[rr].y + g.y * v1;
-            } else {
-              v0 += x[rr].x;
-              v1 += x[rr].y;
-            }
-          }
-          if (ep.out_f32 != nullptr) *reinterpret_cast<float2*>(ep.out_f32 + (size_t)row * ep.ld32 + col) = make_float2(v0, v1);
-          if (ep.out_bf16 != nullptr) {
-            if (ep.act == ACT_SILU) {
-              v0 = silu(v0);
-              v1 = silu(v1);
-            } else if (ep.act == ACT_SNAKE) {
-              const float s0 = sinf(v0 * sa0), s1 = sinf(v1 * sa1);
-              v0 = v0 + sb0 * s0 * s0;
-              v1 = v1 + sb1 * s1 * s1;
-            }
-            store_bf16x2(ep.out_bf16 + (size_t)row * ep.ld16 + c16, ep.split_stride, v0, v1);
-          }
+        const int code = (ep.resid != nullptr ? 1 : 0) | (ep.gate != nullptr ? 2 : 0) | (ep.out_f32 != nullptr ? 4 : 0) | (ep.out_bf16 != nullptr ? 8 : 0) |
+                         (ep.act << 4) | ((ep.split_stride > 0 || ep.out_scale != 0.f) ? 256 : 0);
+        const RowCtx rc{st, lane, nv, row0, brow, b0, b1, g0, g1, sa0, sa1, sb0, sb1,
+                        ep.out_f32 != nullptr ? ep.out_f32 + (size_t)row0 * ep.ld32 + col : nullptr, ep.ld32,
+                        ep.out_bf16 != nullptr ? ep.out_bf16 + (size_t)row0 * ep.ld16 + c16 : nullptr, ep.ld16};
+        switch (code) {
+          case 4: rows_t<false, false, true, false, ACT_NONE>(rc, x); break;             // bias -> f32
+          case 7: rows_t<true, true, true, false, ACT_NONE>(rc, x); break;               // gated residual (in place)
+          case 5: rows_t<true, false, true, false, ACT_NONE>(rc, x); break;              // residual
+          case 8: rows_t<false, false, false, true, ACT_NONE>(rc, x); break;             // bf16
+          case 8 | (ACT_SILU << 4): rows_t<false, false, false, true, ACT_SILU>(rc, x); break;
+          case 8 | (ACT_SNAKE << 4): rows_t<false, false, false, true, ACT_SNAKE>(rc, x); break;       // conv7
+          case 12 | (ACT_SNAKE << 4): rows_t<false, false, true, true, ACT_SNAKE>(rc, x); break;       // conv-transpose
+          case 13 | (ACT_SNAKE << 4): rows_t<true, false, true, true, ACT_SNAKE>(rc, x); break;        // conv1 + residual
+          case 9 | (ACT_SNAKE << 4): rows_t<true, false, false, true, ACT_SNAKE>(rc, x); break;        // last conv1 of a block
+          default: rows_generic(ep, rc, x, col, c16); break;
         }
       }
     }
@@ -173,19 +232,30 @@ struct EpiGegluParams {
   int ld16;
   int split_stride;
 };
-// erf with 1.5e-7 absolute error (Abramowitz-Stegun 7.1.26): one rcp, one ex2, 7 FMA -- used by the bf16 throughput path
-// (the bf16 rounding of the result is 4e-3 relative); the bf16x3 parity path calls the exact erff.
-__device__ __forceinline__ float erf_fast(float x) {
-  const float ax = fabsf(x);
-  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// h * gelu(g) with erf from Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7 + 2 ulp of the MUFU rcp / ex2): 2 MUFU + ~14 FP32 ops.
+// Used by the bf16 throughput path only (its output is rounded to bf16, 4e-3 relative); bf16x3 calls the exact erff.
+__device__ __forceinline__ float geglu_fast(float h, float g) {
+  const float z = g * 0.70710678118654752440f, az = fabsf(z);
+  const float t = rcp_approx(fmaf(0.3275911f, az, 1.0f));
   float p = fmaf(1.061405429f, t, -1.453152027f);
   p = fmaf(p, t, 1.421413741f);
   p = fmaf(p, t, -0.284496736f);
   p = fmaf(p, t, 0.254829592f);
-  const float e = exp2f(-1.4426950408889634f * ax * ax);
-  return copysignf(fmaf(-p * t, e, 1.0f), x);
+  const float e = ex2_approx(az * az * -1.4426950408889634f);
+  const float erf_abs = fmaf(-p * t, e, 1.0f);
+  const float erf_s = copysignf(erf_abs, z);
+  return h * (0.5f * g) * (1.0f + erf_s);
 }
-__device__ __forceinline__ float gelu_fast(float x) { return 0.5f * x * (1.0f + erf_fast(x * 0.70710678118654752440f)); }
 
 template <int BN>
 struct EpiGeglu {
@@ -234,8 +304,8 @@ struct EpiGeglu {
         const float* bg = ep.bias + n0 + HALF + c + q4 * 32;
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
-          const float o0 = (__uint_as_float(h[j]) + __ldg(bh + j)) * gelu_fast(__uint_as_float(g[j]) + __ldg(bg + j));
-          const float o1 = (__uint_as_float(h[j + 1]) + __ldg(bh + j + 1)) * gelu_fast(__uint_as_float(g[j + 1]) + __ldg(bg + j + 1));
+          const float o0 = geglu_fast(__uint_as_float(h[j]) + __ldg(bh + j), __uint_as_float(g[j]) + __ldg(bg + j));
+          const float o1 = geglu_fast(__uint_as_float(h[j + 1]) + __ldg(bh + j + 1), __uint_as_float(g[j + 1]) + __ldg(bg + j + 1));
           pk[q4 * 16 + j / 2] = pack_bf16(o0, o1);
         }
       }
@@ -536,6 +606,9 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const bool dbg = g.dbg != nullptr && blockIdx.x == 0;
+  const long long t_start = clock64();
+  long long w0 = 0, w1 = 0;
 
   if (warp == 0) {
     // ------------------------------------------------ TMA producer (both CTAs; bytes are credited to the leader's barrier)
@@ -545,7 +618,9 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const int mt = tile % g.num_m_tiles, nt = tile / g.num_m_tiles;
         const int m0 = mt * 2 * GEMM_BM + (int)rank * GEMM_BM, n0 = nt * BN + (int)rank * (BN / 2);
         for (int kb = 0; kb < g.num_k_blocks; ++kb) {
+          const long long tq = clock64();
           mbar_wait(&empty[stage], phase ^ 1);
+          w0 += clock64() - tq;
           const uint32_t bar = mapa_u32(smem_u32(&full[stage]), 0);
           if (leader) mbar_expect_tx(&full[stage], 2 * (SM::A_BYTES + SM::B_BYTES));
           tma_load_2d_pair(sA + stage * SM::A_BYTES, &tmA, bar, kb * GEMM_BK, m0);
@@ -560,11 +635,15 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       constexpr uint32_t idesc = umma_idesc_bf16(2 * GEMM_BM, BN);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        long long tq = clock64();
         mbar_wait(&tempty[acc], acc_phase ^ 1);
+        w1 += clock64() - tq;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < g.num_k_blocks; ++kb) {
+          tq = clock64();
           mbar_wait(&full[stage], phase);
+          w0 += clock64() - tq;
           tc_fence_after();
           if (lane == 0) {
             const uint64_t ad = umma_desc_sw128(smem_u32(sA + stage * SM::A_BYTES));
@@ -593,15 +672,26 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       const int ch = (warp - 2) >> 2;
       uint64_t* tf = &tfull[acc];
       const uint32_t ph = acc_phase;
-      Epi::run(ep, sStage + (warp - 2) * Epi::STAGE_FLOATS, taddr_row, row0, g.M - row0, nt * BN, g.N, lane, ch * CW, (ch + 1) * CW, [tf, ph]() {
+      const long long te = clock64();
+      long long tw = 0;
+      Epi::run(ep, sStage + (warp - 2) * Epi::STAGE_FLOATS, taddr_row, row0, g.M - row0, nt * BN, g.N, lane, ch * CW, (ch + 1) * CW, [tf, ph, &tw]() {
+        const long long tq = clock64();
         mbar_wait(tf, ph);
+        tw = clock64() - tq;
         tc_fence_after();
       });
+      w0 += tw;
+      w1 += clock64() - te - tw;
       tc_fence_before();
       mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[acc]), 0));
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+  }
+  if (dbg && lane == 0) {
+    if (warp == 0) atomicAdd(&g.dbg[2], (unsigned long long)w0);
+    if (warp == 1) { atomicAdd(&g.dbg[0], (unsigned long long)w0); atomicAdd(&g.dbg[1], (unsigned long long)w1); }
+    if (warp == 2) { atomicAdd(&g.dbg[3], (unsigned long long)w0); atomicAdd(&g.dbg[4], (unsigned long long)w1); atomicAdd(&g.dbg[5], (unsigned long long)(clock64() - t_start)); }
   }
   tc_fence_before();
   __syncthreads();

@@ -27,6 +27,10 @@ inline int& opt_pair_gemm() {
   static int v = 1;
   return v;
 }
+inline unsigned long long*& gemm_dbg_buf() {
+  static unsigned long long* p = nullptr;
+  return p;
+}
 struct GemmProf {
   bool on = false;
   std::vector<cudaEvent_t> ev;   // pairs
@@ -185,6 +189,7 @@ int gemm2(Device& dev, cudaStream_t st, const __nv_bfloat16* A, int lda, const _
   GemmShape g;
   memset(&g, 0, sizeof g);
   g.M = M; g.N = N;
+  g.dbg = gemm_dbg_buf();
   g.num_n_tiles = (N + BN - 1) / BN;
   g.num_m_tiles = (M + 2 * GEMM_BM - 1) / (2 * GEMM_BM);
   g.num_k_blocks = (K + GEMM_BK - 1) / GEMM_BK;

@@ -114,6 +114,8 @@ int ezb_test_attention(int device, const void* q, const void* k, const void* vt,
 
 /* runtime switch for A/B measurements: "pair_gemm" (1 = cta_group::2 256-row tiles, default; 0 = single-CTA 128x128) */
 int ezb_set_option(const char* name, int value);
+/* debugging aid: with option "gemm_debug"=1, CTA 0 of each pair-GEMM accumulates cycle counters; this reads and resets them */
+int ezb_debug_read(unsigned long long* out8);
 /* accounting: kernels launched by this library so far (process-wide); per-GEMM CUDA-event timing for bench.py's roofline leg */
 unsigned long long ezb_launch_count(void);
 int ezb_prof_gemm_begin(void);
