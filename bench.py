@@ -177,8 +177,9 @@ def main():
     ue, um = enc([""])
     te, tm, ue, um = te.to(dev), tm.to(dev), ue.to(dev), um.to(dev)
 
-    def step_resident():
-        lat = sample_latents(ez.unet, ez.noise_scheduler, te, tm, ue, um, None, None, L, gs, gr, STEPS_DDIM, 1, 2024 + rank * B, device=dev)
+    def step_resident(use_graphs=True):
+        lat = sample_latents(ez.unet, ez.noise_scheduler, te, tm, ue, um, None, None, L, gs, gr, STEPS_DDIM, 1, 2024 + rank * B, device=dev,
+                             use_graphs=use_graphs)
         return ez.autoencoder(embedding=lat)
 
     def step_e2e():
@@ -231,15 +232,15 @@ def main():
     pk = peaks()
     if rank == 0:
         _lib.check(Lb.ezb_prof_gemm_begin())
-        step_resident()
+        step_resident(use_graphs=False)  # eager launches so that every GEMM passes the event-timing hook
         nl, fl, tms = C.c_int(), C.c_double(), C.c_double()
         _lib.check(Lb.ezb_prof_gemm_end(C.byref(nl), C.byref(fl), C.byref(tms)))
         ach = fl.value / (tms.value * 1e-3) / 1e12
-        roof = dict(bound="tensor", kernel="gemm_tcgen05_kernel", achieved=ach, peak=pk["sustained"], unit="TFLOP/s", frac=ach / pk["sustained"],
+        roof = dict(bound="tensor", kernel="gemm2_tcgen05_kernel / gemm_tcgen05_kernel (all tcgen05 GEMM launches)", achieved=ach, peak=pk["sustained"], unit="TFLOP/s", frac=ach / pk["sustained"],
                     peak_source=pk["src"] + ", sustained figure (kernel timed inside a long step)", traffic=None,
                     launches=nl.value, flops_per_launch=fl.value / max(1, nl.value), ms_per_launch=tms.value / max(1, nl.value),
                     gemm_share_of_step=tms.value / (ms / a.steps),
-                    how="CUDA events around every GEMM launch on the launch stream during one extra instrumented generation")
+                    how="CUDA events around every GEMM launch on the launch stream during one extra instrumented (eager, non-graph) generation")
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()

@@ -55,6 +55,7 @@ _SIGS = {
     "ezb_set_option": ([C.c_char_p, _I], _I),
     "ezb_debug_read": ([C.POINTER(C.c_ulonglong)], _I),
     "ezb_launch_count": ([], C.c_ulonglong),
+    "ezb_launch_count_add": ([C.c_ulonglong], None),
     "ezb_prof_gemm_begin": ([], _I),
     "ezb_prof_gemm_end": ([C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double)], _I),
     "ezb_test_gemm": ([_I, _VP, _I, _VP, _I, _I, _I, _I, _I, _I, C.POINTER(TestEpilogue), _I, _I, _I, _I, _I, _I, _VP], _I),

@@ -4,11 +4,11 @@
 //
 // Persistent, warp-specialised, software-pipelined: one CTA per SM walks work items (b*H + h, 128-query tile); every item
 // is a sequence of "units" (one 128-key block each).  Units are numbered across items so all rings keep rolling:
-//   warp 9  (TMA)     : Q tile per item (2-deep ring), K / V^T tiles per unit (2-deep ring).
-//   warp 8  (MMA)     : S_u = Q K_u^T (tcgen05.mma M128 N128) into TMEM S[u%2] is issued BEFORE waiting for unit u-1's
+//   warp 17 (TMA)     : Q tile per item (2-deep ring), K / V^T tiles per unit (2-deep ring).
+//   warp 16 (MMA)     : S_u = Q K_u^T (tcgen05.mma M128 N128) into TMEM S[u%2] is issued BEFORE waiting for unit u-1's
 //                       probabilities, then O_{u-1} = P_{u-1} V_{u-1} (M128 N=DVP) into TMEM O[(u-1)%2]: the tensor pipe
 //                       works one unit ahead of the softmax warps.
-//   warps 0-7 (softmax): thread (w, lane) owns query row 32*(w%4)+lane and key columns 64*(w/4)..+63 of the S tile:
+//   warps 0-15 (softmax): thread (w, lane) owns query row 32*(w%4)+lane and key columns 32*(w/4)..+31 of the S tile:
 //                       tcgen05.ld, running max / exp2 / sum in fp32, P (bf16) written to smem in the 128B-swizzled K-major
 //                       layout, O_{u-1} folded into the fp32 register accumulator (running-max correction) while the tensor
 //                       pipe already computes S_{u+1}.
@@ -21,7 +21,7 @@
 namespace ezb {
 
 constexpr int AT_BQ = 128, AT_BK = 128;
-constexpr int AT_SOFTMAX_THREADS = 256;
+constexpr int AT_SOFTMAX_THREADS = 512;   // 16 warps: 4 per TMEM lane group, each owning 32 key columns of the S tile
 constexpr int AT_THREADS = AT_SOFTMAX_THREADS + 64;
 
 struct AttnParams {
@@ -30,6 +30,8 @@ struct AttnParams {
   int H, Lq, Lk, dh, dvp;
   int n_qt, n_items;        // query tiles per (b,h); total work items
   float scale_log2;         // (1/sqrt(dh)) * log2(e)
+  unsigned long long* dbg;  // optional cycle counters of CTA 0: [0] softmax wait S, [1] softmax wait O, [2] softmax barrier, [3] softmax total,
+                            // [4] mma wait kv, [5] mma wait P, [6] mma total, [7] tma wait
 };
 
 template <int KH>
@@ -39,7 +41,7 @@ struct AttnSmem {
   static constexpr int P_BYTES = 2 * 16384;
   static __host__ __device__ constexpr int v_bytes(int dvp) { return 2 * dvp * 128; }
   static __host__ __device__ constexpr int total(int dvp) {
-    return 1024 + 2 * Q_BYTES + 2 * K_BYTES + 2 * v_bytes(dvp) + P_BYTES + 2 * 2 * 128 * 4 + 16 * 8;
+    return 1024 + 2 * Q_BYTES + 2 * K_BYTES + 2 * v_bytes(dvp) + P_BYTES + 2 * 4 * 128 * 4 + 16 * 8;
   }
 };
 
@@ -54,8 +56,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   uint8_t* sK = sQ + 2 * SM::Q_BYTES;      // [2][K_BYTES]
   uint8_t* sV = sK + 2 * SM::K_BYTES;      // [2][VB]
   uint8_t* sP = sV + 2 * VB;               // [P_BYTES]
-  float* sx = reinterpret_cast<float*>(sP + SM::P_BYTES);  // [2][2][128] max / sum exchange
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sx + 2 * 2 * 128);
+  float* sx = reinterpret_cast<float*>(sP + SM::P_BYTES);  // [2][4][128] max / sum exchange
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sx + 2 * 4 * 128);
   uint64_t *q_full = bars, *q_empty = bars + 2, *kv_full = bars + 4, *kv_empty = bars + 6, *s_full = bars + 8, *o_full = bars + 10, *p_full = bars + 12;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
@@ -64,7 +66,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   const int my_items = (p.n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int n_units = my_items * n_kv;
 
-  if (warp == 8) {
+  if (warp == 16) {
     if (lane == 0) {
       tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
       for (int i = 0; i < 2; ++i) {
@@ -83,7 +85,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem0 = *tmem_slot;  // S[0] @0, S[1] @128, O[0] @256, O[1] @384
 
-  if (warp == 9) {
+  if (warp == 17) {
     // ------------------------------------------------ TMA producer
     if (lane == 0) {
       for (int it = 0, u = 0; it < my_items; ++it) {
@@ -102,13 +104,17 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         }
       }
     }
-  } else if (warp == 8) {
+  } else if (warp == 16) {
     // ------------------------------------------------ MMA issuer
     if (lane == 0) {
       const uint32_t idesc_s = umma_idesc_bf16(AT_BQ, AT_BK), idesc_o = umma_idesc_bf16(AT_BQ, p.dvp);
+      long long m_wkv = 0, m_wp = 0;
+      const long long m_t0 = clock64();
       auto issue_pv = [&](int u) {  // O[u%2] = P_u V_u ; frees kv stage u%2
         const int s = u & 1;
+        const long long tq = clock64();
         mbar_wait(p_full, u & 1);
+        m_wp += clock64() - tq;
         tc_fence_after();
         for (int hh = 0; hh < 2; ++hh) {
           const uint64_t pd = umma_desc_sw128(smem_u32(sP + hh * 16384)), vd = umma_desc_sw128(smem_u32(sV + s * VB + hh * (VB / 2)));
@@ -123,7 +129,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         mbar_wait(&q_full[qb], (it >> 1) & 1);
         for (int j = 0; j < n_kv; ++j, ++u) {
           const int s = u & 1;
+          const long long tq = clock64();
           mbar_wait(&kv_full[s], (u >> 1) & 1);
+          m_wkv += clock64() - tq;
           tc_fence_after();
           for (int kh = 0; kh < KH; ++kh) {
             const uint64_t qd = umma_desc_sw128(smem_u32(sQ + qb * SM::Q_BYTES + kh * 16384));
@@ -137,54 +145,58 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         }
       }
       if (n_units > 0) issue_pv(n_units - 1);
+      if (p.dbg != nullptr && blockIdx.x == 0) {
+        atomicAdd(&p.dbg[4], (unsigned long long)m_wkv); atomicAdd(&p.dbg[5], (unsigned long long)m_wp); atomicAdd(&p.dbg[6], (unsigned long long)(clock64() - m_t0));
+      }
     }
   } else {
     // ------------------------------------------------ softmax / accumulate
-    const int lg = warp & 3, ch = warp >> 2;       // TMEM lane group, key-column half
+    const int lg = warp & 3, cq = warp >> 2;       // TMEM lane group, key-column quarter
     const int r = lg * 32 + lane;                  // query row within the tile
     const uint32_t t_row = static_cast<uint32_t>(lg * 32) << 16;
-    const int ocn = p.dvp / 2;                     // 32 or 40 O columns per thread
-    const int oc0 = ch * ocn;
+    const int ocn = p.dvp / 4;                     // 16 or 20 O columns per thread
+    const int oc0 = cq * ocn;
+    long long c_ws = 0, c_wo = 0, c_bar = 0;
+    const long long c_t0 = clock64();
     float m_run = -INFINITY, l_run = 0.f;
-    float o[40];
+    float o[20];
 #pragma unroll
-    for (int i = 0; i < 40; ++i) o[i] = 0.f;
+    for (int i = 0; i < 20; ++i) o[i] = 0.f;
 
     auto fold_o = [&](int u) {  // o += O_u (TMEM O[u%2]) once P_u V_u has completed
+      const long long tq = clock64();
       mbar_wait(&o_full[u & 1], (u >> 1) & 1);
+      c_wo += clock64() - tq;
       tc_fence_after();
       const uint32_t ta = tmem0 + 256 + (u & 1) * 128 + t_row + oc0;
-      uint32_t orr[32], t8[8];
-      tmem_ld_32x32(ta, orr);
-      if (ocn == 40) tmem_ld_32x8(ta + 32, t8);
+      uint32_t orr[16], t4[4];
+      tmem_ld_32x16(ta, orr);
+      if (ocn == 20) tmem_ld_32x4(ta + 16, t4);
       tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 32; ++i) o[i] += __uint_as_float(orr[i]);
-      if (ocn == 40) {
+      for (int i = 0; i < 16; ++i) o[i] += __uint_as_float(orr[i]);
+      if (ocn == 20) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o[32 + i] += __uint_as_float(t8[i]);
+        for (int i = 0; i < 4; ++i) o[16 + i] += __uint_as_float(t4[i]);
       }
       tc_fence_before();
     };
-    auto finish_item = [&](int item) {  // combine the two column halves' partial sums, normalise, store
+    auto finish_item = [&](int item) {  // combine the four column quarters' partial sums, normalise, store
       named_bar_sync(1, AT_SOFTMAX_THREADS);
       float* xl = sx;
-      xl[ch * 128 + r] = l_run;
+      xl[cq * 128 + r] = l_run;
       named_bar_sync(1, AT_SOFTMAX_THREADS);
-      const float inv = 1.f / (l_run + xl[(ch ^ 1) * 128 + r]);
+      const float inv = 1.f / ((xl[r] + xl[128 + r]) + (xl[256 + r] + xl[384 + r]));
       const int bh = item / p.n_qt, q0 = (item - bh * p.n_qt) * AT_BQ;
       const int b = bh / p.H, h = bh - b * p.H;
       const int qrow = q0 + r;
       if (qrow < p.Lq) {
         __nv_bfloat16* orow = p.out + ((size_t)b * p.Lq + qrow) * (size_t)(p.H * p.dh) + h * p.dh;
 #pragma unroll
-        for (int v8 = 0; v8 < 5; ++v8) {
-          const int c0 = oc0 + v8 * 8;
-          if (v8 * 8 < ocn && c0 + 8 <= p.dh) {
-            uint4 pk = make_uint4(pack_bf16(o[v8 * 8 + 0] * inv, o[v8 * 8 + 1] * inv), pack_bf16(o[v8 * 8 + 2] * inv, o[v8 * 8 + 3] * inv),
-                                  pack_bf16(o[v8 * 8 + 4] * inv, o[v8 * 8 + 5] * inv), pack_bf16(o[v8 * 8 + 6] * inv, o[v8 * 8 + 7] * inv));
-            *reinterpret_cast<uint4*>(orow + c0) = pk;
-          }
+        for (int v4 = 0; v4 < 5; ++v4) {
+          const int c0 = oc0 + v4 * 4;
+          if (v4 * 4 < ocn && c0 + 4 <= p.dh)
+            *reinterpret_cast<uint2*>(orow + c0) = make_uint2(pack_bf16(o[v4 * 4 + 0] * inv, o[v4 * 4 + 1] * inv), pack_bf16(o[v4 * 4 + 2] * inv, o[v4 * 4 + 3] * inv));
         }
       }
       named_bar_sync(1, AT_SOFTMAX_THREADS);  // xl is reused by the next unit's max exchange
@@ -196,41 +208,48 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       const uint8_t* km = p.key_mask ? p.key_mask + (size_t)b * p.Lk : nullptr;
       for (int j = 0; j < n_kv; ++j, ++u) {
         // ---- 1. scores of this unit
+        long long tq = clock64();
         mbar_wait(&s_full[u & 1], (u >> 1) & 1);
+        c_ws += clock64() - tq;
         tc_fence_after();
-        uint32_t sr[64];
-        const uint32_t ts = tmem0 + (u & 1) * 128 + t_row + ch * 64;
-        tmem_ld_32x32(ts, sr);
-        tmem_ld_32x32(ts + 32, sr + 32);
+        uint32_t sr[32];
+        tmem_ld_32x32(tmem0 + (u & 1) * 128 + t_row + cq * 32, sr);
         tmem_ld_wait();
         tc_fence_before();
-        const int kbase = j * AT_BK + ch * 64;
-        const bool full = (km == nullptr) && (kbase + 64 <= p.Lk);
-        float mx = -INFINITY;
-        if (full) {
+        const int kbase = j * AT_BK + cq * 32;
+        const bool full = (km == nullptr) && (kbase + 32 <= p.Lk);
+        if (!full) {  // branch-free masking: one validity bit per key column of this thread
+          const int rem = p.Lk - kbase;  // keys of this quarter that exist
+          uint32_t valid = rem >= 32 ? 0xffffffffu : (rem <= 0 ? 0u : ((1u << rem) - 1u));
+          if (km != nullptr) {
+            uint32_t mk = 0u;
 #pragma unroll
-          for (int c = 0; c < 64; ++c) mx = fmaxf(mx, __uint_as_float(sr[c]));
-        } else {
-#pragma unroll
-          for (int c = 0; c < 64; ++c) {
-            const int kidx = kbase + c;
-            const bool ok = kidx < p.Lk && (km == nullptr || km[kidx] != 0);
-            const float v = ok ? __uint_as_float(sr[c]) : -INFINITY;
-            sr[c] = __float_as_uint(v);
-            mx = fmaxf(mx, v);
+            for (int c = 0; c < 32; ++c) mk |= (uint32_t)(km[min(kbase + c, p.Lk - 1)] != 0) << c;
+            valid &= mk;
           }
+#pragma unroll
+          for (int c = 0; c < 32; ++c) sr[c] = ((valid >> c) & 1u) ? sr[c] : 0xff800000u;  // -inf
         }
-        float* xm = sx + (u & 1) * 256;
-        xm[ch * 128 + r] = mx;
+        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int c = 0; c < 32; c += 4) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) mx4[e] = fmaxf(mx4[e], __uint_as_float(sr[c + e]));
+        }
+        const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+        float* xm = sx + (u & 1) * 512;
+        xm[cq * 128 + r] = mx;
+        tq = clock64();
         named_bar_sync(1, AT_SOFTMAX_THREADS);
-        const float m_blk = fmaxf(mx, xm[(ch ^ 1) * 128 + r]);
+        c_bar += clock64() - tq;
+        const float m_blk = fmaxf(fmaxf(xm[r], xm[128 + r]), fmaxf(xm[256 + r], xm[384 + r]));
         // ---- 2. previous unit's P V product: fold into the accumulator (and close the previous item)
         if (u > 0) {
           fold_o(u - 1);
           if (j == 0) {  // the previous unit was the last one of the previous item
             finish_item(item - (int)gridDim.x);
 #pragma unroll
-            for (int i = 0; i < 40; ++i) o[i] = 0.f;
+            for (int i = 0; i < 20; ++i) o[i] = 0.f;
             m_run = -INFINITY;
             l_run = 0.f;
           }
@@ -239,23 +258,23 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         const float m_new = fmaxf(m_run, m_blk);
         const float corr = (m_run == -INFINITY) ? 0.f : ex2_approx((m_run - m_new) * p.scale_log2);
         const float mb = (m_new == -INFINITY) ? 0.f : m_new * p.scale_log2;  // fully masked so far: p = exp2(-inf) = 0
-        float sum = 0.f;
-        uint8_t* prow = sP + ch * 16384 + (r >> 3) * 1024 + (r & 7) * 128;
+        float sum4[4] = {0.f, 0.f, 0.f, 0.f};
+        uint8_t* prow = sP + (cq >> 1) * 16384 + (r >> 3) * 1024 + (r & 7) * 128;
 #pragma unroll
-        for (int c8 = 0; c8 < 8; ++c8) {
+        for (int c8 = 0; c8 < 4; ++c8) {
           float pv[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             pv[e] = ex2_approx(fmaf(__uint_as_float(sr[c8 * 8 + e]), p.scale_log2, -mb));
-            sum += pv[e];
+            sum4[e & 3] += pv[e];
           }
           uint4 pk = make_uint4(pack_bf16(pv[0], pv[1]), pack_bf16(pv[2], pv[3]), pack_bf16(pv[4], pv[5]), pack_bf16(pv[6], pv[7]));
-          *reinterpret_cast<uint4*>(prow + ((c8 ^ (r & 7)) << 4)) = pk;
+          *reinterpret_cast<uint4*>(prow + ((((cq & 1) * 4 + c8) ^ (r & 7)) << 4)) = pk;
         }
-        l_run = l_run * corr + sum;
+        l_run = l_run * corr + ((sum4[0] + sum4[1]) + (sum4[2] + sum4[3]));
         m_run = m_new;
 #pragma unroll
-        for (int i = 0; i < 40; ++i) o[i] *= corr;
+        for (int i = 0; i < 20; ++i) o[i] *= corr;
         fence_proxy_async_smem();
         mbar_arrive(p_full);
       }
@@ -264,16 +283,20 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       fold_o(n_units - 1);
       finish_item(blockIdx.x + (my_items - 1) * gridDim.x);
     }
+    if (p.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+      atomicAdd(&p.dbg[0], (unsigned long long)c_ws); atomicAdd(&p.dbg[1], (unsigned long long)c_wo); atomicAdd(&p.dbg[2], (unsigned long long)c_bar);
+      atomicAdd(&p.dbg[3], (unsigned long long)(clock64() - c_t0));
+    }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc<512>(tmem0);
+  if (warp == 16) tmem_dealloc<512>(tmem0);
 }
 
 inline int attention_tc(Device& dev, cudaStream_t st, const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* vt, const uint8_t* key_mask,
                         __nv_bfloat16* out, int B, int H, int Lq, int Lk, int Lkpad, int dh, int dhp, int dvp, float scale) {
   if (dhp != 64 && dhp != 128) return fail(EZB_ERR_UNSUPPORTED, "attention_tc: dhp %d", dhp);
-  if (dvp % 16 || dvp > 80 || dvp < 16 || (dvp / 2) % 8) return fail(EZB_ERR_UNSUPPORTED, "attention_tc: dvp %d", dvp);
+  if (dvp % 16 || dvp > 80 || dvp < 16 || (dvp / 4) % 4) return fail(EZB_ERR_UNSUPPORTED, "attention_tc: dvp %d", dvp);
   const CUtensorMap *tq, *tk, *tv;
   EZB_TRY(dev.tmaps.get3d(q, dhp, Lq, (uint64_t)B * H, dhp, (uint64_t)Lq * dhp, AT_BQ, &tq));
   EZB_TRY(dev.tmaps.get3d(k, dhp, Lk, (uint64_t)B * H, dhp, (uint64_t)Lk * dhp, AT_BK, &tk));
@@ -283,6 +306,7 @@ inline int attention_tc(Device& dev, cudaStream_t st, const __nv_bfloat16* q, co
   p.n_qt = (Lq + AT_BQ - 1) / AT_BQ;
   p.n_items = p.n_qt * B * H;
   p.scale_log2 = scale * 1.4426950408889634f;
+  p.dbg = gemm_dbg_buf();
   const int grid = p.n_items < dev.num_sms ? p.n_items : dev.num_sms;
   ++launch_counter();
   if (dhp == 64) {

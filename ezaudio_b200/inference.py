@@ -44,7 +44,8 @@ def _ddim_step(model_out, latents, noise, B, Cc, L, gs, gr, coef):
 @torch.no_grad()
 def sample_latents(unet, noise_scheduler, text, text_mask, uncond_text=None, uncond_mask=None, gt=None, gt_mask=None,
                    audio_frames=500, guidance_scale=3, guidance_rescale=0.0, ddim_steps=50, eta=1, random_seed=2024,
-                   controlnet=None, condition=None, conditioning_scale=1.0, init_noise=None, step_noise=None, device="cuda"):
+                   controlnet=None, condition=None, conditioning_scale=1.0, init_noise=None, step_noise=None, device="cuda",
+                   use_graphs=True):
     """Denoising loop on cached text embeddings.  text (B,Lc,ctx) / text_mask (B,Lc); uncond_* (1 or B rows) when
     guidance_scale is truthy.  gt / gt_mask (B,C,L) for inpainting.  Returns the final latents (B,C,L) fp32 on device.
     `init_noise` / `step_noise` inject the RNG draws (parity tests); otherwise per-prompt generators are used."""
@@ -99,30 +100,73 @@ def sample_latents(unet, noise_scheduler, text, text_mask, uncond_text=None, unc
         cond_c = torch.cat([cond, cond], 0).contiguous() if use_cfg else cond.contiguous()
         skips = [torch.empty(Be, L, unet.cfg["embed_dim"], device=device, dtype=torch.float32) for _ in range(controlnet.half)]
 
-    x_in = torch.empty(Be, Cc, L, device=device, dtype=torch.float32) if use_cfg else None
-    out = torch.empty(Be, Cc, L, device=device, dtype=torch.float32)
-    noise_buf = torch.empty(B, Cc, L, device=device, dtype=torch.float32) if (eta and eta > 0) else None
-    for i, t in enumerate(timesteps):
+    # ---- the loop.  Every step is the same launch sequence on static buffers, so each step index is captured once into a
+    # CUDA graph (per shape / schedule) and replayed: ~500 kernel launches per step collapse into one graph launch.
+    key = (B, L, tuple(timesteps), use_cfg, float(guidance_scale or 0.0), float(guidance_rescale or 0.0), float(eta or 0.0), gt is not None,
+           id(controlnet) if controlnet is not None else 0, float(conditioning_scale))
+    cache = unet.__dict__.setdefault("_loop_cache", {})
+    st = cache.get(key) if use_graphs else None
+    if st is None:
+        st = dict(lat=torch.empty(B, Cc, L, device=device, dtype=torch.float32),
+                  x_in=torch.empty(Be, Cc, L, device=device, dtype=torch.float32) if use_cfg else None,
+                  out=torch.empty(Be, Cc, L, device=device, dtype=torch.float32),
+                  noise=torch.empty(B, Cc, L, device=device, dtype=torch.float32) if (eta and eta > 0) else None,
+                  gt=None if gt_c is None else torch.empty_like(gt_c), m8=None if m8 is None else torch.empty_like(m8),
+                  cond=None, skips=None, graphs=[None] * len(timesteps), launches=[0] * len(timesteps))
+        if controlnet is not None:
+            st["cond"] = torch.empty_like(cond_c)
+            st["skips"] = skips
+        if use_graphs:
+            if len(cache) >= 4:
+                cache.clear()
+            cache[key] = st
+    st["lat"].copy_(latents)
+    if gt_c is not None:
+        st["gt"].copy_(gt_c)
+        st["m8"].copy_(m8)
+    if controlnet is not None:
+        st["cond"].copy_(cond_c)
+    lat, x_in, out, noise_buf = st["lat"], st["x_in"], st["out"], st["noise"]
+
+    def one_step(i, t):
         if use_cfg:
-            x_in[:B].copy_(latents)
-            x_in[B:].copy_(latents)
+            x_in[:B].copy_(lat)
+            x_in[B:].copy_(lat)
             xi = x_in
         else:
-            xi = latents
+            xi = lat
         sk = None
         if controlnet is not None:
-            sk = controlnet.forward_step(xi, i, cond_c, conditioning_scale, gt=gt_c, gt_mask_u8=m8, outs=skips)
-        unet.forward_step(xi, i, gt=gt_c, gt_mask_u8=m8, controlnet_skips=sk, out=out)
+            sk = controlnet.forward_step(xi, i, st["cond"], conditioning_scale, gt=st["gt"], gt_mask_u8=st["m8"], outs=st["skips"])
+        unet.forward_step(xi, i, gt=st["gt"], gt_mask_u8=st["m8"], controlnet_skips=sk, out=out)
         coef = noise_scheduler.step_coefficients(t, float(eta or 0.0))
-        nz = None
-        if noise_buf is not None:
+        _ddim_step(out, lat, noise_buf, B, Cc, L, guidance_scale if use_cfg else 0.0, guidance_rescale, coef)
+
+    L_ = _lib.lib()
+    for i, t in enumerate(timesteps):
+        if noise_buf is not None:  # RNG stays in PyTorch, outside the graph
             if step_noise is not None:
                 noise_buf.copy_(step_noise[i])
             else:
                 for b, g in enumerate(gens):
                     noise_buf[b:b + 1].normal_(generator=g)
-            nz = noise_buf
-        _ddim_step(out, latents, nz, B, Cc, L, guidance_scale if use_cfg else 0.0, guidance_rescale, coef)
+        if not use_graphs:
+            one_step(i, t)
+            continue
+        if st["graphs"][i] is None:
+            one_step(i, t)  # eager first pass: warms caches (tensor maps, function attributes) and IS this step's result
+            snap = lat.clone()
+            g = torch.cuda.CUDAGraph()
+            n0 = L_.ezb_launch_count()
+            with torch.cuda.graph(g):
+                one_step(i, t)
+            st["launches"][i] = int(L_.ezb_launch_count() - n0)
+            st["graphs"][i] = g
+            lat.copy_(snap)  # capture does not execute; keep the eager result
+        else:
+            st["graphs"][i].replay()
+            L_.ezb_launch_count_add(st["launches"][i])
+    latents = lat.clone()
     if gt is not None:  # src/inference.py:104-105: pred[~gt_mask] = gt[~gt_mask]
         latents = torch.where(gt_mask.to(device).bool().expand_as(latents), latents, gt)
     return latents

@@ -118,6 +118,7 @@ int ezb_set_option(const char* name, int value);
 int ezb_debug_read(unsigned long long* out8);
 /* accounting: kernels launched by this library so far (process-wide); per-GEMM CUDA-event timing for bench.py's roofline leg */
 unsigned long long ezb_launch_count(void);
+void ezb_launch_count_add(unsigned long long n); /* launches replayed from a captured CUDA graph */
 int ezb_prof_gemm_begin(void);
 int ezb_prof_gemm_end(int* launches, double* flops, double* ms);
 
