@@ -84,6 +84,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem0 = *tmem_slot;  // S[0] @0, S[1] @128, O[0] @256, O[1] @384
+  pdl_launch();
+  pdl_wait();
 
   if (warp == 17) {
     // ------------------------------------------------ TMA producer
@@ -108,13 +110,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     // ------------------------------------------------ MMA issuer
     if (lane == 0) {
       const uint32_t idesc_s = umma_idesc_bf16(AT_BQ, AT_BK), idesc_o = umma_idesc_bf16(AT_BQ, p.dvp);
-      long long m_wkv = 0, m_wp = 0;
-      const long long m_t0 = clock64();
+      EZB_DBG(long long m_wkv = 0, m_wp = 0; const long long m_t0 = clock64();)
       auto issue_pv = [&](int u) {  // O[u%2] = P_u V_u ; frees kv stage u%2
         const int s = u & 1;
-        const long long tq = clock64();
+        EZB_DBG(const long long tq = clock64();)
         mbar_wait(p_full, u & 1);
-        m_wp += clock64() - tq;
+        EZB_DBG(m_wp += clock64() - tq;)
         tc_fence_after();
         for (int hh = 0; hh < 2; ++hh) {
           const uint64_t pd = umma_desc_sw128(smem_u32(sP + hh * 16384)), vd = umma_desc_sw128(smem_u32(sV + s * VB + hh * (VB / 2)));
@@ -129,9 +130,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         mbar_wait(&q_full[qb], (it >> 1) & 1);
         for (int j = 0; j < n_kv; ++j, ++u) {
           const int s = u & 1;
-          const long long tq = clock64();
+          EZB_DBG(const long long tq = clock64();)
           mbar_wait(&kv_full[s], (u >> 1) & 1);
-          m_wkv += clock64() - tq;
+          EZB_DBG(m_wkv += clock64() - tq;)
           tc_fence_after();
           for (int kh = 0; kh < KH; ++kh) {
             const uint64_t qd = umma_desc_sw128(smem_u32(sQ + qb * SM::Q_BYTES + kh * 16384));
@@ -145,9 +146,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         }
       }
       if (n_units > 0) issue_pv(n_units - 1);
-      if (p.dbg != nullptr && blockIdx.x == 0) {
+      EZB_DBG(if (p.dbg != nullptr && blockIdx.x == 0) {
         atomicAdd(&p.dbg[4], (unsigned long long)m_wkv); atomicAdd(&p.dbg[5], (unsigned long long)m_wp); atomicAdd(&p.dbg[6], (unsigned long long)(clock64() - m_t0));
-      }
+      })
     }
   } else {
     // ------------------------------------------------ softmax / accumulate
@@ -156,17 +157,16 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const uint32_t t_row = static_cast<uint32_t>(lg * 32) << 16;
     const int ocn = p.dvp / 4;                     // 16 or 20 O columns per thread
     const int oc0 = cq * ocn;
-    long long c_ws = 0, c_wo = 0, c_bar = 0;
-    const long long c_t0 = clock64();
+    EZB_DBG(long long c_ws = 0, c_wo = 0, c_bar = 0; const long long c_t0 = clock64();)
     float m_run = -INFINITY, l_run = 0.f;
     float o[20];
 #pragma unroll
     for (int i = 0; i < 20; ++i) o[i] = 0.f;
 
     auto fold_o = [&](int u) {  // o += O_u (TMEM O[u%2]) once P_u V_u has completed
-      const long long tq = clock64();
+      EZB_DBG(const long long tq = clock64();)
       mbar_wait(&o_full[u & 1], (u >> 1) & 1);
-      c_wo += clock64() - tq;
+      EZB_DBG(c_wo += clock64() - tq;)
       tc_fence_after();
       const uint32_t ta = tmem0 + 256 + (u & 1) * 128 + t_row + oc0;
       uint32_t orr[16], t4[4];
@@ -208,9 +208,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       const uint8_t* km = p.key_mask ? p.key_mask + (size_t)b * p.Lk : nullptr;
       for (int j = 0; j < n_kv; ++j, ++u) {
         // ---- 1. scores of this unit
-        long long tq = clock64();
+        EZB_DBG(long long tq = clock64();)
         mbar_wait(&s_full[u & 1], (u >> 1) & 1);
-        c_ws += clock64() - tq;
+        EZB_DBG(c_ws += clock64() - tq;)
         tc_fence_after();
         uint32_t sr[32];
         tmem_ld_32x32(tmem0 + (u & 1) * 128 + t_row + cq * 32, sr);
@@ -239,9 +239,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
         float* xm = sx + (u & 1) * 512;
         xm[cq * 128 + r] = mx;
-        tq = clock64();
+        EZB_DBG(tq = clock64();)
         named_bar_sync(1, AT_SOFTMAX_THREADS);
-        c_bar += clock64() - tq;
+        EZB_DBG(c_bar += clock64() - tq;)
         const float m_blk = fmaxf(fmaxf(xm[r], xm[128 + r]), fmaxf(xm[256 + r], xm[384 + r]));
         // ---- 2. previous unit's P V product: fold into the accumulator (and close the previous item)
         if (u > 0) {
@@ -283,10 +283,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       fold_o(n_units - 1);
       finish_item(blockIdx.x + (my_items - 1) * gridDim.x);
     }
-    if (p.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+    EZB_DBG(if (p.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
       atomicAdd(&p.dbg[0], (unsigned long long)c_ws); atomicAdd(&p.dbg[1], (unsigned long long)c_wo); atomicAdd(&p.dbg[2], (unsigned long long)c_bar);
       atomicAdd(&p.dbg[3], (unsigned long long)(clock64() - c_t0));
-    }
+    })
   }
   tc_fence_before();
   __syncthreads();
@@ -308,17 +308,16 @@ inline int attention_tc(Device& dev, cudaStream_t st, const __nv_bfloat16* q, co
   p.scale_log2 = scale * 1.4426950408889634f;
   p.dbg = gemm_dbg_buf();
   const int grid = p.n_items < dev.num_sms ? p.n_items : dev.num_sms;
-  ++launch_counter();
   if (dhp == 64) {
     const int smem = AttnSmem<1>::total(dvp);
     static bool set = false;
     if (!set) { EZB_CUDA(cudaFuncSetAttribute(attn_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem<1>::total(80))); set = true; }
-    attn_tc_kernel<1><<<grid, AT_THREADS, smem, st>>>(*tq, *tk, *tv, p);
+    EZB_TRY(launch_k(attn_tc_kernel<1>, dim3(grid), dim3(AT_THREADS), smem, st, 1, *tq, *tk, *tv, p));
   } else {
     const int smem = AttnSmem<2>::total(dvp);
     static bool set = false;
     if (!set) { EZB_CUDA(cudaFuncSetAttribute(attn_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem<2>::total(80))); set = true; }
-    attn_tc_kernel<2><<<grid, AT_THREADS, smem, st>>>(*tq, *tk, *tv, p);
+    EZB_TRY(launch_k(attn_tc_kernel<2>, dim3(grid), dim3(AT_THREADS), smem, st, 1, *tq, *tk, *tv, p));
   }
   EZB_CUDA(cudaGetLastError());
   return EZB_OK;

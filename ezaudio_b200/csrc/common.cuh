@@ -18,6 +18,13 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// ------------------------------------------------------------------ programmatic dependent launch (PDL)
+// Kernels launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while their predecessor drains:
+// pdl_launch() lets the successor be scheduled, pdl_wait() blocks until every prerequisite grid has completed and its
+// writes are visible.  Both are no-ops for a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ------------------------------------------------------------------ mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));

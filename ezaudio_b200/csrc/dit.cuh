@@ -332,10 +332,11 @@ struct Dit {
     LnParams p;
     p.x = x; p.x2 = x2; p.x3 = x3; p.D1 = D1; p.D2 = D2; p.w = w; p.b = b; p.shift = shift; p.scale = scale; p.mod_bstride = mod_bstride;
     p.rows_per_batch = rows_per_batch; p.out = out; p.kmul = kmul; p.M = M;
-    ++launch_counter();
-    ln_mod_cast_kernel<<<(M + 7) / 8, 256, 0, st>>>(p);
-    EZB_CUDA(cudaGetLastError());
-    return EZB_OK;
+    if (kmul == 1 && x2 == nullptr && w != nullptr && (D1 == 1152 || D1 == 1024)) {
+      if (D1 == 1152) return launch_k(ln_mod_cast_reg_kernel<9>, dim3((M + 3) / 4), dim3(128), 0, st, 1, p);
+      return launch_k(ln_mod_cast_reg_kernel<8>, dim3((M + 3) / 4), dim3(128), 0, st, 1, p);
+    }
+    return launch_k(ln_mod_cast_kernel, dim3((M + 7) / 8), dim3(256), 0, st, 1, p);
   }
   EpiLinearParams epi() {
     EpiLinearParams e;
@@ -566,9 +567,7 @@ struct Dit {
   int embed(cudaStream_t st, const float* x, const float* gt, const uint8_t* gt_mask, const float* resid, int Be, int L) {
     dim3 grid((L + 31) / 32, (2 * C) / 32, Be), blockd(32, 8);
     if ((2 * C) % 32) return fail(EZB_ERR_UNSUPPORTED, "latent_chans must be a multiple of 16");
-    ++launch_counter();
-    patch_pack_kernel<<<grid, blockd, 0, st>>>(x, gt, gt_mask, mask_embed, a_patch, Be, C, L, Kp, kmul);
-    EZB_CUDA(cudaGetLastError());
+    EZB_TRY(launch_k(patch_pack_kernel, grid, blockd, 0, st, 1, x, gt, gt_mask, (const float*)mask_embed, a_patch, Be, C, L, Kp, kmul));
     EpiLinearParams e = epi();
     e.bias = b_patch; e.out_f32 = x0; e.ld32 = D; e.resid = resid; e.ldr = D;
     return lin(st, a_patch, Kp, w_patch, Be * L, D, e);
@@ -609,9 +608,7 @@ struct Dit {
     EZB_TRY(lin(st, act, D, w_final, M, C, e));
     dim3 grid((L + 31) / 32, Be);
     const size_t smem = (size_t)34 * C * sizeof(float);
-    ++launch_counter();
-    final_conv_kernel<<<grid, 128, smem, st>>>(ybuf, fc_w, fc_b, out, Be, C, L);
-    EZB_CUDA(cudaGetLastError());
+    EZB_TRY(launch_k(final_conv_kernel, grid, dim3(128), smem, st, 1, (const float*)ybuf, (const float*)fc_w, (const float*)fc_b, out, Be, C, L));
     return EZB_OK;
   }
 

@@ -38,6 +38,8 @@ struct LnParams {
 };
 
 __global__ void __launch_bounds__(256) ln_mod_cast_kernel(const LnParams p) {
+  pdl_launch();
+  pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= p.M) return;
   const int D = p.D1 + p.D2;
@@ -93,6 +95,52 @@ __global__ void __launch_bounds__(256) ln_mod_cast_kernel(const LnParams p) {
     }
 #pragma unroll
     for (int e = 0; e < 4; ++e) store_act(o, c + e, D, p.kmul, y[e]);
+  }
+}
+
+// Register-resident variant for the hot shapes (single source, D = 128 * NCH): the row is read once, both moments come
+// from registers (two-pass formula, same numerics as above), 8-byte bf16 stores.  One warp per row, 4 rows per 128-thread block.
+template <int NCH>
+__global__ void __launch_bounds__(128) ln_mod_cast_reg_kernel(const LnParams p) {
+  pdl_launch();
+  pdl_wait();
+  const int row = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= p.M) return;
+  constexpr int D = NCH * 128;
+  const float4* x = reinterpret_cast<const float4*>(p.x + (size_t)row * D);
+  float4 v[NCH];
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) v[i] = x[lane + 32 * i];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  const float mean = warp_sum(s) * (1.0f / D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + 1e-5f);
+  const float4 *w4 = reinterpret_cast<const float4*>(p.w), *b4 = reinterpret_cast<const float4*>(p.b);
+  const float4 *sh4 = nullptr, *sc4 = nullptr;
+  if (p.shift) {
+    const size_t off = (size_t)(row / p.rows_per_batch) * p.mod_bstride;
+    sh4 = reinterpret_cast<const float4*>(p.shift + off);
+    sc4 = reinterpret_cast<const float4*>(p.scale + off);
+  }
+  __nv_bfloat16* o = p.out + (size_t)row * D;
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) {
+    const int c4 = lane + 32 * i;
+    const float4 w = __ldg(w4 + c4), b = __ldg(b4 + c4);
+    float y0 = (v[i].x - mean) * rstd * w.x + b.x, y1 = (v[i].y - mean) * rstd * w.y + b.y;
+    float y2 = (v[i].z - mean) * rstd * w.z + b.z, y3 = (v[i].w - mean) * rstd * w.w + b.w;
+    if (sh4) {
+      const float4 a = __ldg(sc4 + c4), d = __ldg(sh4 + c4);
+      y0 = y0 * (1.f + a.x) + d.x; y1 = y1 * (1.f + a.y) + d.y; y2 = y2 * (1.f + a.z) + d.z; y3 = y3 * (1.f + a.w) + d.w;
+    }
+    *reinterpret_cast<uint2*>(o + 4 * c4) = make_uint2(pack_bf16(y0, y1), pack_bf16(y2, y3));
   }
 }
 
@@ -194,6 +242,8 @@ __global__ void __launch_bounds__(256) qk_prep_kernel(const QkPrepParams<TIn> p)
 //   mask channel = gt ? gt_mask[b,l] : 1          (mae_mask[:,0:1,:]: ones when gt is None)
 __global__ void patch_pack_kernel(const float* __restrict__ x, const float* __restrict__ gt, const uint8_t* __restrict__ gt_mask,
                                   const float* __restrict__ mask_embed, __nv_bfloat16* __restrict__ out, int B, int C, int L, int Kp, int kmul) {
+  pdl_launch();
+  pdl_wait();
   __shared__ float tile[32][33];
   const int b = blockIdx.z, l0 = blockIdx.x * 32, c0 = blockIdx.y * 32;  // c0 over 2C channels
   const int tx = threadIdx.x, ty = threadIdx.y;                            // 32 x 8
@@ -231,6 +281,8 @@ __global__ void patch_pack_kernel(const float* __restrict__ x, const float* __re
 // w packed [3][Cin][Cout] so consecutive threads (co) read consecutive addresses.
 __global__ void __launch_bounds__(128) final_conv_kernel(const float* __restrict__ y, const float* __restrict__ wp, const float* __restrict__ bias,
                                                          float* __restrict__ out, int B, int C, int L) {
+  pdl_launch();
+  pdl_wait();
   extern __shared__ float sy[];  // [(TL + 2)][C]
   constexpr int TL = 32;
   const int b = blockIdx.y, l0 = blockIdx.x * TL;

@@ -20,6 +20,11 @@ namespace ezb {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
+#ifdef EZB_GEMM_DEBUG
+#define EZB_DBG(...) __VA_ARGS__
+#else
+#define EZB_DBG(...)
+#endif
 constexpr int GEMM_SMEM_BUDGET = 227 * 1024 - 2048;  // dynamic smem per CTA minus alignment slack and barriers
 
 struct GemmShape {
@@ -325,10 +330,15 @@ struct EpiGeglu {
   }
 };
 
-template <int BN, class Epi, bool PAIR>
+// KSUB: 64-wide K sub-tiles per pipeline stage.  The single MMA thread pays ~250 cycles of fixed cost per stage (mbarrier
+// wait, fence, two commits); with N <= 144 a 64-deep stage is only 4 x 64..72 cycles of tensor work, so narrow tiles use
+// 128-deep stages (KSUB = 2) to keep the issue loop off the critical path.
+template <int BN, class Epi, bool PAIR, int KSUB = 1>
 struct GemmCfg {
-  static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
-  static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * GEMM_BK * 2;
+  static constexpr int A_SUB = GEMM_BM * GEMM_BK * 2;
+  static constexpr int B_SUB = (PAIR ? BN / 2 : BN) * GEMM_BK * 2;
+  static constexpr int A_BYTES = KSUB * A_SUB;
+  static constexpr int B_BYTES = KSUB * B_SUB;
   static constexpr int EPI_WARPS = Epi::EPI_WARPS;
   static constexpr int THREADS = 64 + 32 * EPI_WARPS;
   static constexpr int STAGE_BYTES = EPI_WARPS * Epi::STAGE_FLOATS * 4;   // one transpose tile per epilogue warp
@@ -379,6 +389,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch();
+  pdl_wait();  // everything above overlapped the previous kernel's tail; global memory is touched only below
 
   if (warp == 0) {
     // ------------------------------------------------ TMA producer
@@ -563,11 +575,11 @@ namespace ezb {
 // 128 rows of A and rows [r*BN/2, (r+1)*BN/2) of the W tile; the leader's single MMA thread issues M=256 instructions that
 // read both CTAs' shared memory, so each SM pulls half the operand bytes per flop through L2 (the 128x128 single-CTA tile
 // is L2->smem bound at ~64 flop/B).  Accumulator rows 128r..128r+127 live in CTA r's TMEM; both CTAs run the epilogue.
-template <int BN, class Epi>
-__global__ void __launch_bounds__((GemmCfg<BN, Epi, true>::THREADS), 1)
+template <int BN, class Epi, int KSUB>
+__global__ void __launch_bounds__((GemmCfg<BN, Epi, true, KSUB>::THREADS), 1)
 gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmShape g, const typename Epi::Params ep) {
   static_assert(BN % 16 == 0 && BN >= 64 && BN <= 256, "BN");
-  using SM = GemmCfg<BN, Epi, true>;
+  using SM = GemmCfg<BN, Epi, true, KSUB>;
   constexpr int STAGES = SM::STAGES;
   constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   extern __shared__ uint8_t smem_raw[];
@@ -606,9 +618,9 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const bool dbg = g.dbg != nullptr && blockIdx.x == 0;
-  const long long t_start = clock64();
-  long long w0 = 0, w1 = 0;
+  pdl_launch();
+  pdl_wait();
+  EZB_DBG(const bool dbg = g.dbg != nullptr && blockIdx.x == 0; const long long t_start = clock64(); long long w0 = 0, w1 = 0;)
 
   if (warp == 0) {
     // ------------------------------------------------ TMA producer (both CTAs; bytes are credited to the leader's barrier)
@@ -617,14 +629,17 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
         const int mt = tile % g.num_m_tiles, nt = tile / g.num_m_tiles;
         const int m0 = mt * 2 * GEMM_BM + (int)rank * GEMM_BM, n0 = nt * BN + (int)rank * (BN / 2);
-        for (int kb = 0; kb < g.num_k_blocks; ++kb) {
-          const long long tq = clock64();
+        for (int kb = 0; kb < g.num_k_blocks; kb += KSUB) {
+          EZB_DBG(const long long tq = clock64();)
           mbar_wait(&empty[stage], phase ^ 1);
-          w0 += clock64() - tq;
+          EZB_DBG(w0 += clock64() - tq;)
           const uint32_t bar = mapa_u32(smem_u32(&full[stage]), 0);
-          if (leader) mbar_expect_tx(&full[stage], 2 * (SM::A_BYTES + SM::B_BYTES));
-          tma_load_2d_pair(sA + stage * SM::A_BYTES, &tmA, bar, kb * GEMM_BK, m0);
-          tma_load_2d_pair(sB + stage * SM::B_BYTES, &tmB, bar, kb * GEMM_BK, n0);
+          const int nsub = (g.num_k_blocks - kb) < KSUB ? (g.num_k_blocks - kb) : KSUB;
+          if (leader) mbar_expect_tx(&full[stage], 2 * nsub * (SM::A_SUB + SM::B_SUB));
+          for (int sub = 0; sub < nsub; ++sub) {
+            tma_load_2d_pair(sA + stage * SM::A_BYTES + sub * SM::A_SUB, &tmA, bar, (kb + sub) * GEMM_BK, m0);
+            tma_load_2d_pair(sB + stage * SM::B_BYTES + sub * SM::B_SUB, &tmB, bar, (kb + sub) * GEMM_BK, n0);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -635,23 +650,26 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       constexpr uint32_t idesc = umma_idesc_bf16(2 * GEMM_BM, BN);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-        long long tq = clock64();
+        EZB_DBG(long long tq = clock64();)
         mbar_wait(&tempty[acc], acc_phase ^ 1);
-        w1 += clock64() - tq;
+        EZB_DBG(w1 += clock64() - tq;)
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < g.num_k_blocks; ++kb) {
-          tq = clock64();
+        for (int kb = 0; kb < g.num_k_blocks; kb += KSUB) {
+          EZB_DBG(tq = clock64();)
           mbar_wait(&full[stage], phase);
-          w0 += clock64() - tq;
+          EZB_DBG(w0 += clock64() - tq;)
           tc_fence_after();
           if (lane == 0) {
-            const uint64_t ad = umma_desc_sw128(smem_u32(sA + stage * SM::A_BYTES));
-            const uint64_t bd = umma_desc_sw128(smem_u32(sB + stage * SM::B_BYTES));
+            const int nsub = (g.num_k_blocks - kb) < KSUB ? (g.num_k_blocks - kb) : KSUB;
+            for (int sub = 0; sub < nsub; ++sub) {
+              const uint64_t ad = umma_desc_sw128(smem_u32(sA + stage * SM::A_BYTES + sub * SM::A_SUB));
+              const uint64_t bd = umma_desc_sw128(smem_u32(sB + stage * SM::B_BYTES + sub * SM::B_SUB));
 #pragma unroll
-            for (int k = 0; k < GEMM_BK / 16; ++k) umma_bf16_pair(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
+              for (int k = 0; k < GEMM_BK / 16; ++k) umma_bf16_pair(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (kb | sub | k) != 0);
+            }
             umma_commit_pair(&empty[stage]);
-            if (kb == g.num_k_blocks - 1) umma_commit_pair(&tfull[acc]);
+            if (kb + KSUB >= g.num_k_blocks) umma_commit_pair(&tfull[acc]);
           }
           __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -672,27 +690,25 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       const int ch = (warp - 2) >> 2;
       uint64_t* tf = &tfull[acc];
       const uint32_t ph = acc_phase;
-      const long long te = clock64();
-      long long tw = 0;
-      Epi::run(ep, sStage + (warp - 2) * Epi::STAGE_FLOATS, taddr_row, row0, g.M - row0, nt * BN, g.N, lane, ch * CW, (ch + 1) * CW, [tf, ph, &tw]() {
-        const long long tq = clock64();
+      EZB_DBG(const long long te = clock64(); long long tw = 0;)
+      Epi::run(ep, sStage + (warp - 2) * Epi::STAGE_FLOATS, taddr_row, row0, g.M - row0, nt * BN, g.N, lane, ch * CW, (ch + 1) * CW, [&]() {
+        EZB_DBG(const long long tq = clock64();)
         mbar_wait(tf, ph);
-        tw = clock64() - tq;
+        EZB_DBG(tw = clock64() - tq;)
         tc_fence_after();
       });
-      w0 += tw;
-      w1 += clock64() - te - tw;
+      EZB_DBG(w0 += tw; w1 += clock64() - te - tw;)
       tc_fence_before();
       mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[acc]), 0));
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
   }
-  if (dbg && lane == 0) {
+  EZB_DBG(if (dbg && lane == 0) {
     if (warp == 0) atomicAdd(&g.dbg[2], (unsigned long long)w0);
     if (warp == 1) { atomicAdd(&g.dbg[0], (unsigned long long)w0); atomicAdd(&g.dbg[1], (unsigned long long)w1); }
     if (warp == 2) { atomicAdd(&g.dbg[3], (unsigned long long)w0); atomicAdd(&g.dbg[4], (unsigned long long)w1); atomicAdd(&g.dbg[5], (unsigned long long)(clock64() - t_start)); }
-  }
+  })
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();

@@ -10,6 +10,7 @@
 #include <map>
 #include <string>
 #include <tuple>
+#include <utility>
 #include <vector>
 
 #include "../../include/ezb200.h"
@@ -145,6 +146,27 @@ struct Device {
   TmapCache tmaps;
 };
 
+inline int& opt_pdl() {
+  static int v = 1;
+  return v;
+}
+// Launch through cudaLaunchKernelEx with the programmatic-stream-serialization attribute (kernels launched this way MUST call
+// pdl_wait() before touching global memory) and an optional cluster dimension.
+template <typename... KArgs, typename... Args>
+int launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (cluster > 1) { attr[n].id = cudaLaunchAttributeClusterDimension; attr[n].val.clusterDim.x = cluster; attr[n].val.clusterDim.y = 1; attr[n].val.clusterDim.z = 1; ++n; }
+  if (opt_pdl()) { attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[n].val.programmaticStreamSerializationAllowed = 1; ++n; }
+  cfg.attrs = attr; cfg.numAttrs = n;
+  ++launch_counter();
+  EZB_CUDA(cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...));
+  return EZB_OK;
+}
+
 struct ConvAddr {  // implicit-GEMM addressing of A, see gemm.cuh
   int taps = 0, center = 0, dilation = 1, cin_pad = 0, T = 0, B = 0;
 };
@@ -173,15 +195,13 @@ int launch_gemm_t(Device& dev, cudaStream_t st, const CUtensorMap* tA, const CUt
     gp.flops.push_back(2.0 * (double)g.M * (double)g.N * (double)g.num_k_blocks * GEMM_BK);
     EZB_CUDA(cudaEventRecord(e0, st));
   }
-  ++launch_counter();
-  kern<<<grid, GEMM_THREADS, smem, st>>>(*tA, *tB, g, ep);
+  EZB_TRY(launch_k(kern, dim3(grid), dim3(GEMM_THREADS), smem, st, 1, *tA, *tB, g, ep));
   if (gp.on) EZB_CUDA(cudaEventRecord(e1, st));
-  EZB_CUDA(cudaGetLastError());
   return EZB_OK;
 }
 
 // CTA-pair GEMM launch: 256 x BN tiles, cluster (2,1,1), one pair per TPC.
-template <int BN, class Epi>
+template <int BN, class Epi, int KSUB = (BN <= 144 ? 2 : 1)>
 int gemm2(Device& dev, cudaStream_t st, const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, int M, int N, int K,
           const typename Epi::Params& ep) {
   if (M <= 0 || N <= 0 || K <= 0) return fail(EZB_ERR_SHAPE, "gemm2: empty problem %d %d %d", M, N, K);
@@ -196,9 +216,9 @@ int gemm2(Device& dev, cudaStream_t st, const __nv_bfloat16* A, int lda, const _
   const CUtensorMap *tA, *tB;
   EZB_TRY(dev.tmaps.get2d(A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, GEMM_BM, &tA));
   EZB_TRY(dev.tmaps.get2d(W, (uint64_t)K, (uint64_t)N, (uint64_t)ldw, BN / 2, &tB));
-  auto kern = gemm2_tcgen05_kernel<BN, Epi>;
-  constexpr int smem = GemmCfg<BN, Epi, true>::BYTES;
-  constexpr int GEMM_THREADS = GemmCfg<BN, Epi, true>::THREADS;
+  auto kern = gemm2_tcgen05_kernel<BN, Epi, KSUB>;
+  constexpr int smem = GemmCfg<BN, Epi, true, KSUB>::BYTES;
+  constexpr int GEMM_THREADS = GemmCfg<BN, Epi, true, KSUB>::THREADS;
   static bool attr_set[16] = {};
   if (!attr_set[dev.id & 15]) {
     EZB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -206,16 +226,6 @@ int gemm2(Device& dev, cudaStream_t st, const __nv_bfloat16* A, int lda, const _
   }
   const int tiles = g.num_m_tiles * g.num_n_tiles, max_pairs = dev.num_sms / 2;
   const int pairs = tiles < max_pairs ? tiles : max_pairs;
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof cfg);
-  cfg.gridDim = dim3(2 * pairs);
-  cfg.blockDim = dim3(GEMM_THREADS);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
   GemmProf& gp = gemm_prof();
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (gp.on) {
@@ -227,8 +237,7 @@ int gemm2(Device& dev, cudaStream_t st, const __nv_bfloat16* A, int lda, const _
     gp.flops.push_back(2.0 * (double)M * (double)N * (double)g.num_k_blocks * GEMM_BK);
     EZB_CUDA(cudaEventRecord(e0, st));
   }
-  ++launch_counter();
-  EZB_CUDA(cudaLaunchKernelEx(&cfg, kern, *tA, *tB, g, ep));
+  EZB_TRY(launch_k(kern, dim3(2 * pairs), dim3(GEMM_THREADS), smem, st, 2, *tA, *tB, g, ep));
   if (gp.on) EZB_CUDA(cudaEventRecord(e1, st));
   return EZB_OK;
 }
