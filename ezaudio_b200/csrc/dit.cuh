@@ -68,6 +68,7 @@ struct Dit {
   float2* rope_cs = nullptr;
   bool fused_heads = false;
   bool pair = true;       // CTA-pair (cta_group::2) GEMMs
+  bool swap_ab = true;    // swap-AB tiles for the fp32-output N = D layers
   int geglu_bn = 128;     // N-tile of the GEGLU GEMM: packing group = geglu_bn / 2
 
   ~Dit() {
@@ -127,6 +128,7 @@ struct Dit {
     kmul = d.precision == 1 ? 3 : 1;
     if (d.precision != 0 && d.precision != 1) return fail(EZB_ERR_UNSUPPORTED, "precision %d", d.precision);
     pair = opt_pair_gemm() != 0;
+    swap_ab = opt_swap_ab() != 0;
     geglu_bn = (pair && inner % 128 == 0) ? 256 : 128;
     if (dh > 96 || dh % 8 || D % 16 || inner % 64 || d.context_dim % 8 || d.depth % 2)
       return fail(EZB_ERR_UNSUPPORTED, "unsupported dims: D %d dh %d inner %d ctx %d depth %d", D, dh, inner, d.context_dim, d.depth);
@@ -344,6 +346,9 @@ struct Dit {
     return e;
   }
   int lin(cudaStream_t st, const bf16* A, int K, const bf16* W, int M, int N, const EpiLinearParams& e) {
+    // fp32-output layers (residual / gated-residual / plain): swap-AB 128 x 256 tiles -- one full wave for N = 1152 at M = 4000
+    if (pair && swap_ab && kmul == 1 && e.out_bf16 == nullptr && e.out_f32 != nullptr && e.out_scale == 0.f && e.bias_mod == 0 && M >= 512)
+      return gemm_swapped<EpiLinearT<256>>(*dev, st, A, K, W, K, M, N, K, e);
     if (pair) return gemm2<128, EpiLinear<128>>(*dev, st, A, kmul * K, W, kmul * K, M, N, kmul * K, e);
     return gemm<128, EpiLinear<128>>(*dev, st, A, kmul * K, W, kmul * K, M, N, kmul * K, e);
   }

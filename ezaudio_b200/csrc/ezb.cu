@@ -46,6 +46,11 @@ __attribute__((visibility("default"))) int ezb_test_gemm(int device, const void*
   ConvAddr conv;
   conv.taps = conv_taps; conv.center = conv_center; conv.dilation = conv_dil; conv.cin_pad = conv_cin_pad; conv.T = conv_T; conv.B = conv_B;
   const ConvAddr* cp = conv_taps > 0 ? &conv : nullptr;
+  if (epi_kind == 20) {  // swap-AB: 128 features x 256 tokens tiles, fp32 output
+    if (cp) return fail(EZB_ERR_UNSUPPORTED, "swap-AB GEMM has no conv addressing");
+    EpiLinearParams p = to_epi(e);
+    return gemm_swapped<EpiLinearT<256>>(dev, st, a, lda, w, ldw, M, N, K, p);
+  }
   if (epi_kind == 10 || epi_kind == 11) {  // CTA-pair kernel (bn is the pair tile's N)
     if (cp) return fail(EZB_ERR_UNSUPPORTED, "pair GEMM has no conv addressing");
     if (epi_kind == 10) {
@@ -179,6 +184,7 @@ EZB_API int ezb_test_attention(int device, const void* q, const void* k, const v
 EZB_API int ezb_set_option(const char* name, int value) {
   if (name && !strcmp(name, "pair_gemm")) { opt_pair_gemm() = value; return EZB_OK; }
   if (name && !strcmp(name, "pdl")) { opt_pdl() = value; return EZB_OK; }
+  if (name && !strcmp(name, "swap_ab")) { opt_swap_ab() = value; return EZB_OK; }
   if (name && !strcmp(name, "gemm_debug")) {  // cycle counters of CTA 0 of every pair-GEMM launch (accumulated)
     if (value && !gemm_dbg_buf()) { EZB_CUDA(cudaMalloc(&gemm_dbg_buf(), 64)); EZB_CUDA(cudaMemset(gemm_dbg_buf(), 0, 64)); }
     if (!value && gemm_dbg_buf()) { cudaFree(gemm_dbg_buf()); gemm_dbg_buf() = nullptr; }

@@ -330,6 +330,62 @@ struct EpiGeglu {
   }
 };
 
+// ---------------------------------------------------------------------------------------------------------------
+// Transposed ("swap-AB") linear epilogue.  For N_out = 1152-wide layers the natural 128/144-column tiles leave the tensor
+// pipe ~55 % efficient (operand bytes per flop) and a 256-column tile does not divide 1152.  Computing C^T = W A^T instead
+// puts the 1152 output features on the accumulator ROWS (9 tiles of 128) and 256 tokens on the columns: 144 tiles of
+// 128 x 256 = one full wave on 148 SMs.  A thread now owns one output feature; for a given token the 32 lanes of a warp hold
+// 32 consecutive features, so residual loads and stores are 128-byte coalesced without any staging.
+template <int BN>
+struct EpiLinearT {
+  using Params = EpiLinearParams;   // bias/gate indexed by feature, resid/out_f32 [token, feature]; bf16/act/split unsupported
+  static constexpr int EPI_WARPS = 8;
+  static constexpr int STAGE_FLOATS = 0;
+  template <class Wait>
+  static __device__ __forceinline__ void run(const Params& ep, float* st, uint32_t taddr_row, int row0, int nvalid, int n0, int N, int lane, int c_begin,
+                                             int c_end, Wait wait) {
+    const int f = row0 + lane;                 // output feature of this thread
+    const bool f_ok = lane < nvalid;
+    const float bias = (ep.bias != nullptr && f_ok) ? ep.bias[f] : 0.f;
+    bool waited = false;
+#pragma unroll 1
+    for (int c = c_begin; c < c_end; c += 32) {
+      const int t0 = n0 + c;                   // first token of this chunk
+      if (t0 >= N) break;                      // warp-uniform
+      const int nt = (N - t0) < 32 ? (N - t0) : 32;
+      float x[32];
+      if (ep.resid != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] = (f_ok && j < nt) ? ep.resid[(size_t)(t0 + j) * ep.ldr + f] : 0.f;
+      }
+      float g0 = 1.f, g1 = 1.f;
+      int btok = 0x7fffffff;                   // first token that belongs to the second batch item of this chunk
+      if (ep.gate != nullptr && f_ok) {
+        const int b0i = t0 / ep.rows_per_batch;
+        btok = (b0i + 1) * ep.rows_per_batch;
+        g0 = 1.0f - ep.gate[(size_t)b0i * ep.gate_bstride + f];
+        if (btok < t0 + nt) g1 = 1.0f - ep.gate[(size_t)(b0i + 1) * ep.gate_bstride + f];
+      }
+      if (!waited) { wait(); waited = true; }
+      uint32_t r[32];
+      __syncwarp();
+      tmem_ld_32x32(taddr_row + c, r);
+      tmem_ld_wait();
+      if (f_ok) {
+        float* o = ep.out_f32 + (size_t)t0 * ep.ld32 + f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (j >= nt) break;
+          float v = __uint_as_float(r[j]) + bias;
+          if (ep.resid != nullptr) v = fmaf((t0 + j >= btok) ? g1 : g0, v, x[j]);
+          o[(size_t)j * ep.ld32] = v;
+        }
+      }
+    }
+    if (!waited) wait();
+  }
+};
+
 // KSUB: 64-wide K sub-tiles per pipeline stage.  The single MMA thread pays ~250 cycles of fixed cost per stage (mbarrier
 // wait, fence, two commits); with N <= 144 a 64-deep stage is only 4 x 64..72 cycles of tensor work, so narrow tiles use
 // 128-deep stages (KSUB = 2) to keep the issue loop off the critical path.

@@ -146,6 +146,10 @@ struct Device {
   TmapCache tmaps;
 };
 
+inline int& opt_swap_ab() {
+  static int v = 1;
+  return v;
+}
 inline int& opt_pdl() {
   static int v = 1;
   return v;
@@ -198,6 +202,27 @@ int launch_gemm_t(Device& dev, cudaStream_t st, const CUtensorMap* tA, const CUt
   EZB_TRY(launch_k(kern, dim3(grid), dim3(GEMM_THREADS), smem, st, 1, *tA, *tB, g, ep));
   if (gp.on) EZB_CUDA(cudaEventRecord(e1, st));
   return EZB_OK;
+}
+
+// Swap-AB launch: C[tokens, features] = A[tokens, K] W[features, K]^T computed as C^T tiles of 128 features x 256 tokens
+// (single-CTA kernel; W plays the M-side operand, the activations the N-side operand).
+template <class Epi>
+int gemm_swapped(Device& dev, cudaStream_t st, const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, int M_tokens, int N_features, int K,
+                 const typename Epi::Params& ep) {
+  if (M_tokens <= 0 || N_features <= 0 || K <= 0) return fail(EZB_ERR_SHAPE, "gemm_swapped: empty problem");
+  if ((K % 8) || (lda % 8) || (ldw % 8)) return fail(EZB_ERR_SHAPE, "gemm_swapped: K/ld must be multiples of 8");
+  constexpr int BN = 256;
+  GemmShape g;
+  memset(&g, 0, sizeof g);
+  g.M = N_features;
+  g.N = M_tokens;
+  g.num_m_tiles = (N_features + GEMM_BM - 1) / GEMM_BM;
+  g.num_n_tiles = (M_tokens + BN - 1) / BN;
+  g.num_k_blocks = (K + GEMM_BK - 1) / GEMM_BK;
+  const CUtensorMap *tA, *tB;
+  EZB_TRY(dev.tmaps.get2d(W, (uint64_t)K, (uint64_t)N_features, (uint64_t)ldw, GEMM_BM, &tA));
+  EZB_TRY(dev.tmaps.get2d(A, (uint64_t)K, (uint64_t)M_tokens, (uint64_t)lda, BN, &tB));
+  return launch_gemm_t<BN, Epi>(dev, st, tA, tB, g, ep);
 }
 
 // CTA-pair GEMM launch: 256 x BN tiles, cluster (2,1,1), one pair per TPC.

@@ -62,5 +62,8 @@ run(M, 1152, 1152, 128, 10, "pair proj bf16 128")
 run(M, 1152, 1152, 128, 10, "pair proj resid+gate 128", resid=True)
 run(M, 1152, 4608, 128, 10, "pair mlp2 resid+gate 128", resid=True)
 run(M, 1152, 4608, 128, 0, "1cta mlp2 resid+gate 128", resid=True)
+run(M, 1152, 1152, 256, 20, "swapAB proj resid+gate", resid=True)
+run(M, 1152, 4608, 256, 20, "swapAB mlp2 resid+gate", resid=True)
+run(M, 1152, 2304, 256, 20, "swapAB skip resid", resid=True)
 run(8192, 8192, 8192, 256, 10, "pair 8192^3 bf16 256", reps=5)
 run(8192, 8192, 8192, 128, 0, "1cta 8192^3 bf16 128", reps=5)

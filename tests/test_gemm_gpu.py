@@ -144,3 +144,27 @@ def test_pair_gemm_geglu():
     u = A.float() @ W.float().t() + bias
     ref = u[:, :inner] * torch.nn.functional.gelu(u[:, inner:])
     assert (out.float() - ref).abs().max().item() < 2e-2 * max(1.0, ref.abs().max().item() / 4)
+
+
+@pytest.mark.parametrize("M,N,K,L", [(4000, 1152, 1152, 500), (1000, 1152, 4608, 250), (300, 144, 144, 100), (777, 1024, 264, 259), (4000, 1152, 2304, 500)])
+def test_swap_ab_gemm_gated_residual(M, N, K, L):
+    """Swap-AB kernel (features on accumulator rows): bias + gated residual in place, and plain bias -> f32."""
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    W = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    x = torch.randn(M, N, device="cuda", generator=g)
+    nb = (M + L - 1) // L
+    gate = torch.randn(nb, 6 * N, device="cuda", generator=g) * 0.3
+    ref_mm = A.float() @ W.float().t() + bias
+    tol = 3e-3 * max(1.0, math.sqrt(K / 1024))
+    out = torch.full((M, N), float("nan"), device="cuda")
+    _run(A, W, _epi(bias=bias, out_f32=out, ld32=N), M, N, K, 256, kind=20)
+    assert (out - ref_mm).abs().max().item() < tol
+    x2 = x.clone()
+    _run(A, W, _epi(bias=bias, resid=x2, ldr=N, gate=gate[:, 5 * N:], gate_bstride=6 * N, rows_per_batch=L, out_f32=x2, ld32=N), M, N, K, 256, kind=20)
+    ref = x + (1 - gate[:, 5 * N:].repeat_interleave(L, 0)[:M]) * ref_mm
+    assert (x2 - ref).abs().max().item() < tol
+    x3 = x.clone()
+    _run(A, W, _epi(bias=bias, resid=x3, ldr=N, out_f32=x3, ld32=N), M, N, K, 256, kind=20)
+    assert (x3 - (x + ref_mm)).abs().max().item() < tol
