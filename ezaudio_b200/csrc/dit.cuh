@@ -23,6 +23,7 @@ struct BlockW {
   float *table = nullptr, *lora_a = nullptr, *lora_b = nullptr, *inv_freq = nullptr;
   bf16* zero_w = nullptr;
   float* zero_b = nullptr;
+  float h_nq[2][96] = {}, h_nk[2][96] = {}, h_cnq[2][96] = {}, h_cnk[2][96] = {};  // host copies [weight|bias][dh] of the per-head LayerNorms
   // per-clip cross-attention K / V^T caches
   float *kc32 = nullptr, *vc32 = nullptr;
   bf16 *kc16 = nullptr, *vtc16 = nullptr;
@@ -70,6 +71,7 @@ struct Dit {
   bool pair = true;       // CTA-pair (cta_group::2) GEMMs
   bool swap_ab = true;    // swap-AB tiles for the fp32-output N = D layers
   int geglu_bn = 128;     // N-tile of the GEGLU GEMM: packing group = geglu_bn / 2
+  int qkv3_bn = 0;        // >0: self-attention QKV weight packed three heads per N-tile of this width (EpiHeads<DH,3>)
 
   ~Dit() {
     for (void* p : allocs) cudaFree(p);
@@ -104,13 +106,15 @@ struct Dit {
     return EZB_OK;
   }
   // fp32 [N, K] -> rows [row_off, row_off+N) of bf16 dst [Ntot, kmul*Kpad]
-  void reg_linear(const std::string& key, int N, int K, bf16* dst, int Kpad, int row_off, int geglu_inner = 0, std::vector<int64_t> shape = {}) {
+  void reg_linear(const std::string& key, int N, int K, bf16* dst, int Kpad, int row_off, int geglu_inner = 0, std::vector<int64_t> shape = {},
+                  int h3_head_off = -1) {
     const int km = kmul, gh = geglu_bn / 2;
+    const int h3dh = h3_head_off >= 0 ? dh : 0, h3off = h3_head_off >= 0 ? h3_head_off : 0, h3bn = qkv3_bn;
     if (shape.empty()) shape = {N, K};
     reg(key, shape, [=](const float* src, cudaStream_t st) -> int {
       const size_t n = (size_t)N * Kpad;
       ++launch_counter();
-      pack_weight_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, N, K, dst, Kpad, km, row_off, geglu_inner, gh);
+      pack_weight_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, N, K, dst, Kpad, km, row_off, geglu_inner, gh, h3dh, h3off, h3bn);
       EZB_CUDA(cudaGetLastError());
       return EZB_OK;
     });
@@ -130,6 +134,7 @@ struct Dit {
     pair = opt_pair_gemm() != 0;
     swap_ab = opt_swap_ab() != 0;
     geglu_bn = (pair && inner % 128 == 0) ? 256 : 128;
+    qkv3_bn = (pair && d.precision == 0 && (D / H == 72 || D / H == 64) && H % 2 == 0 && opt_qkv3()) ? (D / H == 72 ? 224 : 192) : 0;
     if (dh > 96 || dh % 8 || D % 16 || inner % 64 || d.context_dim % 8 || d.depth % 2)
       return fail(EZB_ERR_UNSUPPORTED, "unsupported dims: D %d dh %d inner %d ctx %d depth %d", D, dh, inner, d.context_dim, d.depth);
     if (d.max_batch < 1 || d.max_batch > 256 || d.max_len < 1 || d.max_ctx_len < 1 || d.max_timesteps < 1) return fail(EZB_ERR_ARG, "workspace bounds");
@@ -172,10 +177,17 @@ struct Dit {
       EZB_TRY(reg_f32(p + ".norm2.weight", {D}, &w.n2w)); EZB_TRY(reg_f32(p + ".norm2.bias", {D}, &w.n2b));
       EZB_TRY(reg_f32(p + ".norm3.weight", {D}, &w.n3w)); EZB_TRY(reg_f32(p + ".norm3.bias", {D}, &w.n3b));
       EZB_TRY(reg_f32(p + ".norm_context.weight", {D}, &w.ncw)); EZB_TRY(reg_f32(p + ".norm_context.bias", {D}, &w.ncb));
-      EZB_TRY(alloc_w(&w.qkv, 3 * D, D));
-      reg_linear(p + ".attn.to_q.weight", D, D, w.qkv, D, 0);
-      reg_linear(p + ".attn.to_k.weight", D, D, w.qkv, D, D);
-      reg_linear(p + ".attn.to_v.weight", D, D, w.qkv, D, 2 * D);
+      if (qkv3_bn > 0) {
+        EZB_TRY(alloc_w(&w.qkv, H * qkv3_bn, D));  // zero-initialised: the 8 pad rows of every 224-row tile stay 0
+        reg_linear(p + ".attn.to_q.weight", D, D, w.qkv, D, 0, 0, {}, 0);
+        reg_linear(p + ".attn.to_k.weight", D, D, w.qkv, D, 0, 0, {}, H);
+        reg_linear(p + ".attn.to_v.weight", D, D, w.qkv, D, 0, 0, {}, 2 * H);
+      } else {
+        EZB_TRY(alloc_w(&w.qkv, 3 * D, D));
+        reg_linear(p + ".attn.to_q.weight", D, D, w.qkv, D, 0);
+        reg_linear(p + ".attn.to_k.weight", D, D, w.qkv, D, D);
+        reg_linear(p + ".attn.to_v.weight", D, D, w.qkv, D, 2 * D);
+      }
       EZB_TRY(reg_f32(p + ".attn.norm_q.weight", {dh}, &w.nqw)); EZB_TRY(reg_f32(p + ".attn.norm_q.bias", {dh}, &w.nqb));
       EZB_TRY(reg_f32(p + ".attn.norm_k.weight", {dh}, &w.nkw)); EZB_TRY(reg_f32(p + ".attn.norm_k.bias", {dh}, &w.nkb));
       EZB_TRY(alloc_w(&w.proj, D, D));
@@ -317,6 +329,13 @@ struct Dit {
   int finalize() {
     for (auto& kv : specs)
       if (!kv.second.loaded) return fail(EZB_ERR_WEIGHT, "missing state-dict key '%s'", kv.first.c_str());
+    EZB_CUDA(cudaDeviceSynchronize());
+    for (auto& w : blk) {  // the fused heads epilogue takes these by value (constant bank)
+      EZB_CUDA(cudaMemcpy(w.h_nq[0], w.nqw, dh * sizeof(float), cudaMemcpyDeviceToHost)); EZB_CUDA(cudaMemcpy(w.h_nq[1], w.nqb, dh * sizeof(float), cudaMemcpyDeviceToHost));
+      EZB_CUDA(cudaMemcpy(w.h_nk[0], w.nkw, dh * sizeof(float), cudaMemcpyDeviceToHost)); EZB_CUDA(cudaMemcpy(w.h_nk[1], w.nkb, dh * sizeof(float), cudaMemcpyDeviceToHost));
+      EZB_CUDA(cudaMemcpy(w.h_cnq[0], w.cnqw, dh * sizeof(float), cudaMemcpyDeviceToHost)); EZB_CUDA(cudaMemcpy(w.h_cnq[1], w.cnqb, dh * sizeof(float), cudaMemcpyDeviceToHost));
+      EZB_CUDA(cudaMemcpy(w.h_cnk[0], w.cnkw, dh * sizeof(float), cudaMemcpyDeviceToHost)); EZB_CUDA(cudaMemcpy(w.h_cnk[1], w.cnkb, dh * sizeof(float), cudaMemcpyDeviceToHost));
+    }
     {
       const int n = d.max_len * (dh / 2);
       ++launch_counter();
@@ -382,16 +401,23 @@ struct Dit {
     return EZB_OK;
   }
   // Q/K/V projection with the fused per-head LN + RoPE + attention-layout epilogue (fast mode)
-  int lin_heads(cudaStream_t st, const bf16* A, const bf16* W, int M, int N, const int* kinds, const float* nqw_, const float* nqb_, const float* nkw_,
-                const float* nkb_, bool rope, int L, bf16* qo, bf16* ko, bf16* vto, int Lpad) {
+  int lin_heads(cudaStream_t st, const bf16* A, const bf16* W, int M, int N, const int* kinds, const float (*nq)[96], const float (*nk)[96], bool rope,
+                int L, bf16* qo, bf16* ko, bf16* vto, int Lpad) {
     EpiHeadsParams e;
     memset(&e, 0, sizeof e);
+    for (int i = 0; i < dh && i < 72; ++i) {
+      if (nq) { e.nw[0][i] = nq[0][i]; e.nb[0][i] = nq[1][i]; }
+      if (nk) { e.nw[1][i] = nk[0][i]; e.nb[1][i] = nk[1][i]; }
+    }
     e.D = D; e.H = H; e.L = L;
     for (int i = 0; i < 3; ++i) e.kind[i] = i < N / D ? kinds[i] : 0;
-    e.nw[0] = nqw_; e.nb[0] = nqb_; e.nw[1] = nkw_; e.nb[1] = nkb_;
-    e.rope = rope ? rope_cs : nullptr; e.rope_kinds = 3;
+    e.rope = rope ? rope_cs : nullptr; e.rope_kinds = 3; e.rope_ld = d.max_len;
     e.out[0] = qo; e.out[1] = ko; e.out[2] = vto;
     e.ld_qk = DHP; e.dvp = DVP; e.Lpad = Lpad;
+    if (qkv3_bn > 0 && N == 3 * D) {  // packed self-attention QKV: three heads per tile
+      if (dh == 72) return gemm2<224, EpiHeads<72, 3>>(*dev, st, A, D, W, D, M, H * 224, D, e);
+      return gemm2<192, EpiHeads<64, 3>>(*dev, st, A, D, W, D, M, H * 192, D, e);
+    }
     if (pair) {
       if (dh == 72) return gemm2<144, EpiHeads<72>>(*dev, st, A, D, W, D, M, N, D, e);
       return gemm2<128, EpiHeads<64>>(*dev, st, A, D, W, D, M, N, D, e);
@@ -441,7 +467,7 @@ struct Dit {
       EZB_TRY(ln(st, ctx_emb, D, nullptr, nullptr, 0, w.ncw, w.ncb, nullptr, nullptr, 0, 1, act, Mc));
       const int off[2] = {0, D}, kinds[2] = {1, 2};
       if (fused_heads) {
-        EZB_TRY(lin_heads(st, act, w.ckv, Mc, 2 * D, kinds, nullptr, nullptr, w.cnkw, w.cnkb, false, Lc, nullptr, w.kc16, w.vtc16, ctx_Lpad));
+        EZB_TRY(lin_heads(st, act, w.ckv, Mc, 2 * D, kinds, nullptr, w.h_cnk, false, Lc, nullptr, w.kc16, w.vtc16, ctx_Lpad));
         continue;
       }
       EZB_TRY(lin_to_qkv(st, act, D, w.ckv, Mc, 2 * D));
@@ -520,7 +546,7 @@ struct Dit {
     if (fused_heads) {
       const int kinds[3] = {0, 1, 2};
       const int Lp = (L + 7) / 8 * 8;
-      EZB_TRY(lin_heads(st, act, w.qkv, M, 3 * D, kinds, w.nqw, w.nqb, w.nkw, w.nkb, true, L, q16, k16, vt16, Lp));
+      EZB_TRY(lin_heads(st, act, w.qkv, M, 3 * D, kinds, w.h_nq, w.h_nk, true, L, q16, k16, vt16, Lp));
       EZB_TRY(attention(st, q32, k32, v32, q16, k16, vt16, nullptr, Be, L, L, Lp));
     } else {
       EZB_TRY(lin_to_qkv(st, act, D, w.qkv, M, 3 * D));
@@ -540,7 +566,7 @@ struct Dit {
     EZB_TRY(ln(st, x_out, D, nullptr, nullptr, 0, w.n2w, w.n2b, nullptr, nullptr, 0, L, act, M));
     if (fused_heads) {
       const int kinds[1] = {0};
-      EZB_TRY(lin_heads(st, act, w.cq, M, D, kinds, w.cnqw, w.cnqb, nullptr, nullptr, false, L, q16, nullptr, nullptr, 0));
+      EZB_TRY(lin_heads(st, act, w.cq, M, D, kinds, w.h_cnq, nullptr, false, L, q16, nullptr, nullptr, 0));
       EZB_TRY(attention(st, q32, w.kc32, w.vc32, q16, w.kc16, w.vtc16, ctx_mask, Be, L, ctx_Lc, ctx_Lpad));
     } else {
       EZB_TRY(lin_to_qkv(st, act, D, w.cq, M, D));
@@ -581,6 +607,7 @@ struct Dit {
   int check_call(int Be, int L) {
     if (!finalized) return fail(EZB_ERR_STATE, "weights not finalized");
     if (Be < 1 || Be > d.max_batch || L < 1 || L > d.max_len) return fail(EZB_ERR_SHAPE, "Be %d / L %d exceed workspace (%d, %d)", Be, L, d.max_batch, d.max_len);
+    if (L < 32) return fail(EZB_ERR_SHAPE, "L %d: at least 32 latent frames are required (epilogues assume a warp's 32 rows span <= 2 clips)", L);
     if (Be != ctx_Be) return fail(EZB_ERR_STATE, "batch %d differs from the context set by ezb_dit_set_context (%d)", Be, ctx_Be);
     return EZB_OK;
   }

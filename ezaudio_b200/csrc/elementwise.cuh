@@ -339,7 +339,8 @@ __global__ void __launch_bounds__(256) small_linear_kernel(const float* __restri
   }
 }
 
-// RoPE table (rotary.py:48-70): cs[l][i] = (cos, sin)(l * inv_freq[i]), fp32, i < dh/2
+// RoPE table (rotary.py:48-70): cs[l][i] = (cos, sin)(l * inv_freq[i]), fp32, i < dh/2 (token-major: a thread reads its
+// token's dh/2 pairs as 9 full 32-byte sectors; the frequency-major alternative measured slower, profiles/r1)
 __global__ void rope_table_kernel(const float* __restrict__ inv_freq, float2* __restrict__ cs, int L, int half) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= L * half) return;
@@ -374,8 +375,10 @@ __global__ void add_rowvec_kernel(float* __restrict__ dst, int ld_dst, const flo
 // ---------------------------------------------------------------------------------------------------------------
 // Weight repacking fp32 [N, K] (reference layout) -> bf16 [N', kmul*Kpad] rows; optional GEGLU tile interleave
 // (dst row = tile*BN + {0,HALF} + j) and row offset (QKV / KV concatenation).  Split mode writes W' = [hi | hi | lo].
+// heads3 mode (h3_dh > 0): rows are heads of one of the q / k / v sections; global head g = h3_head_off + n / dh goes to row
+// (g / 3) * h3_bn + (g % 3) * dh + n % dh of the packed QKV weight (three heads per N-tile, see EpiHeads<DH, 3>).
 __global__ void pack_weight_kernel(const float* __restrict__ src, int N, int K, __nv_bfloat16* __restrict__ dst, int Kpad, int kmul, int row_off,
-                                   int geglu_inner, int geglu_half) {
+                                   int geglu_inner, int geglu_half, int h3_dh, int h3_head_off, int h3_bn) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)N * Kpad) return;
   const int n = i / Kpad, k = i - (size_t)n * Kpad;
@@ -383,6 +386,10 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, int N, int K, 
   if (geglu_inner > 0) {
     const int g = n >= geglu_inner, m = g ? n - geglu_inner : n;
     dn = (m / geglu_half) * (2 * geglu_half) + g * geglu_half + (m % geglu_half);
+  }
+  if (h3_dh > 0) {
+    const int g = h3_head_off + n / h3_dh;
+    dn = (g / 3) * h3_bn + (g % 3) * h3_dh + n % h3_dh;
   }
   const float v = k < K ? src[(size_t)n * K + k] : 0.f;
   const __nv_bfloat16 hi = __float2bfloat16_rn(v);

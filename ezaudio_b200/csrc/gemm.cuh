@@ -542,19 +542,23 @@ namespace ezb {
 struct EpiHeadsParams {
   int D, H, L;                 // model width, heads, tokens per batch item
   int kind[3];                 // section (n / D) -> 0 q, 1 k, 2 v
-  const float* nw[2];          // LayerNorm(dh) weight for q, k
-  const float* nb[2];
+  float nw[2][72];             // LayerNorm(dh) weight / bias for q, k -- BY VALUE: they live in the constant bank, so the
+  float nb[2][72];             // normalisation FFMAs take them as operands instead of issuing 2 x dh loads per token
   const float2* rope;          // [L][dh/2] (cos, sin) or null
+  int rope_ld;
   int rope_kinds;              // bit k set: apply RoPE to kind k
   __nv_bfloat16* out[3];       // per kind: q rows, k rows, v^T
   int ld_qk, dvp, Lpad;
 };
 
-template <int DH>
+// HPT = 2: tile = two adjacent heads of the reference column order (N-tile 2*dh).  HPT = 3: the packed QKV layout -- the
+// 3H heads of [q | k | v] are regrouped three per tile (N-tile 224 for dh = 72: 3 x 72 + 8 zero columns; 192 for dh = 64), which
+// makes the tile wide enough for the tensor pipe (narrow tiles are operand-bandwidth bound) and keeps one head per warp.
+template <int DH, int HPT = 2>
 struct EpiHeads {
   using Params = EpiHeadsParams;
-  static constexpr int BN = 2 * DH;
-  static constexpr int EPI_WARPS = 8;   // the two warps of a TMEM lane group take one head each
+  static constexpr int BN = HPT == 3 ? (DH == 72 ? 224 : 3 * DH) : 2 * DH;
+  static constexpr int EPI_WARPS = 4 * HPT;   // the HPT warps of a TMEM lane group take one head each
   static constexpr int STAGE_FLOATS = EPI_STAGE_FLOATS;
   template <class Wait>
   static __device__ __forceinline__ void run(const Params& ep, float* st, uint32_t taddr_row, int row0, int nvalid, int n0, int N, int lane, int c_begin,
@@ -563,11 +567,20 @@ struct EpiHeads {
     const int row = row0 + lane;
     const bool row_ok = lane < nvalid;
     const int b = row_ok ? row / ep.L : 0, l = row_ok ? row - b * ep.L : 0;
-#pragma unroll 1
-    for (int hh = c_begin / DH; hh < c_end / DH; ++hh) {
-      const int n = n0 + hh * DH;
-      if (n >= N) break;
-      const int sec = n / ep.D, kind = ep.kind[sec], head = (n - sec * ep.D) / DH;
+    {
+      const int hh = c_begin / (BN / HPT);    // this warp's head inside the tile
+      int sec, head;
+      if (HPT == 3) {
+        const int g = (n0 / BN) * 3 + hh;     // global head index in [q heads | k heads | v heads]
+        sec = g / ep.H;
+        head = g - sec * ep.H;
+      } else {
+        const int n = n0 + hh * DH;
+        if (n >= N) return;
+        sec = n / ep.D;
+        head = (n - sec * ep.D) / DH;
+      }
+      const int kind = ep.kind[sec];
       uint32_t r[DH];
       __syncwarp();
       tmem_ld_32x64(taddr_row + hh * DH, r);
@@ -578,18 +591,20 @@ struct EpiHeads {
       for (int i = 0; i < DH; ++i) v[i] = __uint_as_float(r[i]);
       const size_t bh = (size_t)b * ep.H + head;
       if (kind < 2) {
-        float s = 0.f;
+        float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int i = 0; i < DH; ++i) s += v[i];
-        const float mean = s * (1.0f / DH);
-        float q = 0.f;
+        for (int i = 0; i < DH; ++i) { s1[i & 3] += v[i]; s2[i & 3] = fmaf(v[i], v[i], s2[i & 3]); }
+        const float mean = ((s1[0] + s1[1]) + (s1[2] + s1[3])) * (1.0f / DH);
+        const float var = fmaxf(((s2[0] + s2[1]) + (s2[2] + s2[3])) * (1.0f / DH) - mean * mean, 0.f);
+        const float rstd = rsqrtf(var + 1e-5f);
+        const float nmr = -mean * rstd;
+        if (kind == 0) {
 #pragma unroll
-        for (int i = 0; i < DH; ++i) q += (v[i] - mean) * (v[i] - mean);
-        const float rstd = rsqrtf(q * (1.0f / DH) + 1e-5f);
-        const float* w = ep.nw[kind];
-        const float* bb = ep.nb[kind];
+          for (int i = 0; i < DH; ++i) v[i] = fmaf(fmaf(v[i], rstd, nmr), ep.nw[0][i], ep.nb[0][i]);
+        } else {
 #pragma unroll
-        for (int i = 0; i < DH; ++i) v[i] = (v[i] - mean) * rstd * __ldg(w + i) + __ldg(bb + i);
+          for (int i = 0; i < DH; ++i) v[i] = fmaf(fmaf(v[i], rstd, nmr), ep.nw[1][i], ep.nb[1][i]);
+        }
         if (ep.rope != nullptr && ((ep.rope_kinds >> kind) & 1)) {
           const float2* cs = ep.rope + (size_t)l * (DH / 2);
 #pragma unroll
@@ -606,18 +621,22 @@ struct EpiHeads {
           stage_put(st, lane, g, __uint_as_float(pack_bf16(v[4 * g], v[4 * g + 1])), __uint_as_float(pack_bf16(v[4 * g + 2], v[4 * g + 3])));
         __syncwarp();
         if (lane < DH / 4) {
-          for (int rr = 0; rr < nvalid && rr < 32; ++rr) {
-            const int rw = row0 + rr, rb = rw / ep.L, rl = rw - rb * ep.L;
-            const float2 pk = stage_get(st, rr, lane);
-            __nv_bfloat16* dst = ep.out[kind] + (((size_t)rb * ep.H + head) * ep.L + rl) * ep.ld_qk + 4 * lane;
-            *reinterpret_cast<float2*>(dst) = pk;
+          const int rb0 = row0 / ep.L, rl0 = row0 - rb0 * ep.L;
+          __nv_bfloat16* base = ep.out[kind] + 4 * lane;
+          const size_t head_rows = (size_t)ep.L * ep.ld_qk;
+          const int nv = nvalid < 32 ? nvalid : 32;
+#pragma unroll 4
+          for (int rr = 0; rr < nv; ++rr) {
+            int rl = rl0 + rr, rb = rb0;
+            while (rl >= ep.L) { rl -= ep.L; ++rb; }   // normally at most one wrap (L >= 32); short contexts may wrap more
+            *reinterpret_cast<float2*>(base + ((size_t)rb * ep.H + head) * head_rows + (size_t)rl * ep.ld_qk) = stage_get(st, rr, lane);
           }
         }
       } else if (row_ok) {
         __nv_bfloat16* dst = ep.out[2] + bh * ep.dvp * ep.Lpad + l;
 #pragma unroll
-        for (int i = 0; i < DH; ++i) dst[(size_t)i * ep.Lpad] = __float2bfloat16_rn(v[i]);
-        for (int i = DH; i < ep.dvp; ++i) dst[(size_t)i * ep.Lpad] = __float2bfloat16_rn(0.f);
+        for (int i = 0; i < DH; ++i) { *dst = __float2bfloat16_rn(v[i]); dst += ep.Lpad; }
+        for (int i = DH; i < ep.dvp; ++i) { *dst = __float2bfloat16_rn(0.f); dst += ep.Lpad; }
       }
     }
   }

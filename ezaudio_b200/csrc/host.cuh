@@ -146,6 +146,10 @@ struct Device {
   TmapCache tmaps;
 };
 
+inline int& opt_qkv3() {
+  static int v = 1;
+  return v;
+}
 inline int& opt_swap_ab() {
   static int v = 1;
   return v;
