@@ -112,8 +112,8 @@ __device__ __forceinline__ void rows_t(const RowCtx& c, const float2* x) {
     if (F32) { *reinterpret_cast<float2*>(o32) = make_float2(v0, v1); o32 += c.ld32; }
     if (BF16) {
       if (ACT == ACT_SILU) { v0 = silu(v0); v1 = silu(v1); }
-      if (ACT == ACT_SNAKE) {
-        const float s0 = sinf(v0 * c.sa0), s1 = sinf(v1 * c.sa1);
+      if (ACT == ACT_SNAKE) {  // bf16 throughput path: MUFU sine (the result is rounded to bf16); bf16x3 uses the exact sinf (rows_generic)
+        const float s0 = __sinf(v0 * c.sa0), s1 = __sinf(v1 * c.sa1);
         v0 = fmaf(c.sb0 * s0, s0, v0);
         v1 = fmaf(c.sb1 * s1, s1, v1);
       }

@@ -1,0 +1,64 @@
+"""Public API conformance on the GPU (api/ezaudio.py:101-130, api/controlnet.py:113-161): signatures, return types, shapes,
+determinism under a fixed seed, batched extension.  Uses the tiny architecture through `config_path`-free params injection."""
+import inspect
+
+import numpy as np
+import pytest
+import torch
+
+from ezaudio_b200 import config, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _tiny_params():
+    p = config.load_params("s3_xl")
+    p["model"] = synth.tiny_model(72)
+    p["text_encoder"] = dict(p["text_encoder"], max_length=16)
+    return p
+
+
+def test_signatures_match_reference():
+    from ezaudio_b200.api import EzAudio, EzAudio_ControlNet
+    g = inspect.signature(EzAudio.generate_audio).parameters
+    assert list(g)[:9] == ["self", "text", "length", "guidance_scale", "guidance_rescale", "ddim_steps", "eta", "random_seed", "randomize_seed"]
+    assert (g["length"].default, g["guidance_scale"].default, g["guidance_rescale"].default, g["ddim_steps"].default, g["eta"].default) == (10, 5, 0.75, 100, 1)
+    e = inspect.signature(EzAudio.editing_audio).parameters
+    assert list(e)[:6] == ["self", "text", "boundary", "gt_file", "mask_start", "mask_length"]
+    assert (e["guidance_scale"].default, e["guidance_rescale"].default, e["ddim_steps"].default) == (3.5, 0, 100)
+    c = inspect.signature(EzAudio_ControlNet.generate_audio).parameters
+    assert list(c)[:4] == ["self", "text", "audio_path", "surpass_noise"]
+    assert (c["guidance_scale"].default, c["ddim_steps"].default, c["conditioning_scale"].default) == (3.5, 50, 1)
+
+
+def test_generate_audio_shapes_types_determinism(monkeypatch):
+    from ezaudio_b200 import api
+    monkeypatch.setattr(config, "load_params", lambda name, path=None, table=None: _tiny_params())
+    enc = api.SyntheticTextEncoder(64, 16)
+    ez = api.EzAudio("s3_xl", ckpt_path="synthetic:3", vae_path="synthetic:6", text_encoder=enc, max_batch=2, max_length_s=2,
+                     vae_config_path=None)
+    sr, wav = ez.generate_audio("a dog barks", length=1, ddim_steps=4, random_seed=7)
+    assert sr == 24000 and isinstance(wav, np.ndarray) and wav.dtype == np.float32 and wav.shape == (24000,)
+    assert np.isfinite(wav).all()
+    sr2, wav2 = ez.generate_audio("a dog barks", length=1, ddim_steps=4, random_seed=7)
+    assert np.array_equal(wav, wav2)                      # same seed -> same audio (graph replay path on the 2nd call)
+    _, wav3 = ez.generate_audio("a dog barks", length=1, ddim_steps=4, random_seed=8)
+    assert not np.array_equal(wav, wav3)
+    sr, batch = ez.generate_audio(["a dog barks", "rain on a roof"], length=1, ddim_steps=4, random_seed=7)
+    assert isinstance(batch, list) and len(batch) == 2 and batch[0].shape == (24000,)
+    assert np.allclose(batch[0], wav, atol=2e-2)          # prompt 0 of a batch == the single-prompt run (bf16 batch-size noise only)
+    _, nocfg = ez.generate_audio("", length=1, ddim_steps=4, random_seed=7)   # text == '' -> no CFG branch (api/ezaudio.py:109-111)
+    assert nocfg.shape == (24000,) and np.isfinite(nocfg).all()
+
+
+def test_controlnet_generate_audio(monkeypatch):
+    from ezaudio_b200 import api
+    p = _tiny_params()
+    p["controlnet"] = synth.CONTROLNET
+    p["conditioner"] = config.BUILTIN_CONTROLNET["energy"]["conditioner"]
+    enc = api.SyntheticTextEncoder(64, 16)
+    ez = api.EzAudio_ControlNet("energy", ckpt_path="synthetic:5", controlnet_path="synthetic:6", vae_path="synthetic:6", text_encoder=enc, max_batch=1,
+                                params=p)
+    ref_audio = (0.1 * torch.randn(3 * 24000, generator=torch.Generator().manual_seed(9))).numpy()
+    sr, wav = ez.generate_audio("a siren", ref_audio, ddim_steps=3, random_seed=1)
+    assert sr == 24000 and wav.dtype == np.float32 and wav.shape == (3 * 24000,) and np.isfinite(wav).all()
