@@ -22,7 +22,8 @@ class DitDesc(C.Structure):
 class VaeDesc(C.Structure):
     _fields_ = [("latent_dim", C.c_int32), ("channels", C.c_int32), ("out_channels", C.c_int32), ("n_stages", C.c_int32),
                 ("c_mults", C.c_int32 * 8), ("strides", C.c_int32 * 8), ("max_batch", C.c_int32),
-                ("max_latent_len", C.c_int32), ("precision", C.c_int32)]
+                ("max_latent_len", C.c_int32), ("precision", C.c_int32), ("with_encoder", C.c_int32), ("in_channels", C.c_int32),
+                ("enc_latent_dim", C.c_int32)]
 
 
 class TestEpilogue(C.Structure):
@@ -52,6 +53,7 @@ _SIGS = {
     "ezb_vae_load_weight": ([_VP, C.c_char_p, _VP, C.POINTER(C.c_int64), _I, _VP], _I),
     "ezb_vae_finalize_weights": ([_VP, _VP], _I),
     "ezb_vae_decode": ([_VP, _VP, _VP, _I, _I, _VP], _I),
+    "ezb_vae_encode": ([_VP, _VP, _VP, _VP, _I, _I, _VP], _I),
     "ezb_set_option": ([C.c_char_p, _I], _I),
     "ezb_debug_read": ([C.POINTER(C.c_ulonglong)], _I),
     "ezb_launch_count": ([], C.c_ulonglong),

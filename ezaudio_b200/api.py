@@ -115,9 +115,11 @@ class EzAudio(_Base):
         self.unet = MaskDiT(precision=precision, max_batch=2 * max_batch, max_len=max_len, max_ctx_len=p["text_encoder"]["max_length"],
                             max_timesteps=1000, device=device, **p["model"])
         self.unet.load_state_dict(_state_dict(ckpt_path, weights.dit_param_shapes(p["model"]), "model"))
-        dcfg = config.load_vae_decoder_config(vae_config_path)
-        dec = OobleckDecoder(precision=precision, max_batch=max_batch, max_latent_len=max_len, device=device, **dcfg)
-        vsd = _state_dict(vae_path, weights.vae_decoder_param_shapes(dcfg), "state_dict")
+        dcfg, ecfg = config.load_vae_decoder_config(vae_config_path), config.load_vae_encoder_config(vae_config_path)
+        dec = OobleckDecoder(precision=precision, max_batch=max_batch, max_latent_len=max_len, device=device, encoder_cfg=ecfg, **dcfg)
+        vshapes = dict(weights.vae_decoder_param_shapes(dcfg))
+        vshapes.update(weights.vae_encoder_param_shapes(ecfg))
+        vsd = _state_dict(vae_path, vshapes, "state_dict")
         vsd = {(k[len("autoencoder."):] if k.startswith("autoencoder.") else k): v for k, v in vsd.items()}  # stable_vae/__init__.py:25-31
         dec.load_state_dict(vsd)
         self.autoencoder = Autoencoder(dec)
@@ -166,7 +168,7 @@ class EzAudio(_Base):
         mask_start -= start_idx
         mask_end -= start_idx
         gt_t = gt_t[:, :, round(start_idx * sr):round(end_idx * sr)]
-        gt_latent = self.autoencoder(audio=gt_t)  # VAE encode: next SURVEY 8(f) row -- raises until built
+        gt_latent = self.autoencoder(audio=gt_t)  # OobleckEncoder + stochastic VAE bottleneck (global RNG, bottleneck.py:69)
         B, D, L = gt_latent.shape
         gt_mask = torch.zeros(B, D, L, device=self.device)
         latent_sr = self.params["autoencoder"]["latent_sr"]

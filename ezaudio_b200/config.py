@@ -47,6 +47,13 @@ def load_params(name: str, config_path=None, table=None):
     return copy.deepcopy(table[name])
 
 
+def load_vae_encoder_config(path=None):
+    if path is None:
+        return copy.deepcopy(synth.VAE_ENCODER)
+    with open(path) as f:
+        return json.load(f)["model"]["encoder"]["config"]
+
+
 def load_vae_decoder_config(path=None):
     if path is None:
         return copy.deepcopy(synth.VAE_DECODER)

@@ -154,6 +154,10 @@ EZB_API int ezb_vae_finalize_weights(ezb_vae* h, void* stream) {
   if (!h) return fail(EZB_ERR_ARG, "null handle");
   return reinterpret_cast<Vae*>(h)->finalize(ST(stream));
 }
+EZB_API int ezb_vae_encode(ezb_vae* h, const float* audio, const float* noise, float* z, int B, int T, void* stream) {
+  if (!h || !audio || !z) return fail(EZB_ERR_ARG, "ezb_vae_encode: null argument");
+  return reinterpret_cast<Vae*>(h)->encode(audio, noise, z, B, T, ST(stream));
+}
 EZB_API int ezb_vae_decode(ezb_vae* h, const float* z, float* wav, int B, int L, void* stream) {
   if (!h || !z || !wav) return fail(EZB_ERR_ARG, "ezb_vae_decode: null argument");
   return reinterpret_cast<Vae*>(h)->decode(z, wav, B, L, ST(stream));

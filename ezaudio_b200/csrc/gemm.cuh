@@ -33,6 +33,7 @@ struct GemmShape {
   int num_m_tiles, num_n_tiles;
   // implicit-conv addressing of A (taps == 0 -> plain 2-D A[M,K])
   int taps, center, dilation, cin_blocks, T, tiles_per_batch;
+  int stride, pad;     // stride > 1: strided conv (VAE encoder): A is a 4-D map [B, T/stride, stride, C], tap k reads row q*stride + k - pad
   unsigned long long* dbg;  // optional cycle counters (CTA 0): [0] mma wait full, [1] mma wait tempty, [2] producer wait empty,
                             // [3] epilogue warp 2 wait tfull, [4] epilogue warp 2 busy, [5] total
 };
@@ -463,7 +464,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           } else {
             const int tap = kb / g.cin_blocks, cb = kb - tap * g.cin_blocks;
             const int bidx = mt / g.tiles_per_batch, t0 = (mt - bidx * g.tiles_per_batch) * GEMM_BM;
-            tma_load_3d(sA + stage * SM::A_BYTES, &tmA, &full[stage], cb * GEMM_BK, t0 + (tap - g.center) * g.dilation, bidx);
+            if (g.stride > 1) {
+              const int off = tap - g.pad;                                   // input row = q * stride + off
+              const int r = ((off % g.stride) + g.stride) % g.stride, dq = (off - r) / g.stride;
+              tma_load_4d(sA + stage * SM::A_BYTES, &tmA, &full[stage], cb * GEMM_BK, r, t0 + dq, bidx);
+            } else {
+              tma_load_3d(sA + stage * SM::A_BYTES, &tmA, &full[stage], cb * GEMM_BK, t0 + (tap - g.center) * g.dilation, bidx);
+            }
           }
           tma_load_2d(sB + stage * SM::B_BYTES, &tmB, &full[stage], kb * GEMM_BK, n0);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }

@@ -140,6 +140,13 @@ struct TmapCache {
   }
 };
 
+inline int make_tmap4_strided(CUtensorMap* out, const void* ptr, uint64_t C, uint64_t stride, uint64_t Tq, uint64_t B, uint64_t ldc) {
+  // activations [B, Tq*stride, ldc] viewed as [B, Tq, stride, C]: box {64 channels, 1 phase, 128 rows, 1 clip}
+  uint64_t dims[4] = {C, stride, Tq, B}, str[3] = {ldc * 2, stride * ldc * 2, Tq * stride * ldc * 2};
+  uint32_t box[4] = {64, 1, 128, 1};
+  return make_tmap(out, ptr, 4, dims, str, box);
+}
+
 struct Device {
   int id = 0;
   int num_sms = 148;
@@ -177,6 +184,7 @@ int launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStr
 
 struct ConvAddr {  // implicit-GEMM addressing of A, see gemm.cuh
   int taps = 0, center = 0, dilation = 1, cin_pad = 0, T = 0, B = 0;
+  int stride = 1, pad = 0;  // stride > 1: T is the OUTPUT length, the input has T * stride rows per clip
 };
 
 template <int BN, class Epi>
@@ -292,7 +300,19 @@ int gemm(Device& dev, cudaStream_t st, const __nv_bfloat16* A, int lda, const __
     g.tiles_per_batch = (conv->T + GEMM_BM - 1) / GEMM_BM;
     g.num_m_tiles = g.tiles_per_batch * conv->B;
     g.num_k_blocks = conv->taps * g.cin_blocks;
+    g.stride = conv->stride;
+    g.pad = conv->pad;
     // A viewed as [B, T, lda]; channels beyond lda zero-fill (K here = real channel count)
+    if (conv->stride > 1) {
+      TmapCache::Key k(A, (uint64_t)K, (uint64_t)conv->T, (uint64_t)conv->B, (uint64_t)lda * 1000003ull + conv->stride, GEMM_BM, 4);
+      auto it = dev.tmaps.maps.find(k);
+      if (it == dev.tmaps.maps.end()) {
+        CUtensorMap m;
+        EZB_TRY(make_tmap4_strided(&m, A, (uint64_t)K, (uint64_t)conv->stride, (uint64_t)conv->T, (uint64_t)conv->B, (uint64_t)lda));
+        it = dev.tmaps.maps.emplace(k, m).first;
+      }
+      tA = &it->second;
+    } else
     EZB_TRY(dev.tmaps.get3d(A, (uint64_t)K, (uint64_t)conv->T, (uint64_t)conv->B, (uint64_t)lda, (uint64_t)lda * conv->T, GEMM_BM, &tA));
     EZB_TRY(dev.tmaps.get2d(W, (uint64_t)conv->taps * conv->cin_pad, (uint64_t)N, (uint64_t)ldw, BN, &tB));
   } else {

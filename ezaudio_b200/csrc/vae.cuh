@@ -107,6 +107,42 @@ __global__ void fold_wave_w_kernel(const float* __restrict__ v, const float* __r
   if (i < 7 * C) { const int k = i / C, c = i - k * C; w[i] = g[0] * v[c * 7 + k] / norms[0]; }
 }
 
+// encoder stem: Conv1d(1 -> C0, k=7, pad 3) on the raw waveform (autoencoders.py:133) -> channels-last fp32 residual stream
+// + bf16 SnakeBeta(next) operand.  w folded fp32 [7][C0].
+__global__ void enc_conv_in_kernel(const float* __restrict__ audio, const float* __restrict__ w, const float* __restrict__ bias, const float* __restrict__ sa,
+                                   const float* __restrict__ sb, float* __restrict__ raw, __nv_bfloat16* __restrict__ act, int C, int T, int kmul) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (i >= (size_t)T * C) return;
+  const int t = i / C, c = i - (size_t)t * C;
+  const float* a = audio + (size_t)b * T;
+  float v = bias[c];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) {
+    const int tt = t + k - 3;
+    if (tt >= 0 && tt < T) v = fmaf(w[k * C + c], a[tt], v);
+  }
+  raw[((size_t)b * T + t) * C + c] = v;
+  const float sn = sinf(v * sa[c]);
+  store_act(act + ((size_t)b * T + t) * kmul * C, c, C, kmul, v + sb[c] * sn * sn);
+}
+__global__ void fold_conv_in_w_kernel(const float* __restrict__ v, const float* __restrict__ g, const float* __restrict__ norms, float* __restrict__ w, int C) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // v [C, 1, 7] -> w [7][C]
+  if (i < 7 * C) { const int k = i / C, c = i - k * C; w[i] = g[c] * v[c * 7 + k] / norms[c]; }
+}
+// VAEBottleneck.encode (bottleneck.py:66-70,77-87): enc [B*L, 2*Cz] channels-last (mean | scale) -> z (B, Cz, L)
+__global__ void vae_sample_kernel(const float* __restrict__ enc, const float* __restrict__ noise, float* __restrict__ z, int Cz, int L) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (i >= (size_t)Cz * L) return;
+  const int c = i / L, l = i - (size_t)c * L;
+  const float* row = enc + ((size_t)b * L + l) * 2 * Cz;
+  const float mean = row[c], sc = row[Cz + c];
+  const float sp = sc > 20.f ? sc : log1pf(expf(sc));  // F.softplus (threshold 20)
+  const float nz = noise ? noise[((size_t)b * Cz + c) * L + l] : 0.f;
+  z[((size_t)b * Cz + c) * L + l] = nz * (sp + 1e-4f) + mean;
+}
+
 struct VaeConv {  // one packed conv / conv-transpose
   __nv_bfloat16* w = nullptr;
   float* bias = nullptr;
@@ -133,6 +169,13 @@ struct Vae {
   __nv_bfloat16 *actA = nullptr, *actB = nullptr;
   float* resid = nullptr;
   size_t elems_per_clip = 0;
+  // ---- encoder (OobleckEncoder, autoencoders.py:115-146), present when desc.with_encoder
+  float *e_in_w = nullptr, *e_in_b = nullptr;                 // stem conv folded [7][C0], bias
+  std::vector<VaeConv> e_res7, e_res1, e_down;              // [stage*3 + unit], per stage strided conv
+  std::vector<VaeSnake> e_res_s0, e_res_s2, e_down_snake;
+  VaeSnake e_out_snake;
+  VaeConv e_out;
+  std::vector<int> e_cin, e_cout, e_stride;
 
   ~Vae() { for (void* p : allocs) cudaFree(p); }
   template <typename T>
@@ -168,6 +211,22 @@ struct Vae {
     }
     expect_snake(p + std::to_string(nst + 1));
     expect_wn(p + std::to_string(nst + 2), false);
+    if (d.with_encoder) {
+      if (d.in_channels != 1 || d.enc_latent_dim != 2 * d.latent_dim) return fail(EZB_ERR_UNSUPPORTED, "vae encoder config");
+      const std::string e = "encoder.layers.";
+      expect_wn(e + "0", true);
+      for (int i = 0; i < nst; ++i) {
+        e_cin.push_back(mults[i] * d.channels); e_cout.push_back(mults[i + 1] * d.channels); e_stride.push_back(d.strides[i]);
+        const std::string q = e + std::to_string(i + 1) + ".layers.";
+        for (int u = 0; u < 3; ++u) {
+          const std::string ru = q + std::to_string(u) + ".layers.";
+          expect_snake(ru + "0"); expect_wn(ru + "1", true); expect_snake(ru + "2"); expect_wn(ru + "3", true);
+        }
+        expect_snake(q + "3"); expect_wn(q + "4", true);
+      }
+      expect_snake(e + std::to_string(nst + 1));
+      expect_wn(e + std::to_string(nst + 2), true);
+    }
     // workspace: largest channels-last activation per clip
     size_t T = d.max_latent_len, mx = (size_t)T * cin_s[0];
     for (int j = 0; j < nst; ++j) { T *= stride_s[j]; mx = std::max(mx, T * (size_t)cout_s[j]); }
@@ -230,6 +289,45 @@ struct Vae {
     EZB_CUDA(cudaGetLastError());
     return EZB_OK;
   }
+  // strided Conv1d(cin -> cout, k = 2s, stride s, pad ceil(s/2)) (EncoderBlock, autoencoders.py:76-77): same packing as a conv
+  int pack_conv_strided(const std::string& k, int cout, int cin, int s_, VaeConv* c, cudaStream_t st) {
+    EZB_TRY(pack_conv(k, cout, cin, 2 * s_, 1, true, c, st));
+    c->stride = s_;
+    c->center = (s_ + 1) / 2;  // padding
+    return EZB_OK;
+  }
+  int finalize_encoder(cudaStream_t st) {
+    const std::string e = "encoder.layers.";
+    const int C0 = e_cin[0];
+    {
+      float *g, *v, *b, *norms;
+      EZB_TRY(need(e + "0.weight_g", {C0, 1, 1}, &g)); EZB_TRY(need(e + "0.weight_v", {C0, 1, 7}, &v)); EZB_TRY(need(e + "0.bias", {C0}, &b));
+      EZB_TRY(alloc(&norms, (size_t)C0)); EZB_TRY(alloc(&e_in_w, (size_t)7 * C0));
+      ++launch_counter();
+      wn_norm_kernel<<<C0, 256, 0, st>>>(v, 7, norms);
+      ++launch_counter();
+      fold_conv_in_w_kernel<<<(7 * C0 + 255) / 256, 256, 0, st>>>(v, g, norms, e_in_w, C0);
+      EZB_CUDA(cudaGetLastError());
+      e_in_b = b;
+    }
+    e_res7.resize(3 * nst); e_res1.resize(3 * nst); e_res_s0.resize(3 * nst); e_res_s2.resize(3 * nst); e_down.resize(nst); e_down_snake.resize(nst);
+    const int dils[3] = {1, 3, 9};
+    for (int j = 0; j < nst; ++j) {
+      const std::string q = e + std::to_string(j + 1) + ".layers.";
+      for (int u = 0; u < 3; ++u) {
+        const std::string ru = q + std::to_string(u) + ".layers.";
+        EZB_TRY(prep_snake(ru + "0", e_cin[j], &e_res_s0[3 * j + u], st));
+        EZB_TRY(pack_conv(ru + "1", e_cin[j], e_cin[j], 7, dils[u], true, &e_res7[3 * j + u], st));
+        EZB_TRY(prep_snake(ru + "2", e_cin[j], &e_res_s2[3 * j + u], st));
+        EZB_TRY(pack_conv(ru + "3", e_cin[j], e_cin[j], 1, 1, true, &e_res1[3 * j + u], st));
+      }
+      EZB_TRY(prep_snake(q + "3", e_cin[j], &e_down_snake[j], st));
+      EZB_TRY(pack_conv_strided(q + "4", e_cout[j], e_cin[j], e_stride[j], &e_down[j], st));
+    }
+    EZB_TRY(prep_snake(e + std::to_string(nst + 1), e_cout[nst - 1], &e_out_snake, st));
+    EZB_TRY(pack_conv(e + std::to_string(nst + 2), d.enc_latent_dim, e_cout[nst - 1], 3, 1, true, &e_out, st));
+    return EZB_OK;
+  }
   int prep_snake(const std::string& k, int C, VaeSnake* s, cudaStream_t st) {
     float *al, *be;
     EZB_TRY(need(k + ".alpha", {C}, &al)); EZB_TRY(need(k + ".beta", {C}, &be));
@@ -269,6 +367,7 @@ struct Vae {
       fold_wave_w_kernel<<<(7 * C0 + 255) / 256, 256, 0, st>>>(v, g, norms, out_w, C0);
       EZB_CUDA(cudaGetLastError());
     }
+    if (d.with_encoder) EZB_TRY(finalize_encoder(st));
     EZB_CUDA(cudaStreamSynchronize(st));
     finalized = true;
     return EZB_OK;
@@ -292,8 +391,47 @@ struct Vae {
     if (snake) { e.act = ACT_SNAKE; e.act_a = snake->a; e.act_b = snake->binv; }
     ConvAddr ca;
     ca.taps = c.taps; ca.center = c.center; ca.dilation = c.dil; ca.cin_pad = c.cin_pad; ca.T = T; ca.B = B;
+    if (c.stride > 1 && c.N == c.cout) { ca.stride = c.stride; ca.pad = c.center; }  // strided conv (T = output length); conv-transpose has N = s*cout
     const int ld = c.taps * c.cin_pad;
     return gemm<128, EpiLinear<128>>(*dev, st, A, kmul * c.cin, c.w, ld, B * T, c.N, kmul * c.cin, e, &ca);
+  }
+
+  // audio (B, 1, T) fp32, T = hop * L; noise (B, latent, L) fp32 or null (-> mean); z (B, latent, L) fp32
+  int encode(const float* audio, const float* noise, float* z, int B, int T, cudaStream_t st) {
+    if (!finalized || !d.with_encoder) return fail(EZB_ERR_STATE, "VAE encoder weights not loaded");
+    int hop = 1;
+    for (int j = 0; j < nst; ++j) hop *= e_stride[j];
+    if (T % hop) return fail(EZB_ERR_SHAPE, "vae_encode: T %d is not a multiple of the hop %d", T, hop);
+    const int L = T / hop;
+    if (B < 1 || B > d.max_batch || L < 1 || L > d.max_latent_len) return fail(EZB_ERR_SHAPE, "vae_encode: B %d L %d exceed workspace", B, L);
+    const int C0 = e_cin[0];
+    __nv_bfloat16 *cur = actA, *oth = actB;
+    {
+      dim3 grid((unsigned)(((size_t)T * C0 + 255) / 256), B);
+      ++launch_counter();
+      enc_conv_in_kernel<<<grid, 256, 0, st>>>(audio, e_in_w, e_in_b, e_res_s0[0].a, e_res_s0[0].binv, resid, cur, C0, T, kmul);
+      EZB_CUDA(cudaGetLastError());
+    }
+    int Tc = T;
+    for (int j = 0; j < nst; ++j) {
+      for (int u = 0; u < 3; ++u) {
+        EZB_TRY(run_conv(st, e_res7[3 * j + u], cur, B, Tc, nullptr, nullptr, oth, &e_res_s2[3 * j + u]));
+        const bool last = u == 2;
+        const VaeSnake* nxt = last ? &e_down_snake[j] : &e_res_s0[3 * j + u + 1];
+        EZB_TRY(run_conv(st, e_res1[3 * j + u], oth, B, Tc, resid, last ? nullptr : resid, cur, nxt));
+      }
+      Tc /= e_stride[j];
+      const bool last_stage = j + 1 == nst;
+      const VaeSnake* nxt = last_stage ? &e_out_snake : &e_res_s0[3 * (j + 1)];
+      EZB_TRY(run_conv(st, e_down[j], cur, B, Tc, nullptr, last_stage ? nullptr : resid, oth, nxt));
+      std::swap(cur, oth);
+    }
+    EZB_TRY(run_conv(st, e_out, cur, B, Tc, nullptr, resid, nullptr, nullptr));  // (mean | scale), channels-last fp32
+    dim3 g2((unsigned)(((size_t)d.latent_dim * L + 255) / 256), B);
+    ++launch_counter();
+    vae_sample_kernel<<<g2, 256, 0, st>>>(resid, noise, z, d.latent_dim, L);
+    EZB_CUDA(cudaGetLastError());
+    return EZB_OK;
   }
 
   int decode(const float* z, float* wav, int B, int L, cudaStream_t st) {

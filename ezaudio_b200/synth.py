@@ -24,6 +24,10 @@ VAE_DECODER = dict(out_channels=1, channels=128, c_mults=[1, 2, 4, 8], strides=[
                    latent_dim=128, use_snake=True, final_tanh=False)  # ckpts/vae/config.json:18-28
 
 
+VAE_ENCODER = dict(in_channels=1, channels=128, c_mults=[1, 2, 4, 8], strides=[2, 4, 6, 10], latent_dim=256,
+                   use_snake=True)  # ckpts/vae/config.json:7-16
+
+
 def tiny_model(head_dim: int = 72, heads: int = 2, depth: int = 4, ctx_dim: int = 64, rank: int = 4) -> Dict:
     """Same architecture switches as the shipped configs, small dims (head_dim 72 like XL or 64 like L)."""
     return dict(XL_MODEL, embed_dim=head_dim * heads, num_heads=heads, depth=depth, context_dim=ctx_dim,
@@ -32,6 +36,10 @@ def tiny_model(head_dim: int = 72, heads: int = 2, depth: int = 4, ctx_dim: int 
 
 def tiny_vae(channels: int = 16) -> Dict:
     return dict(VAE_DECODER, channels=channels)
+
+
+def tiny_vae_encoder(channels: int = 16) -> Dict:
+    return dict(VAE_ENCODER, channels=channels)
 
 
 def model_cfg(name: str) -> Dict:

@@ -178,6 +178,41 @@ def vae_decoder_param_shapes(dec_cfg: dict, prefix: str = "decoder.") -> "Ordere
     return out
 
 
+def vae_encoder_param_shapes(enc_cfg: dict, prefix: str = "encoder.") -> "OrderedDict[str, Tuple[int, ...]]":
+    """Keys/shapes of the `encoder.*` slice of the VAE state-dict (stable_vae/models/autoencoders.py:115-146;
+    ckpts/vae/config.json:7-16: in 1 ch, channels 128, c_mults [1,2,4,8], strides [2,4,6,10], latent 256 = mean|scale)."""
+    ch, mults, strides = enc_cfg["channels"], [1] + list(enc_cfg["c_mults"]), list(enc_cfg["strides"])
+    if not enc_cfg.get("use_snake", False):
+        raise NotImplementedError("ezaudio_b200 VAE encoder: only use_snake=true")
+    out: Dict = OrderedDict()
+    p = prefix + "layers."
+
+    def wn(key, co, ci, k):
+        out[key + ".weight_g"] = (co, 1, 1)
+        out[key + ".weight_v"] = (co, ci, k)
+        out[key + ".bias"] = (co,)
+
+    def snake(key, c):
+        out[key + ".alpha"] = (c,)
+        out[key + ".beta"] = (c,)
+
+    wn(p + "0", mults[0] * ch, enc_cfg["in_channels"], 7)
+    for i in range(len(mults) - 1):
+        cin, cout, s = mults[i] * ch, mults[i + 1] * ch, strides[i]
+        q = f"{p}{i + 1}.layers."
+        for u in range(3):
+            snake(f"{q}{u}.layers.0", cin)
+            wn(f"{q}{u}.layers.1", cin, cin, 7)
+            snake(f"{q}{u}.layers.2", cin)
+            wn(f"{q}{u}.layers.3", cin, cin, 1)
+        snake(q + "3", cin)
+        wn(q + "4", cout, cin, 2 * s)
+    n = len(mults)
+    snake(f"{p}{n}", mults[-1] * ch)
+    wn(f"{p}{n + 1}", enc_cfg["latent_dim"], mults[-1] * ch, 3)
+    return out
+
+
 def synthetic_state_dict(shapes, seed: int = 0, dtype=torch.float32) -> Dict[str, torch.Tensor]:
     """Deterministic random checkpoint (CPU generator; identical bits wherever the same torch
     build runs).  Every tensor the reference zero-initialises is drawn non-zero,

@@ -87,6 +87,9 @@ typedef struct {
   int32_t strides[8];
   int32_t max_batch, max_latent_len;
   int32_t precision;
+  int32_t with_encoder;    /* 1: also hold OobleckEncoder + VAE bottleneck (editing_audio, api/ezaudio.py:175) */
+  int32_t in_channels;     /* 1 */
+  int32_t enc_latent_dim;  /* 2 * latent_dim (mean | scale) */
 } ezb_vae_desc;
 int ezb_vae_create(ezb_vae** out, const ezb_vae_desc* desc, int device);
 int ezb_vae_destroy(ezb_vae* h);
@@ -95,6 +98,10 @@ int ezb_vae_load_weight(ezb_vae* h, const char* ref_key, const float* data, cons
 int ezb_vae_finalize_weights(ezb_vae* h, void* stream);
 int ezb_vae_decode(ezb_vae* h, const float* z /*(B,latent,L)*/, float* wav /*(B,out_channels,L*prod(strides))*/, int B, int L,
                    void* stream);
+/* Autoencoder(audio=x) (src/modules/autoencoder_wrapper.py:69-73): OobleckEncoder (stable_vae/models/autoencoders.py:115-146) +
+ * VAEBottleneck.encode (bottleneck.py:66-87): z = mean + (softplus(scale) + 1e-4) * noise.  audio (B,1,T) fp32, T a multiple of the
+ * hop (480); noise (B,latent,L) fp32 drawn by the caller (the reference uses torch.randn_like), NULL -> z = mean. */
+int ezb_vae_encode(ezb_vae* h, const float* audio, const float* noise, float* z, int B, int T, void* stream);
 
 /* --- kernel-level hooks used by tests/ and profiling only (not part of the drop-in surface). */
 typedef struct {

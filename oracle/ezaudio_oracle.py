@@ -264,6 +264,27 @@ def vae_decode(sd: SD, z, strides=(2, 4, 6, 10), prefix="decoder."):
     return F.conv1d(x, wn_weight(sd, f"{p}{n + 1}"), None, padding=3)
 
 
+def vae_encode(sd: SD, audio, noise=None, strides=(2, 4, 6, 10), prefix="encoder."):
+    """OobleckEncoder.forward (stable_vae/models/autoencoders.py:115-146; EncoderBlock :63-80) followed by
+    VAEBottleneck.encode = vae_sample (stable_vae/models/bottleneck.py:66-70,77-87): audio (B,1,T) -> (B,128,T/480).
+    `noise` replaces torch.randn_like(mean) (None -> returns the mean, for deterministic checks)."""
+    p = prefix + "layers."
+    x = F.conv1d(audio, wn_weight(sd, p + "0"), sd[p + "0.bias"], padding=3)
+    for j, s in enumerate(strides):
+        q = f"{p}{j + 1}.layers."
+        for u, d in enumerate((1, 3, 9)):
+            x = vae_res_unit(x, sd, f"{q}{u}", d)
+        x = snake_beta(x, sd, q + "3")
+        x = F.conv1d(x, wn_weight(sd, q + "4"), sd[q + "4.bias"], stride=s, padding=math.ceil(s / 2))
+    n = len(strides) + 1
+    x = snake_beta(x, sd, f"{p}{n}")
+    x = F.conv1d(x, wn_weight(sd, f"{p}{n + 1}"), sd[f"{p}{n + 1}.bias"], padding=1)
+    mean, scale = x.chunk(2, dim=1)
+    if noise is None:
+        return mean
+    return noise * (F.softplus(scale) + 1e-4) + mean
+
+
 # --------------------------------------------------------------------------- sampling loop
 class DDIM:
     """Restatement of diffusers.DDIMScheduler for ckpts/ezaudio-xl.yml:52-60 (scaled_linear,

@@ -67,23 +67,36 @@ def vae_case(ref, name, dcfg, B, L, seed):
     print(name, tuple(wav.shape), float(wav.std()), float(wav.abs().max()))
 
 
+@torch.no_grad()
+def vae_enc_case(ref, name, ecfg, B, T, seed):
+    """OobleckEncoder output (mean | scale channels) of the unmodified reference; bottleneck sampling is checked by formula."""
+    sd = weights.synthetic_state_dict(weights.vae_encoder_param_shapes(ecfg), seed)
+    m = refimport.build(ref.OobleckEncoder, {k[len("encoder."):]: v for k, v in sd.items()}, **ecfg)
+    audio = 0.3 * torch.randn(B, 1, T, generator=torch.Generator().manual_seed(41))
+    out = m(audio)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), out=out.numpy(), sd_checksum=checksum(sd), seed=seed, B=B, T=T)
+    print(name, tuple(out.shape), float(out.std()), float(out.abs().max()))
+
+
 def main():
     ref = refimport.import_reference()
     assert ref is not None, "reference tree not found"
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
     only = set(sys.argv[1:])
-    global dit_case, controlnet_case, vae_case
+    global dit_case, controlnet_case, vae_case, vae_enc_case
     if only:
         def filt(f):
             return lambda ref, name, *a, **k: f(ref, name, *a, **k) if name in only else None
-        dit_case, controlnet_case, vae_case = filt(dit_case), filt(controlnet_case), filt(vae_case)
+        dit_case, controlnet_case, vae_case, vae_enc_case = filt(dit_case), filt(controlnet_case), filt(vae_case), filt(vae_enc_case)
     dit_case(ref, "dit_tiny72", synth.tiny_model(72), B=2, L=40, Lc=12, seed=3, inpaint=False, tscalar=999)
     dit_case(ref, "dit_tiny72_inpaint", synth.tiny_model(72), B=3, L=52, Lc=12, seed=3, inpaint=True, tvec=[999, 500, 19])
     dit_case(ref, "dit_tiny64", synth.tiny_model(64, heads=4, depth=2), B=2, L=130, Lc=100, seed=4, inpaint=False, tscalar=259)
     controlnet_case(ref, "controlnet_tiny72", synth.tiny_model(72), B=2, L=40, Lc=12, seed=5)
     vae_case(ref, "vae_tiny", synth.tiny_vae(16), B=2, L=9, seed=6)
     vae_case(ref, "vae_full", synth.VAE_DECODER, B=1, L=12, seed=6)
+    vae_enc_case(ref, "vae_enc_tiny", synth.tiny_vae_encoder(16), B=2, T=480 * 9, seed=8)
+    vae_enc_case(ref, "vae_enc_full", synth.VAE_ENCODER, B=1, T=480 * 12, seed=8)
     dit_case(ref, "dit_L_c1", synth.model_cfg("l"), B=1, L=256, Lc=100, seed=1, inpaint=False, tscalar=999)  # BASELINE config 1
     dit_case(ref, "dit_XL", synth.model_cfg("xl"), B=2, L=500, Lc=100, seed=2, inpaint=False, tscalar=479)
 

@@ -36,8 +36,8 @@ def import_reference():
         warnings.simplefilter("ignore")
         from src.models.conditioners import MaskDiT
         from src.models.controlnet import DiTControlNet
-        from src.modules.stable_vae.models.autoencoders import OobleckDecoder
-    ns.MaskDiT, ns.DiTControlNet, ns.OobleckDecoder = MaskDiT, DiTControlNet, OobleckDecoder
+        from src.modules.stable_vae.models.autoencoders import OobleckDecoder, OobleckEncoder
+    ns.MaskDiT, ns.DiTControlNet, ns.OobleckDecoder, ns.OobleckEncoder = MaskDiT, DiTControlNet, OobleckDecoder, OobleckEncoder
     return ns
 
 

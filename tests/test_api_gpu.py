@@ -33,7 +33,8 @@ def test_signatures_match_reference():
 
 def test_generate_audio_shapes_types_determinism(monkeypatch):
     from ezaudio_b200 import api
-    monkeypatch.setattr(config, "load_params", lambda name, path=None, table=None: _tiny_params())
+    tiny = _tiny_params()
+    monkeypatch.setattr(config, "load_params", lambda name, path=None, table=None: tiny)
     enc = api.SyntheticTextEncoder(64, 16)
     ez = api.EzAudio("s3_xl", ckpt_path="synthetic:3", vae_path="synthetic:6", text_encoder=enc, max_batch=2, max_length_s=2,
                      vae_config_path=None)
@@ -62,3 +63,24 @@ def test_controlnet_generate_audio(monkeypatch):
     ref_audio = (0.1 * torch.randn(3 * 24000, generator=torch.Generator().manual_seed(9))).numpy()
     sr, wav = ez.generate_audio("a siren", ref_audio, ddim_steps=3, random_seed=1)
     assert sr == 24000 and wav.dtype == np.float32 and wav.shape == (3 * 24000,) and np.isfinite(wav).all()
+
+
+def test_editing_audio_end_to_end(monkeypatch, tmp_path):
+    """api/ezaudio.py:132-207: crop -> VAE encode (stochastic bottleneck) -> masked sampling -> paste -> decode -> splice."""
+    from scipy.io import wavfile
+    from ezaudio_b200 import api
+    tiny = _tiny_params()
+    monkeypatch.setattr(config, "load_params", lambda name, path=None, table=None: tiny)
+    ez = api.EzAudio("s3_xl", ckpt_path="synthetic:3", vae_path="synthetic:6", text_encoder=api.SyntheticTextEncoder(64, 16), max_batch=1,
+                     max_length_s=6)
+    sr = 24000
+    t = np.arange(4 * sr) / sr
+    wav = (0.3 * np.sin(2 * np.pi * 220 * t)).astype(np.float32)
+    f = str(tmp_path / "in.wav")
+    wavfile.write(f, sr, (wav * 32767).astype(np.int16))
+    torch.manual_seed(0)
+    out_sr, out = ez.editing_audio("a bell", boundary=1, gt_file=f, mask_start=1.5, mask_length=1.0, ddim_steps=3, random_seed=3)
+    assert out_sr == sr and out.dtype == np.float32 and out.shape == (4 * sr,) and np.isfinite(out).all()
+    ref = wav / (np.abs(wav).max() + 1e-9)
+    assert np.allclose(out[: int(0.4 * sr)], ref[: int(0.4 * sr)], atol=1e-3)     # outside [mask-boundary, mask+boundary]: untouched original
+    assert not np.allclose(out[int(1.6 * sr): int(2.4 * sr)], ref[int(1.6 * sr): int(2.4 * sr)], atol=1e-2)  # edited span regenerated

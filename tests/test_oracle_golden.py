@@ -86,3 +86,19 @@ def test_cfg_rescale_matches_formula():
     c = u + 5.0 * (t - u)
     want = 0.75 * c * (t.flatten(1).std(1) / c.flatten(1).std(1)).view(-1, 1, 1) + 0.25 * c
     assert torch.allclose(out, want, atol=1e-6)
+
+
+@pytest.mark.parametrize("name,ecfg,B,L", [("vae_enc_tiny", synth.tiny_vae_encoder(16), 2, 9), ("vae_enc_full", synth.VAE_ENCODER, 1, 12)])
+def test_vae_encoder_oracle_matches_reference_golden(name, ecfg, B, L):
+    g = helpers.load_golden(name)
+    sd = weights.synthetic_state_dict(weights.vae_encoder_param_shapes(ecfg), 8)
+    audio = 0.3 * torch.randn(B, 1, 480 * L, generator=torch.Generator().manual_seed(41))
+    ref = torch.from_numpy(g["out"])  # (B, 256, L): mean | scale
+    with torch.no_grad():
+        mean = O.vae_encode(sd, audio, None, strides=tuple(ecfg["strides"]))
+        noise = torch.randn(B, 128, L, generator=torch.Generator().manual_seed(5))
+        z = O.vae_encode(sd, audio, noise, strides=tuple(ecfg["strides"]))
+    tol = 1e-5 + 1e-4 * float(ref.abs().max())
+    assert float((mean - ref[:, :128]).abs().max()) < tol
+    want = noise * (torch.nn.functional.softplus(ref[:, 128:]) + 1e-4) + ref[:, :128]   # bottleneck.py:66-70
+    assert float((z - want).abs().max()) < 10 * tol

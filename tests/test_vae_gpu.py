@@ -25,3 +25,26 @@ def test_vae_decode_matches_reference(name, dcfg, B, L, precision, rel):
     assert wav.shape == ref.shape
     err = float((wav.cpu() - ref).abs().max())
     assert err < rel * float(ref.abs().max()) + 1e-5, (err, float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("precision,rel", [("bf16x3", 1e-3), ("bf16", 6e-2)])
+@pytest.mark.parametrize("name,cfgs,B,L", [("vae_enc_tiny", (synth.tiny_vae_encoder(16), synth.tiny_vae(16)), 2, 9),
+                                           ("vae_enc_full", (synth.VAE_ENCODER, synth.VAE_DECODER), 1, 12)])
+def test_vae_encode_matches_reference(name, cfgs, B, L, precision, rel):
+    """OobleckEncoder (strided implicit-GEMM convs) + VAE bottleneck vs the UNMODIFIED reference encoder's golden output
+    (mean | scale), with injected noise for the sampling formula (bottleneck.py:66-70)."""
+    from ezaudio_b200.vae import OobleckDecoder
+    ecfg, dcfg = cfgs
+    g = helpers.load_golden(name)
+    sd = dict(weights.synthetic_state_dict(weights.vae_decoder_param_shapes(dcfg), 6))
+    sd.update(weights.synthetic_state_dict(weights.vae_encoder_param_shapes(ecfg), 8))
+    codec = OobleckDecoder(precision=precision, max_batch=B, max_latent_len=L, encoder_cfg=ecfg, **dcfg).load_state_dict(sd)
+    audio = 0.3 * torch.randn(B, 1, 480 * L, generator=torch.Generator().manual_seed(41))
+    ref = torch.from_numpy(g["out"])
+    mean = codec.encode(audio.cuda(), noise=False).cpu()
+    scale_ref = float(ref.abs().max())
+    assert float((mean - ref[:, :128]).abs().max()) < rel * scale_ref + 1e-5
+    noise = torch.randn(B, 128, L, generator=torch.Generator().manual_seed(5))
+    z = codec.encode(audio.cuda(), noise=noise.cuda()).cpu()
+    want = noise * (torch.nn.functional.softplus(ref[:, 128:]) + 1e-4) + ref[:, :128]
+    assert float((z - want).abs().max()) < 4 * rel * scale_ref + 1e-5
