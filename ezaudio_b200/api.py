@@ -45,13 +45,24 @@ class SyntheticTextEncoder:
 
 
 def _load_audio(path: str, sr: int) -> np.ndarray:
-    """librosa.load(path, sr=sr) stand-in (mono float32 resampled), api/ezaudio.py:146."""
-    import torchaudio
-    wav, fs = torchaudio.load(path)
-    wav = wav.mean(0)
+    """librosa.load(path, sr=sr) stand-in (mono float32, resampled), api/ezaudio.py:146.  librosa / soundfile / torchcodec are
+    not in this image: WAV is read with scipy, resampling is polyphase (scipy.signal.resample_poly)."""
+    from math import gcd
+
+    from scipy.io import wavfile
+    from scipy.signal import resample_poly
+    fs, data = wavfile.read(path)
+    if data.dtype.kind == "i":
+        data = data.astype(np.float32) / float(np.iinfo(data.dtype).max + 1)
+    elif data.dtype.kind == "u":
+        data = (data.astype(np.float32) - 128.0) / 128.0
+    data = data.astype(np.float32)
+    if data.ndim == 2:
+        data = data.mean(axis=1)
     if fs != sr:
-        wav = torchaudio.functional.resample(wav, fs, sr)
-    return wav.numpy().astype(np.float32)
+        g = gcd(int(fs), int(sr))
+        data = resample_poly(data, sr // g, fs // g).astype(np.float32)
+    return data
 
 
 def _load_t5(name: str, device):

@@ -147,6 +147,17 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                       // layout type: SWIZZLE_128B
   return d;
 }
+// K-major operand tile of exactly one K step (16 bf16 = 32-byte rows) written by TMA with CU_TENSOR_MAP_SWIZZLE_32B:
+// 8-row groups are 256 B apart.
+__device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(256 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)6 << 61;                       // layout type: SWIZZLE_32B
+  return d;
+}
 // Instruction descriptor: D fp32, A/B bf16, both K-major, shape M x N (K = 16 per instruction).
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
