@@ -60,6 +60,7 @@ _SIGS = {
     "ezb_launch_count_add": ([C.c_ulonglong], None),
     "ezb_prof_gemm_begin": ([], _I),
     "ezb_prof_gemm_end": ([C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double)], _I),
+    "ezb_prof_gemm_stats": ([C.c_double, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double)], _I),
     "ezb_test_gemm": ([_I, _VP, _I, _VP, _I, _I, _I, _I, _I, _I, C.POINTER(TestEpilogue), _I, _I, _I, _I, _I, _I, _VP], _I),
     "ezb_test_attention": ([_I, _VP, _VP, _VP, _VP, _VP, _I, _I, _I, _I, _I, _I, _VP], _I),
 }

@@ -231,4 +231,22 @@ EZB_API int ezb_prof_gemm_end(int* launches, double* flops, double* ms) {
   return EZB_OK;
 }
 
+// After ezb_prof_gemm_end: the same statistics restricted to launches with at least `min_flops` algorithmic FLOPs (the dominant
+// GEMM of the step is the GEGLU MLP-in projection, the largest single launch).
+EZB_API int ezb_prof_gemm_stats(double min_flops, int* launches, double* flops, double* ms) {
+  GemmProf& gp = gemm_prof();
+  double f = 0, t = 0;
+  int n = 0;
+  for (size_t i = 0; i < gp.flops.size(); ++i) {
+    if (gp.flops[i] < min_flops) continue;
+    float m = 0.f;
+    EZB_CUDA(cudaEventElapsedTime(&m, gp.ev[2 * i], gp.ev[2 * i + 1]));
+    f += gp.flops[i]; t += m; ++n;
+  }
+  if (launches) *launches = n;
+  if (flops) *flops = f;
+  if (ms) *ms = t;
+  return EZB_OK;
+}
+
 }  // extern "C"

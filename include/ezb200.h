@@ -128,6 +128,7 @@ unsigned long long ezb_launch_count(void);
 void ezb_launch_count_add(unsigned long long n); /* launches replayed from a captured CUDA graph */
 int ezb_prof_gemm_begin(void);
 int ezb_prof_gemm_end(int* launches, double* flops, double* ms);
+int ezb_prof_gemm_stats(double min_flops, int* launches, double* flops, double* ms); /* subset of the last profile */
 
 #ifdef __cplusplus
 }
