@@ -67,6 +67,7 @@ struct Dit {
         *mod_b = nullptr, *modf_b = nullptr;
   int n_timesteps = 0, ctx_Be = 0, ctx_Lc = 0, ctx_Lpad = 0;
   float2* rope_cs = nullptr;
+  float h_inv_freq[48] = {};
   bool fused_heads = false;
   bool pair = true;       // CTA-pair (cta_group::2) GEMMs
   bool swap_ab = true;    // swap-AB tiles for the fp32-output N = D layers
@@ -330,6 +331,7 @@ struct Dit {
     for (auto& kv : specs)
       if (!kv.second.loaded) return fail(EZB_ERR_WEIGHT, "missing state-dict key '%s'", kv.first.c_str());
     EZB_CUDA(cudaDeviceSynchronize());
+    EZB_CUDA(cudaMemcpy(h_inv_freq, blk[0].inv_freq, (dh / 2) * sizeof(float), cudaMemcpyDeviceToHost));
     for (auto& w : blk) {  // the fused heads epilogue takes these by value (constant bank)
       EZB_CUDA(cudaMemcpy(w.h_nq[0], w.nqw, dh * sizeof(float), cudaMemcpyDeviceToHost)); EZB_CUDA(cudaMemcpy(w.h_nq[1], w.nqb, dh * sizeof(float), cudaMemcpyDeviceToHost));
       EZB_CUDA(cudaMemcpy(w.h_nk[0], w.nkw, dh * sizeof(float), cudaMemcpyDeviceToHost)); EZB_CUDA(cudaMemcpy(w.h_nk[1], w.nkb, dh * sizeof(float), cudaMemcpyDeviceToHost));
@@ -412,6 +414,8 @@ struct Dit {
     e.D = D; e.H = H; e.L = L;
     for (int i = 0; i < 3; ++i) e.kind[i] = i < N / D ? kinds[i] : 0;
     e.rope = rope ? rope_cs : nullptr; e.rope_kinds = 3; e.rope_ld = d.max_len;
+    e.rope_mufu = opt_rope_mufu();
+    for (int i = 0; i < dh / 2 && i < 36; ++i) e.inv_freq[i] = h_inv_freq[i];
     e.out[0] = qo; e.out[1] = ko; e.out[2] = vto;
     e.ld_qk = DHP; e.dvp = DVP; e.Lpad = Lpad;
     if (qkv3_bn > 0 && N == 3 * D) {  // packed self-attention QKV: three heads per tile

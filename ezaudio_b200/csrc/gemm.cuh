@@ -551,8 +551,10 @@ struct EpiHeadsParams {
   int kind[3];                 // section (n / D) -> 0 q, 1 k, 2 v
   float nw[2][72];             // LayerNorm(dh) weight / bias for q, k -- BY VALUE: they live in the constant bank, so the
   float nb[2][72];             // normalisation FFMAs take them as operands instead of issuing 2 x dh loads per token
-  const float2* rope;          // [L][dh/2] (cos, sin) or null
+  const float2* rope;          // [L][dh/2] (cos, sin) table or null
   int rope_ld;
+  int rope_mufu;               // 1: evaluate cos/sin with the MUFU (__sincosf) from inv_freq instead of reading the table
+  float inv_freq[36];          // rotary.py:41-42 (checkpoint buffer), by value -> constant bank
   int rope_kinds;              // bit k set: apply RoPE to kind k
   __nv_bfloat16* out[3];       // per kind: q rows, k rows, v^T
   int ld_qk, dvp, Lpad;
@@ -614,9 +616,12 @@ struct EpiHeads {
         }
         if (ep.rope != nullptr && ((ep.rope_kinds >> kind) & 1)) {
           const float2* cs = ep.rope + (size_t)l * (DH / 2);
+          const float lf = (float)l;
 #pragma unroll
           for (int i = 0; i < DH / 2; ++i) {
-            const float2 c = __ldg(cs + i);
+            float2 c;
+            if (ep.rope_mufu) __sincosf(lf * ep.inv_freq[i], &c.y, &c.x);
+            else c = __ldg(cs + i);
             const float a = v[i], bq = v[i + DH / 2];
             v[i] = a * c.x - bq * c.y;
             v[i + DH / 2] = bq * c.x + a * c.y;

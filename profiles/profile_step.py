@@ -17,8 +17,13 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--steps", type=int, default=1)
 ap.add_argument("--vae", type=int, default=1)
 ap.add_argument("--batch", type=int, default=4)
+ap.add_argument("--opt", action="append", default=[], help="name=value runtime switches (ezb_set_option)")
 a = ap.parse_args()
 B, L = a.batch, 500
+from ezaudio_b200 import _lib  # noqa: E402
+for kv in a.opt:
+    k, v = kv.split("=")
+    _lib.check(_lib.lib().ezb_set_option(k.encode(), int(v)))
 enc = api.SyntheticTextEncoder(2048, 100)
 ez = api.EzAudio("s3_xl", ckpt_path="synthetic:2", vae_path="synthetic:6", text_encoder=enc, max_batch=B)
 te, tm = enc([f"p{i} a b c d e f" for i in range(B)])
@@ -51,3 +56,11 @@ for _ in range(a.vae):
     ez.autoencoder(embedding=lat)
 torch.cuda.synchronize()
 torch.cuda.cudart().cudaProfilerStop()
+# in-situ timing (no profiler): 20 back-to-back steps with CUDA events
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for i in range(20):
+    step(i)
+e1.record()
+torch.cuda.synchronize()
+print(f"opts {a.opt}: {e0.elapsed_time(e1) / 20:.3f} ms per eager DiT step (+CFG/DDIM)")
