@@ -54,6 +54,7 @@ _SIGS = {
     "ezb_vae_finalize_weights": ([_VP, _VP], _I),
     "ezb_vae_decode": ([_VP, _VP, _VP, _I, _I, _VP], _I),
     "ezb_vae_encode": ([_VP, _VP, _VP, _VP, _I, _I, _VP], _I),
+    "ezb_energy_condition": ([_I, _VP, _VP, _I, _I, _I, _I, _F, _I, _I, _VP], _I),
     "ezb_set_option": ([C.c_char_p, _I], _I),
     "ezb_debug_read": ([C.POINTER(C.c_ulonglong)], _I),
     "ezb_launch_count": ([], C.c_ulonglong),

@@ -15,7 +15,8 @@ from typing import Callable, List, Optional, Sequence, Union
 import numpy as np
 import torch
 
-from . import config, weights
+from . import _lib, config, weights
+from ._lib import EzbError
 from .dit import DiTControlNet, MaskDiT
 from .inference import inference
 from .scheduler import DDIMScheduler
@@ -196,18 +197,20 @@ class EzAudio(_Base):
         return sr, output_audio
 
 
-def energy_condition(audio: torch.Tensor, hop_size=240, window_size=1920, padding="reflect", min_db=-60, norm=True, **unused):
-    """EnergyExtractor + Conditioner (src/models/conditions/energy.py:19-56, condition_wrapper.py:26-42): (B,T) -> (B,1,T/hop)."""
-    import torch.nn.functional as F
-    n_frames = int(audio.size(-1) // hop_size)
-    pad = (window_size - hop_size) // 2
-    sq = F.pad(audio[:, None, :], (pad, pad), mode=padding)[:, 0] ** 2
-    energy = F.unfold(sq[:, None, None, :], (1, window_size), stride=hop_size)[:, :, :n_frames].mean(dim=1)
-    gain_db = 10 * torch.log10(torch.clamp(energy, min=float(np.power(10, min_db / 10))))
-    if norm:
-        mx = gain_db.max(dim=-1, keepdim=True)[0]
-        gain_db = (gain_db - min_db) / (mx - min_db + 1e-8)
-    return gain_db.unsqueeze(1).contiguous()
+def energy_condition(audio: torch.Tensor, hop_size=240, window_size=1920, padding="reflect", min_db=-60, norm=True, quantize_levels=None,
+                     **unused):
+    """EnergyExtractor + Conditioner (src/models/conditions/energy.py:19-56, condition_wrapper.py:26-42): (B,T) -> (B,1,T/hop).
+    One CUDA kernel (ezb_energy_condition); no torch fallback."""
+    if padding != "reflect":
+        raise NotImplementedError("energy conditioner: only padding='reflect' (the shipped config)")
+    if not audio.is_cuda:
+        raise EzbError("energy_condition needs a CUDA tensor")
+    a = audio.detach().to(torch.float32).contiguous()
+    B, T = a.shape
+    out = torch.empty(B, 1, T // hop_size, dtype=torch.float32, device=a.device)
+    _lib.check(_lib.lib().ezb_energy_condition(a.device.index or 0, a.data_ptr(), out.data_ptr(), B, T, int(hop_size), int(window_size), float(min_db),
+                                               int(bool(norm)), int(quantize_levels or 0), torch.cuda.current_stream(a.device).cuda_stream))
+    return out
 
 
 class EzAudio_ControlNet(_Base):

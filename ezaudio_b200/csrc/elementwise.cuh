@@ -488,3 +488,46 @@ __global__ void conv1d_direct_kernel(const float* __restrict__ in, const float* 
   out[i] = acc;
 }
 }  // namespace ezb
+
+namespace ezb {
+// ---------------------------------------------------------------------------------------------------------------------------------
+// EnergyExtractor (src/models/conditions/energy.py:19-56): per frame f (hop `hop`, window `win`, reflect padding (win-hop)/2 both sides)
+//   e_f = mean_{j<win} a[reflect(f*hop + j - pad)]^2 ; g_f = 10*log10(max(e_f, 10^(min_db/10)))
+//   norm: g_f = (g_f - min_db) / (max_f g_f - min_db + 1e-8) ; quantize_levels q>0: round(g*(q-1))/(q-1).
+// One CTA per clip: the frame energies stay in shared memory between the reduction over frames and the normalisation.
+// Memory-bound (each sample is read win/hop = 8 times, all but the first from L1/L2); runs once per generate call.
+__global__ void __launch_bounds__(1024) energy_kernel(const float* __restrict__ audio, float* __restrict__ out, int T, int n_frames, int hop,
+                                                      int win, float min_db, float floor_e, int norm, int qlevels) {
+  extern __shared__ float e_db[];  // n_frames
+  __shared__ float red[32];
+  const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const float* a = audio + (size_t)b * T;
+  const int pad = (win - hop) / 2;
+  float wmax = -INFINITY;
+  for (int f = warp; f < n_frames; f += nw) {
+    float acc = 0.f;
+    const int base = f * hop - pad;
+    for (int j = lane; j < win; j += 32) {
+      int i = base + j;
+      if (i < 0) i = -i;                      // F.pad(mode='reflect'): no edge repeat
+      if (i >= T) i = 2 * (T - 1) - i;
+      const float v = __ldg(a + i);
+      acc = fmaf(v, v, acc);
+    }
+    acc = warp_sum(acc);
+    const float g = 10.f * log10f(fmaxf(acc / (float)win, floor_e));
+    if (lane == 0) e_db[f] = g;
+    wmax = fmaxf(wmax, g);
+  }
+  if (lane == 0) red[warp] = wmax;
+  __syncthreads();
+  float mx = red[0];
+  for (int i = 1; i < nw; ++i) mx = fmaxf(mx, red[i]);
+  for (int f = threadIdx.x; f < n_frames; f += blockDim.x) {
+    float g = e_db[f];
+    if (norm) g = (g - min_db) / (mx - min_db + 1e-8f);
+    if (qlevels > 1) g = rintf(g * (float)(qlevels - 1)) / (float)(qlevels - 1);
+    out[(size_t)b * n_frames + f] = g;
+  }
+}
+}  // namespace ezb

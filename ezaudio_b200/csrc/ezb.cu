@@ -158,6 +158,20 @@ EZB_API int ezb_vae_encode(ezb_vae* h, const float* audio, const float* noise, f
   if (!h || !audio || !z) return fail(EZB_ERR_ARG, "ezb_vae_encode: null argument");
   return reinterpret_cast<Vae*>(h)->encode(audio, noise, z, B, T, ST(stream));
 }
+EZB_API int ezb_energy_condition(int device, const float* audio, float* out, int B, int T, int hop, int win, float min_db, int norm, int qlevels,
+                                 void* stream) {
+  if (!audio || !out) return fail(EZB_ERR_ARG, "ezb_energy_condition: null pointer");
+  if (B < 1 || hop < 1 || win < hop || T < hop) return fail(EZB_ERR_SHAPE, "ezb_energy_condition: B=%d T=%d hop=%d window=%d", B, T, hop, win);
+  const int pad = (win - hop) / 2, n_frames = T / hop;
+  if (pad >= T) return fail(EZB_ERR_SHAPE, "ezb_energy_condition: reflect padding %d needs more than %d samples", pad, T);
+  if ((size_t)n_frames * sizeof(float) > 200 * 1024) return fail(EZB_ERR_SHAPE, "ezb_energy_condition: %d frames exceed the shared-memory table", n_frames);
+  EZB_CUDA(cudaSetDevice(device));
+  EZB_CUDA(cudaFuncSetAttribute(energy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  ++launch_counter();
+  energy_kernel<<<B, 1024, n_frames * sizeof(float), ST(stream)>>>(audio, out, T, n_frames, hop, win, min_db, powf(10.f, min_db / 10.f), norm, qlevels);
+  EZB_CUDA(cudaGetLastError());
+  return EZB_OK;
+}
 EZB_API int ezb_vae_decode(ezb_vae* h, const float* z, float* wav, int B, int L, void* stream) {
   if (!h || !z || !wav) return fail(EZB_ERR_ARG, "ezb_vae_decode: null argument");
   return reinterpret_cast<Vae*>(h)->decode(z, wav, B, L, ST(stream));

@@ -68,3 +68,11 @@ def synth_gt(B: int, L: int, C: int = 128, seed: int = 11, lo: float = 0.25, hi:
     m = torch.zeros(B, C, L, dtype=torch.bool)
     m[:, :, int(lo * L):int(hi * L)] = True
     return gt, m
+
+
+def synth_energy_audio(B, T, seed=9):
+    """Clips of very different loudness (1e-3 .. 0.3), slow amplitude modulation, a silent stretch in clip 0 (exercises the min_db floor)."""
+    g = torch.Generator().manual_seed(seed)
+    audio = torch.randn(B, T, generator=g) * torch.logspace(-3, -0.5, B)[:, None]
+    audio[0, T // 3: T // 2] = 0.0
+    return audio * (0.5 + 0.5 * torch.sin(torch.arange(T) / 2400.0))[None]

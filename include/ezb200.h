@@ -103,6 +103,12 @@ int ezb_vae_decode(ezb_vae* h, const float* z /*(B,latent,L)*/, float* wav /*(B,
  * hop (480); noise (B,latent,L) fp32 drawn by the caller (the reference uses torch.randn_like), NULL -> z = mean. */
 int ezb_vae_encode(ezb_vae* h, const float* audio, const float* noise, float* z, int B, int T, void* stream);
 
+/* EnergyExtractor.forward (src/models/conditions/energy.py:19-56) as wrapped by Conditioner (condition_wrapper.py:26-42): audio (B,T) fp32
+ * -> (B, T/hop) fp32 frame energies in dB, normalised per clip when norm != 0; quantize_levels <= 1 disables quantisation. Only the shipped
+ * padding mode ('reflect') exists. */
+int ezb_energy_condition(int device, const float* audio, float* out, int B, int T, int hop_size, int window_size, float min_db, int norm,
+                         int quantize_levels, void* stream);
+
 /* --- kernel-level hooks used by tests/ and profiling only (not part of the drop-in surface). */
 typedef struct {
   const float* bias; int32_t bias_mod;

@@ -285,6 +285,23 @@ def vae_encode(sd: SD, audio, noise=None, strides=(2, 4, 6, 10), prefix="encoder
     return noise * (F.softplus(scale) + 1e-4) + mean
 
 
+def energy_extract(audio, hop_size=240, window_size=1920, min_db=-60.0, norm=True, quantize_levels=None):
+    """EnergyExtractor.forward (src/models/conditions/energy.py:19-56), reflect padding: audio (B,T) -> (B, T//hop, 1)."""
+    B, T = audio.shape
+    n_frames = T // hop_size
+    pad = (window_size - hop_size) // 2
+    sq = F.pad(audio[:, None, :], (pad, pad), mode="reflect")[:, 0].double() ** 2
+    csum = torch.cat([sq.new_zeros(B, 1), sq.cumsum(-1)], dim=-1)
+    start = torch.arange(n_frames) * hop_size
+    energy = ((csum[:, start + window_size] - csum[:, start]) / window_size).float()
+    gain_db = 10 * torch.log10(torch.clamp(energy, min=10 ** (min_db / 10)))
+    if norm:
+        gain_db = (gain_db - min_db) / (gain_db.max(dim=-1, keepdim=True)[0] - min_db + 1e-8)
+    if quantize_levels is not None:
+        gain_db = torch.round(gain_db * (quantize_levels - 1)) / (quantize_levels - 1)
+    return gain_db.unsqueeze(-1)
+
+
 # --------------------------------------------------------------------------- sampling loop
 class DDIM:
     """Restatement of diffusers.DDIMScheduler for ckpts/ezaudio-xl.yml:52-60 (scaled_linear,

@@ -78,17 +78,28 @@ def vae_enc_case(ref, name, ecfg, B, T, seed):
     print(name, tuple(out.shape), float(out.std()), float(out.abs().max()))
 
 
+@torch.no_grad()
+def energy_case(ref, name, B, T, seed, **kw):
+    """EnergyExtractor (src/models/conditions/energy.py) on clips of different loudness, one of them with silent stretches."""
+    audio = synth.synth_energy_audio(B, T, seed)
+    out = ref.EnergyExtractor(**kw)(audio)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), out=out.numpy(), audio_checksum=float(audio.double().abs().sum()), seed=seed, B=B, T=T,
+                        **{k: (v if v is not None else -1) for k, v in kw.items() if k != "padding"})
+    print(name, tuple(out.shape), float(out.mean()), float(out.min()))
+
+
 def main():
     ref = refimport.import_reference()
     assert ref is not None, "reference tree not found"
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
     only = set(sys.argv[1:])
-    global dit_case, controlnet_case, vae_case, vae_enc_case
+    global dit_case, controlnet_case, vae_case, vae_enc_case, energy_case
     if only:
         def filt(f):
             return lambda ref, name, *a, **k: f(ref, name, *a, **k) if name in only else None
         dit_case, controlnet_case, vae_case, vae_enc_case = filt(dit_case), filt(controlnet_case), filt(vae_case), filt(vae_enc_case)
+        energy_case = filt(energy_case)
     dit_case(ref, "dit_tiny72", synth.tiny_model(72), B=2, L=40, Lc=12, seed=3, inpaint=False, tscalar=999)
     dit_case(ref, "dit_tiny72_inpaint", synth.tiny_model(72), B=3, L=52, Lc=12, seed=3, inpaint=True, tvec=[999, 500, 19])
     dit_case(ref, "dit_tiny64", synth.tiny_model(64, heads=4, depth=2), B=2, L=130, Lc=100, seed=4, inpaint=False, tscalar=259)
@@ -97,6 +108,9 @@ def main():
     vae_case(ref, "vae_full", synth.VAE_DECODER, B=1, L=12, seed=6)
     vae_enc_case(ref, "vae_enc_tiny", synth.tiny_vae_encoder(16), B=2, T=480 * 9, seed=8)
     vae_enc_case(ref, "vae_enc_full", synth.VAE_ENCODER, B=1, T=480 * 12, seed=8)
+    energy_case(ref, "energy_api", B=3, T=24000 * 2, seed=9, hop_size=240, window_size=1920, padding="reflect", min_db=-60, norm=True)
+    energy_case(ref, "energy_quant", B=2, T=5000, seed=10, hop_size=512, window_size=1024, padding="reflect", min_db=-80, norm=True,
+                quantize_levels=16)
     dit_case(ref, "dit_L_c1", synth.model_cfg("l"), B=1, L=256, Lc=100, seed=1, inpaint=False, tscalar=999)  # BASELINE config 1
     dit_case(ref, "dit_XL", synth.model_cfg("xl"), B=2, L=500, Lc=100, seed=2, inpaint=False, tscalar=479)
 

@@ -38,6 +38,12 @@ def import_reference():
         from src.models.controlnet import DiTControlNet
         from src.modules.stable_vae.models.autoencoders import OobleckDecoder, OobleckEncoder
     ns.MaskDiT, ns.DiTControlNet, ns.OobleckDecoder, ns.OobleckEncoder = MaskDiT, DiTControlNet, OobleckDecoder, OobleckEncoder
+    # the conditions package __init__ pulls librosa/julius; load the one file the shipped ControlNet config uses
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_ref_energy", os.path.join(root, "src/models/conditions/energy.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    ns.EnergyExtractor = mod.EnergyExtractor
     return ns
 
 

@@ -7,6 +7,7 @@ import pytest
 import torch
 
 from ezaudio_b200 import config, synth
+from tests import helpers
 
 pytestmark = pytest.mark.gpu
 
@@ -84,3 +85,21 @@ def test_editing_audio_end_to_end(monkeypatch, tmp_path):
     ref = wav / (np.abs(wav).max() + 1e-9)
     assert np.allclose(out[: int(0.4 * sr)], ref[: int(0.4 * sr)], atol=1e-3)     # outside [mask-boundary, mask+boundary]: untouched original
     assert not np.allclose(out[int(1.6 * sr): int(2.4 * sr)], ref[int(1.6 * sr): int(2.4 * sr)], atol=1e-2)  # edited span regenerated
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,kw", [("energy_api", dict(hop_size=240, window_size=1920, min_db=-60.0, norm=True)),
+                                     ("energy_quant", dict(hop_size=512, window_size=1024, min_db=-80.0, norm=True, quantize_levels=16))])
+def test_energy_condition_kernel_matches_reference(name, kw):
+    """ezb_energy_condition vs the UNMODIFIED reference EnergyExtractor's golden output (and the oracle on a 10-s clip)."""
+    from ezaudio_b200.api import energy_condition
+    from oracle import ezaudio_oracle as O
+    g = helpers.load_golden(name)
+    audio = synth.synth_energy_audio(int(g["B"]), int(g["T"]), int(g["seed"]))
+    out = energy_condition(audio.cuda(), **kw).cpu()
+    assert out.shape == (int(g["B"]), 1, int(g["T"]) // kw["hop_size"])
+    assert float((out[:, 0] - torch.from_numpy(g["out"])[..., 0]).abs().max()) < 2e-5
+    long = synth.synth_energy_audio(4, 240000, 3)
+    got = energy_condition(long.cuda(), hop_size=240, window_size=1920, min_db=-60, norm=True).cpu()
+    want = O.energy_extract(long, 240, 1920, -60.0, True)
+    assert got.shape == (4, 1, 1000) and float((got[:, 0] - want[..., 0]).abs().max()) < 2e-5

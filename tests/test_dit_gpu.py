@@ -9,6 +9,7 @@ Tolerances (max-abs on outputs of std ~1, |max| ~4):
 import pytest
 import torch
 
+from ezaudio_b200 import synth, weights
 from tests import helpers
 
 pytestmark = pytest.mark.gpu
@@ -43,3 +44,27 @@ def test_dit_parity_mode_matches_reference(name):
 def test_dit_fast_mode_within_bf16_floor(name):
     mx, mean = _run_case(name, "bf16")
     assert mx < TOL["bf16"][0] and mean < TOL["bf16"][1], (mx, mean)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["bf16x3", "bf16"])
+def test_long_clip_30s_matches_oracle(precision):
+    """C5 shape: L = 1500 latent frames (30 s) - 12 x 12 attention tiles per head, rotary positions up to 1499 - on the tiny dh=72 model,
+    inpainting inputs, CFG-style batch with a one-token unconditional row.  Oracle computed here on the host cores."""
+    from ezaudio_b200.dit import MaskDiT
+    from oracle import ezaudio_oracle as O
+    cfg = synth.tiny_model(72)
+    B, L, Lc = 2, 1500, 100
+    sd = weights.synthetic_state_dict(weights.dit_param_shapes(cfg), 3)
+    x = synth.synth_latents(B, L)
+    ctx, mask = synth.synth_context(B, Lc, cfg["context_dim"])
+    mask[-1] = False
+    mask[-1, 0] = True
+    gt, gm = synth.synth_gt(B, L)
+    t = torch.tensor([999, 19])
+    with torch.no_grad():
+        want, _ = O.maskdit_forward(sd, cfg, x, t, ctx, mask, gt=gt.clone(), mae_mask_infer=gm)
+    m = MaskDiT(precision=precision, max_batch=B, max_len=L, max_ctx_len=Lc, max_timesteps=8, **cfg).load_state_dict(sd)
+    got, _ = m(x.cuda(), t.cuda(), ctx.cuda(), context_mask=mask.cuda(), gt=gt.cuda(), mae_mask_infer=gm.cuda())
+    err = (got.cpu() - want).abs()
+    assert float(err.max()) < TOL[precision][0] and float(err.mean()) < TOL[precision][1], (float(err.max()), float(err.mean()))

@@ -102,3 +102,15 @@ def test_vae_encoder_oracle_matches_reference_golden(name, ecfg, B, L):
     assert float((mean - ref[:, :128]).abs().max()) < tol
     want = noise * (torch.nn.functional.softplus(ref[:, 128:]) + 1e-4) + ref[:, :128]   # bottleneck.py:66-70
     assert float((z - want).abs().max()) < 10 * tol
+
+
+@pytest.mark.parametrize("name,kw", [("energy_api", dict(hop_size=240, window_size=1920, min_db=-60.0, norm=True)),
+                                     ("energy_quant", dict(hop_size=512, window_size=1024, min_db=-80.0, norm=True, quantize_levels=16))])
+def test_energy_oracle_matches_reference_golden(name, kw):
+    """EnergyExtractor of the unmodified reference (src/models/conditions/energy.py) vs the oracle's restatement."""
+    g = helpers.load_golden(name)
+    audio = synth.synth_energy_audio(int(g["B"]), int(g["T"]), int(g["seed"]))
+    assert abs(float(audio.double().abs().sum()) - float(g["audio_checksum"])) < 1e-6 * float(g["audio_checksum"])
+    out = O.energy_extract(audio, **kw)
+    assert out.shape == g["out"].shape
+    assert float((out - torch.from_numpy(g["out"])).abs().max()) < 2e-5
