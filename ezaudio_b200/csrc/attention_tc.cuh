@@ -55,7 +55,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   using SM = AttnSmem<DH>;
   constexpr bool HAS_TAIL = DH > 64;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  // 1024-byte alignment by pointer arithmetic on the __shared__ array (a round trip through uintptr_t loses the address space and
+  // turns every staging access into a generic LD.E / ST.E)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int VB = SM::v_bytes(p.dvp);
   uint8_t* sQ = smem;                      // [2][Q_BYTES]
   uint8_t* sK = sQ + 2 * SM::Q_BYTES;      // [2][K_BYTES]

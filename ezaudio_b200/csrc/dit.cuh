@@ -8,6 +8,7 @@
 
 #include "attention_simt.cuh"
 #include "attention_tc.cuh"
+#include "attention_tc4.cuh"
 #include "host.cuh"
 
 namespace ezb {
@@ -449,6 +450,7 @@ struct Dit {
       EZB_CUDA(cudaGetLastError());
       return EZB_OK;
     }
+    if (opt_attn4()) return attention_tc4(*dev, st, q16_, k16_, vt16_, mask, attn_out, B, H, Lq, Lk, Lkpad, dh, DHP, DVP, scale);
     return attention_tc(*dev, st, q16_, k16_, vt16_, mask, attn_out, B, H, Lq, Lk, Lkpad, dh, DHP, DVP, scale);
   }
 

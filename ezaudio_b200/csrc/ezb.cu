@@ -193,6 +193,9 @@ EZB_API int ezb_test_attention(int device, const void* q, const void* k, const v
     return EZB_OK;
   }
   const int dhp = (dh + 63) / 64 * 64, dvp = (dh + 15) / 16 * 16, lkpad = (Lk + 7) / 8 * 8;
+  if (opt_attn4())
+    return attention_tc4(device_ctx(device), ST(stream), reinterpret_cast<const __nv_bfloat16*>(q), reinterpret_cast<const __nv_bfloat16*>(k),
+                         reinterpret_cast<const __nv_bfloat16*>(v), key_mask, reinterpret_cast<__nv_bfloat16*>(out), B, H, Lq, Lk, lkpad, dh, dhp, dvp, scale);
   return attention_tc(device_ctx(device), ST(stream), reinterpret_cast<const __nv_bfloat16*>(q), reinterpret_cast<const __nv_bfloat16*>(k),
                       reinterpret_cast<const __nv_bfloat16*>(v), key_mask, reinterpret_cast<__nv_bfloat16*>(out), B, H, Lq, Lk, lkpad, dh, dhp, dvp, scale);
 }
@@ -204,6 +207,7 @@ EZB_API int ezb_set_option(const char* name, int value) {
   if (name && !strcmp(name, "pdl")) { opt_pdl() = value; return EZB_OK; }
   if (name && !strcmp(name, "swap_ab")) { opt_swap_ab() = value; return EZB_OK; }
   if (name && !strcmp(name, "qkv3")) { opt_qkv3() = value; return EZB_OK; }
+  if (name && !strcmp(name, "attn4")) { opt_attn4() = value; return EZB_OK; }
   if (name && !strcmp(name, "rope_mufu")) { opt_rope_mufu() = value; return EZB_OK; }
   if (name && !strcmp(name, "gemm_debug")) {  // cycle counters of CTA 0 of every pair-GEMM launch (accumulated)
     if (value && !gemm_dbg_buf()) { EZB_CUDA(cudaMalloc(&gemm_dbg_buf(), 64)); EZB_CUDA(cudaMemset(gemm_dbg_buf(), 0, 64)); }

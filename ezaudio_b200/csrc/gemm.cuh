@@ -414,7 +414,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   constexpr int STAGES = SM::STAGES;
   constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  // 1024-byte alignment by pointer arithmetic on the __shared__ array (a round trip through uintptr_t loses the address space and
+  // turns every staging access into a generic LD.E / ST.E)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * SM::A_BYTES;
   float* sStage = reinterpret_cast<float*>(sB + STAGES * SM::B_BYTES);
@@ -670,7 +672,9 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   constexpr int STAGES = SM::STAGES;
   constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  // 1024-byte alignment by pointer arithmetic on the __shared__ array (a round trip through uintptr_t loses the address space and
+  // turns every staging access into a generic LD.E / ST.E)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * SM::A_BYTES;
   float* sStage = reinterpret_cast<float*>(sB + STAGES * SM::B_BYTES);

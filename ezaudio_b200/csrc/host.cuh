@@ -170,6 +170,10 @@ struct Device {
   TmapCache tmaps;
 };
 
+inline int& opt_attn4() {
+  static int v = 1;
+  return v;
+}
 inline int& opt_rope_mufu() {
   static int v = 1;
   return v;

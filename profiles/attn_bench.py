@@ -10,6 +10,9 @@ from ezaudio_b200 import _lib  # noqa: E402
 
 L = _lib.lib()
 L.ezb_set_option(b"gemm_debug", 1)
+if len(sys.argv) > 1:
+    L.ezb_set_option(b"attn4", int(sys.argv[1]))
+    print("attn4 =", sys.argv[1])
 
 
 def run(B, H, Lq, Lk, dh, masked, label, reps=20):

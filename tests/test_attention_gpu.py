@@ -17,16 +17,21 @@ def _ref(q, k, v, mask):
     return o.permute(0, 2, 1, 3).reshape(q.shape[0], q.shape[2], -1)
 
 
-@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("impl", [0, 1, 4])  # 4 = impl 1 with the two-tile ping-pong kernel (attention_tc4.cuh)
 @pytest.mark.parametrize("B,H,Lq,Lk,dh,masked", [(2, 4, 500, 500, 72, False), (2, 3, 256, 256, 64, False), (3, 2, 500, 100, 72, True),
                                                  (2, 2, 40, 12, 72, True), (1, 2, 130, 130, 64, False), (1, 16, 1500, 1500, 72, False),
-                                                 (2, 2, 37, 100, 64, True)])
+                                                 (2, 2, 37, 100, 64, True), (8, 16, 500, 500, 72, False), (2, 5, 700, 700, 72, "grow")])
 def test_attention(impl, B, H, Lq, Lk, dh, masked):
     from ezaudio_b200 import _lib
     g = torch.Generator(device="cuda").manual_seed(Lq * 7 + Lk + dh)
     q = torch.randn(B, H, Lq, dh, device="cuda", generator=g) * 1.5
     k = torch.randn(B, H, Lk, dh, device="cuda", generator=g) * 1.5
     v = torch.randn(B, H, Lk, dh, device="cuda", generator=g)
+    if masked == "grow":  # scores grow by orders of magnitude from key block to key block: exercises the in-place O rescale
+        k = k * torch.linspace(0.2, 3.0, Lk, device="cuda")[None, None, :, None]
+        masked = False
+    attn4 = impl == 4
+    impl = 1 if attn4 else impl
     mask = None
     if masked:
         mask = torch.zeros(B, Lk, dtype=torch.uint8, device="cuda")
@@ -48,8 +53,20 @@ def test_attention(impl, B, H, Lq, Lk, dh, masked):
         vt[:, :, Lk:] = 7.0  # beyond the true length: must never be read
         args = (qb, kb, vt)
         ref = _ref(q.bfloat16().float(), k.bfloat16().float(), v.bfloat16().float(), mask)
-    _lib.check(L.ezb_test_attention(0, _lib.ptr(args[0]), _lib.ptr(args[1]), _lib.ptr(args[2]), _lib.ptr(mask), _lib.ptr(out), B, H, Lq, Lk, dh, impl,
-                                    _lib.stream_ptr()))
+    _lib.check(L.ezb_set_option(b"attn4", int(attn4)))
+    try:
+        _run(L, _lib, args, mask, out, B, H, Lq, Lk, dh, impl)
+    finally:
+        _lib.check(L.ezb_set_option(b"attn4", ATTN4_DEFAULT))
     torch.cuda.synchronize()
     err = (out.float() - ref).abs().max().item()
     assert math.isfinite(err) and err < (2e-2 if impl == 0 else 3e-2), err
+
+
+ATTN4_DEFAULT = 1
+
+
+def _run(L, _lib, args, mask, out, B, H, Lq, Lk, dh, impl):
+    _lib.check(L.ezb_test_attention(0, _lib.ptr(args[0]), _lib.ptr(args[1]), _lib.ptr(args[2]), _lib.ptr(mask), _lib.ptr(out), B, H, Lq, Lk, dh, impl,
+                                    _lib.stream_ptr()))
+    torch.cuda.synchronize()
