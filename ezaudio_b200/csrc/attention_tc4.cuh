@@ -36,6 +36,18 @@ struct Attn4Params {
   float scale_log2;         // (1/sqrt(dh)) * log2(e)
 };
 
+// 2^x on the FMA pipe (Cody-Waite split + degree-3 minimax polynomial on [-0.5, 0.5], max relative error 7.8e-5 -- far below the bf16
+// rounding of P): used for one element in four so that the MUFU (16 exp2 / clock / SM) is not the only unit working through the scores.
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -125.f);
+  const float t = x + 12582912.f;          // 1.5 * 2^23: the integer part lands in the low mantissa bits
+  const float f = x - (t - 12582912.f);    // [-0.5, 0.5]
+  float q = fmaf(0.05508868f, f, 0.24260405f);
+  q = fmaf(q, f, 0.69327623f);
+  q = fmaf(q, f, 0.99992895f);
+  return __int_as_float(__float_as_int(q) + (__float_as_int(t) << 23));
+}
+
 template <int DH>
 struct Attn4Smem {
   static constexpr int TAIL = DH > 64 ? 4096 : 0;
@@ -45,7 +57,7 @@ struct Attn4Smem {
   static __host__ __device__ constexpr int total(int dvp) { return 1024 + 2 * Q_BYTES + A4_STAGES * K_BYTES + A4_STAGES * v_bytes(dvp) + 512; }
 };
 
-template <int DH>
+template <int DH, int POLY>
 __global__ void __launch_bounds__(A4_THREADS, 1)
 attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
              const __grid_constant__ CUtensorMap tmQt, const __grid_constant__ CUtensorMap tmKt, const Attn4Params p) {
@@ -184,6 +196,31 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
     const uint32_t tS = tmem0 + g * 128 + t_row, tO = tmem0 + 256 + g * 128 + t_row;
     const int Ug = g ? U1 : U0;
     float m_ref = -INFINITY, l_run = 0.f;
+
+    auto write_item = [&](int item, float l_fin) {  // O / l of a finished item -> global (its last P V has completed)
+      uint32_t orr[64];
+      uint32_t o8[8];
+      tmem_ld_32x64(tO, orr);
+      if (DH > 64) tmem_ld_32x8(tO + 64, o8);
+      tmem_ld_wait();
+      tc_fence_before();
+      const float inv = 1.f / l_fin;
+      const int bh = item / p.n_qt, b = bh / p.H, h = bh - b * p.H;
+      const int qrow = (item - bh * p.n_qt) * 128 + r;
+      if (qrow < p.Lq) {
+        uint4* orow = reinterpret_cast<uint4*>(p.out + ((size_t)b * p.Lq + qrow) * (size_t)(p.H * DH) + h * DH);
+#pragma unroll
+        for (int v = 0; v < 8; ++v)
+          orow[v] = make_uint4(pack_bf16(__uint_as_float(orr[8 * v]) * inv, __uint_as_float(orr[8 * v + 1]) * inv),
+                               pack_bf16(__uint_as_float(orr[8 * v + 2]) * inv, __uint_as_float(orr[8 * v + 3]) * inv),
+                               pack_bf16(__uint_as_float(orr[8 * v + 4]) * inv, __uint_as_float(orr[8 * v + 5]) * inv),
+                               pack_bf16(__uint_as_float(orr[8 * v + 6]) * inv, __uint_as_float(orr[8 * v + 7]) * inv));
+        if (DH > 64)
+          orow[8] = make_uint4(pack_bf16(__uint_as_float(o8[0]) * inv, __uint_as_float(o8[1]) * inv), pack_bf16(__uint_as_float(o8[2]) * inv, __uint_as_float(o8[3]) * inv),
+                               pack_bf16(__uint_as_float(o8[4]) * inv, __uint_as_float(o8[5]) * inv), pack_bf16(__uint_as_float(o8[6]) * inv, __uint_as_float(o8[7]) * inv));
+      }
+    };
+
     for (int s = 0; s < Ug; ++s) {
       const int itl = s / n_kv, j = s - itl * n_kv;
       const int item = blockIdx.x + (2 * itl + g) * gridDim.x;
@@ -218,6 +255,7 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
       // reference max: fresh for the first key block of an item, afterwards only moved when the row max outgrew it by 2^8
       float fac = 1.f;
       bool need = false;
+      const float l_prev = l_run;  // the previous item's sum (retired below when j == 0)
       if (j == 0) {
         m_ref = mx;
         l_run = 0.f;
@@ -235,13 +273,19 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
 #pragma unroll
       for (int c = 0; c < 128; c += 2) {
         const float p0 = ex2_approx(fmaf(__uint_as_float(sr[c]), p.scale_log2, -mb));
-        const float p1 = ex2_approx(fmaf(__uint_as_float(sr[c + 1]), p.scale_log2, -mb));
+        const float x1 = fmaf(__uint_as_float(sr[c + 1]), p.scale_log2, -mb);
+        const float p1 = (POLY && (c & 2)) ? ex2_poly(x1) : ex2_approx(x1);
         sum4[(c >> 1) & 3] += p0 + p1;
         pk[c >> 1] = pack_bf16(p0, p1);
       }
       l_run += (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
       tmem_st_32x32(tS, pk);
       tmem_st_32x32(tS + 32, pk + 32);
+      if (s > 0 && j == 0) {  // retire the previous item while this unit's S / P hand-off is in flight: its last P V wrote the O that this
+        mbar_wait(&o_full[g], (s - 1) & 1);   // unit's P V (accumulate = 0, issued after our arrive) will overwrite
+        tc_fence_after();
+        write_item(item - 2 * (int)gridDim.x, l_prev);
+      }
       // in-place rescale of the O rows whose reference max moved (warp-collective TMEM access: every lane takes part)
       if (j != 0 && __any_sync(0xffffffffu, need)) {
         mbar_wait(&o_full[g], (s - 1) & 1);  // P_{s-1} V_{s-1} has landed
@@ -265,31 +309,11 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&p_full[g]);
-      if (j == n_kv - 1) {  // item complete: O / l -> global
-        mbar_wait(&o_full[g], s & 1);
-        tc_fence_after();
-        uint32_t orr[64];
-        uint32_t o8[8];
-        tmem_ld_32x64(tO, orr);
-        if (DH > 64) tmem_ld_32x8(tO + 64, o8);
-        tmem_ld_wait();
-        tc_fence_before();
-        const float inv = 1.f / l_run;
-        const int q0 = (item - bh * p.n_qt) * 128, h = bh - b * p.H;
-        const int qrow = q0 + r;
-        if (qrow < p.Lq) {
-          uint4* orow = reinterpret_cast<uint4*>(p.out + ((size_t)b * p.Lq + qrow) * (size_t)(p.H * DH) + h * DH);
-#pragma unroll
-          for (int v = 0; v < 8; ++v)
-            orow[v] = make_uint4(pack_bf16(__uint_as_float(orr[8 * v]) * inv, __uint_as_float(orr[8 * v + 1]) * inv),
-                                 pack_bf16(__uint_as_float(orr[8 * v + 2]) * inv, __uint_as_float(orr[8 * v + 3]) * inv),
-                                 pack_bf16(__uint_as_float(orr[8 * v + 4]) * inv, __uint_as_float(orr[8 * v + 5]) * inv),
-                                 pack_bf16(__uint_as_float(orr[8 * v + 6]) * inv, __uint_as_float(orr[8 * v + 7]) * inv));
-          if (DH > 64)
-            orow[8] = make_uint4(pack_bf16(__uint_as_float(o8[0]) * inv, __uint_as_float(o8[1]) * inv), pack_bf16(__uint_as_float(o8[2]) * inv, __uint_as_float(o8[3]) * inv),
-                                 pack_bf16(__uint_as_float(o8[4]) * inv, __uint_as_float(o8[5]) * inv), pack_bf16(__uint_as_float(o8[6]) * inv, __uint_as_float(o8[7]) * inv));
-        }
-      }
+    }
+    if (Ug > 0) {  // last item of this group
+      mbar_wait(&o_full[g], (Ug - 1) & 1);
+      tc_fence_after();
+      write_item(blockIdx.x + (2 * ((Ug - 1) / n_kv) + g) * (int)gridDim.x, l_run);
     }
   }
   tc_fence_before();
@@ -315,16 +339,15 @@ inline int attention_tc4(Device& dev, cudaStream_t st, const __nv_bfloat16* q, c
   p.n_items = p.n_qt * B * H;
   p.scale_log2 = scale * 1.4426950408889634f;
   const int grid = p.n_items < dev.num_sms ? p.n_items : dev.num_sms;
+  auto go = [&](auto kern, int smem) -> int {
+    EZB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    return launch_k(kern, dim3(grid), dim3(A4_THREADS), smem, st, 1, *tq, *tk, *tv, *tqt, *tkt, p);
+  };
+  const bool poly = opt_attn_poly() != 0;
   if (dh == 64) {
-    const int smem = Attn4Smem<64>::total(dvp);
-    static bool set = false;
-    if (!set) { EZB_CUDA(cudaFuncSetAttribute(attn4_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set = true; }
-    EZB_TRY(launch_k(attn4_kernel<64>, dim3(grid), dim3(A4_THREADS), smem, st, 1, *tq, *tk, *tv, *tqt, *tkt, p));
+    EZB_TRY(poly ? go(attn4_kernel<64, 1>, Attn4Smem<64>::total(dvp)) : go(attn4_kernel<64, 0>, Attn4Smem<64>::total(dvp)));
   } else {
-    const int smem = Attn4Smem<72>::total(dvp);
-    static bool set = false;
-    if (!set) { EZB_CUDA(cudaFuncSetAttribute(attn4_kernel<72>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set = true; }
-    EZB_TRY(launch_k(attn4_kernel<72>, dim3(grid), dim3(A4_THREADS), smem, st, 1, *tq, *tk, *tv, *tqt, *tkt, p));
+    EZB_TRY(poly ? go(attn4_kernel<72, 1>, Attn4Smem<72>::total(dvp)) : go(attn4_kernel<72, 0>, Attn4Smem<72>::total(dvp)));
   }
   return EZB_OK;
 }

@@ -207,6 +207,7 @@ EZB_API int ezb_set_option(const char* name, int value) {
   if (name && !strcmp(name, "pdl")) { opt_pdl() = value; return EZB_OK; }
   if (name && !strcmp(name, "swap_ab")) { opt_swap_ab() = value; return EZB_OK; }
   if (name && !strcmp(name, "qkv3")) { opt_qkv3() = value; return EZB_OK; }
+  if (name && !strcmp(name, "attn_poly")) { opt_attn_poly() = value; return EZB_OK; }
   if (name && !strcmp(name, "attn4")) { opt_attn4() = value; return EZB_OK; }
   if (name && !strcmp(name, "rope_mufu")) { opt_rope_mufu() = value; return EZB_OK; }
   if (name && !strcmp(name, "gemm_debug")) {  // cycle counters of CTA 0 of every pair-GEMM launch (accumulated)

@@ -10,8 +10,13 @@ from ezaudio_b200 import _lib  # noqa: E402
 
 L = _lib.lib()
 L.ezb_set_option(b"gemm_debug", 1)
+V4 = 1
 if len(sys.argv) > 1:
-    L.ezb_set_option(b"attn4", int(sys.argv[1]))
+    V4 = int(sys.argv[1])
+    L.ezb_set_option(b"attn4", V4)
+if len(sys.argv) > 2:
+    L.ezb_set_option(b"attn_poly", int(sys.argv[2]))
+    print("attn_poly =", sys.argv[2])
     print("attn4 =", sys.argv[1])
 
 
@@ -42,8 +47,12 @@ def run(B, H, Lq, Lk, dh, masked, label, reps=20):
     L.ezb_debug_read(dbg)
     d = [v / reps for v in dbg]
     fl = 4.0 * B * H * Lq * Lk * dh
-    print(f"{label:18s} B{B} H{H} Lq{Lq} Lk{Lk} dh{dh}: {ms * 1e3:7.1f} us {fl / ms / 1e9:6.1f} TF/s | softmax: wait_S {d[0]:.0f} wait_O {d[1]:.0f} "
-          f"barrier {d[2]:.0f} total {d[3]:.0f} | mma: wait_kv {d[4]:.0f} wait_P {d[5]:.0f} total {d[6]:.0f}")
+    if V4:
+        print(f"{label:18s} B{B} H{H} Lq{Lq} Lk{Lk} dh{dh}: {ms * 1e3:7.1f} us {fl / ms / 1e9:6.1f} TF/s | softmax g0: wait_S {d[0]:.0f} wait_O {d[1]:.0f} max+exp {d[2]:.0f} "
+              f"st+arrive {d[3]:.0f} out {d[4]:.0f} total {d[5]:.0f} | mma: wait_P {d[6]:.0f} wait_QKV {d[7]:.0f}")
+    else:
+        print(f"{label:18s} B{B} H{H} Lq{Lq} Lk{Lk} dh{dh}: {ms * 1e3:7.1f} us {fl / ms / 1e9:6.1f} TF/s | softmax: wait_S {d[0]:.0f} wait_O {d[1]:.0f} "
+              f"barrier {d[2]:.0f} total {d[3]:.0f} | mma: wait_kv {d[4]:.0f} wait_P {d[5]:.0f} total {d[6]:.0f}")
 
 
 run(8, 16, 500, 500, 72, False, "self XL")
