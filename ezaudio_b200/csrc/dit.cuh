@@ -645,7 +645,8 @@ struct Dit {
     e.bias = b_final; e.out_f32 = ybuf; e.ld32 = C;
     EZB_TRY(lin(st, act, D, w_final, M, C, e));
     dim3 grid((L + 31) / 32, Be);
-    const size_t smem = (size_t)34 * C * sizeof(float);
+    if (C % 4) return fail(EZB_ERR_UNSUPPORTED, "final conv: %d channels (multiple of 4 expected)", C);
+    const size_t smem = (size_t)36 * C * sizeof(float);
     EZB_TRY(launch_k(final_conv_kernel, grid, dim3(128), smem, st, 1, (const float*)ybuf, (const float*)fc_w, (const float*)fc_b, out, Be, C, L));
     return EZB_OK;
   }

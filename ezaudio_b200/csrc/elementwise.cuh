@@ -278,32 +278,52 @@ __global__ void patch_pack_kernel(const float* __restrict__ x, const float* __re
 
 // ---------------------------------------------------------------------------------------------------------------
 // FinalBlock tail (blocks.py:207-211): y [B*L, C] token-major -> unpatchify (transpose) -> Conv1d(C, C, k=3, pad=1).
-// w packed [3][Cin][Cout] so consecutive threads (co) read consecutive addresses.
+// w packed [3][Cin][Cout].  CTA = 32 positions x all C = 128 output channels; thread = 4 output channels x 8 positions, so one
+// input channel costs 10 broadcast LDS + 3 coalesced float4 weight loads for 96 FMAs (the first version issued one dependent
+// global weight load per (tap, channel) and ran 211 us; FMA-bound this is ~10 us).
 __global__ void __launch_bounds__(128) final_conv_kernel(const float* __restrict__ y, const float* __restrict__ wp, const float* __restrict__ bias,
                                                          float* __restrict__ out, int B, int C, int L) {
   pdl_launch();
   pdl_wait();
-  extern __shared__ float sy[];  // [(TL + 2)][C]
-  constexpr int TL = 32;
+  constexpr int TL = 32, TP = TL + 2 + 2;  // 34 positions (+2 so that the 10-wide window of the last thread group stays in bounds)
+  extern __shared__ float sy[];             // [C][TP] channel-major
   const int b = blockIdx.y, l0 = blockIdx.x * TL;
   for (int i = threadIdx.x; i < (TL + 2) * C; i += blockDim.x) {
     const int r = i / C, c = i - r * C, l = l0 + r - 1;
-    sy[i] = (l >= 0 && l < L) ? y[((size_t)b * L + l) * C + c] : 0.f;
+    sy[c * TP + r] = (l >= 0 && l < L) ? y[((size_t)b * L + l) * C + c] : 0.f;
   }
   __syncthreads();
-  for (int co = threadIdx.x; co < C; co += blockDim.x) {
-    float acc[TL];
+  const int tq = threadIdx.x >> 5;           // positions tq*8 .. tq*8+7 of the tile
+  for (int co = (threadIdx.x & 31) * 4; co < C; co += 128) {
+    float acc[8][4];
+    const float4 bv = *reinterpret_cast<const float4*>(bias + co);
 #pragma unroll
-    for (int t = 0; t < TL; ++t) acc[t] = bias[co];
-    for (int k = 0; k < 3; ++k)
-      for (int ci = 0; ci < C; ++ci) {
-        const float w = wp[((size_t)k * C + ci) * C + co];
+    for (int t = 0; t < 8; ++t) { acc[t][0] = bv.x; acc[t][1] = bv.y; acc[t][2] = bv.z; acc[t][3] = bv.w; }
+#pragma unroll 4
+    for (int ci = 0; ci < C; ++ci) {
+      float4 w[3];
 #pragma unroll
-        for (int t = 0; t < TL; ++t) acc[t] = fmaf(w, sy[(t + k) * C + ci], acc[t]);
+      for (int k = 0; k < 3; ++k) w[k] = __ldg(reinterpret_cast<const float4*>(wp + ((size_t)k * C + ci) * C + co));
+      float x[10];
+#pragma unroll
+      for (int t = 0; t < 10; ++t) x[t] = sy[ci * TP + tq * 8 + t];
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          acc[t][0] = fmaf(w[k].x, x[t + k], acc[t][0]);
+          acc[t][1] = fmaf(w[k].y, x[t + k], acc[t][1]);
+          acc[t][2] = fmaf(w[k].z, x[t + k], acc[t][2]);
+          acc[t][3] = fmaf(w[k].w, x[t + k], acc[t][3]);
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const int l = l0 + tq * 8 + t;
+        if (l < L) out[((size_t)b * C + co + e) * L + l] = acc[t][e];
       }
-#pragma unroll
-    for (int t = 0; t < TL; ++t)
-      if (l0 + t < L) out[((size_t)b * C + co) * L + l0 + t] = acc[t];
   }
 }
 

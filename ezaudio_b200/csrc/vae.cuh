@@ -75,32 +75,62 @@ __global__ void latent_pack_kernel(const float* __restrict__ z, __nv_bfloat16* _
     if (l < L && c < C) store_act(out + ((size_t)b * L + l) * kmul * C, c, C, kmul, tile[threadIdx.x][i]);
   }
 }
-// last layer: Conv1d(C -> 1, k=7, pad 3, no bias) on the snake-activated channels-last tensor; w folded fp32 [7][C]
+// last layer: Conv1d(C -> 1, k=7, pad 3, no bias) on the snake-activated channels-last tensor; w folded fp32 [7][C] (C = 128 shipped).
+// HBM-bound (245 MB of bf16 activations per 4 clips).  One warp = 32 consecutive output samples: every input row (t0-3 .. t0+34) is read
+// once with 8-byte loads (lane = 4 channels, a 256-byte row per warp), multiplied into the up-to-7 outputs it feeds (weights in
+// registers), and the 32 per-lane partial sums are reduced with a 31-shuffle transpose-reduction so that lane i ends up with output i
+// (first version: scalar bf16 staging + one 5-shuffle reduction per output, 1045 us; this one is bound by the activation read).
 __global__ void __launch_bounds__(128) wave_out_kernel(const __nv_bfloat16* __restrict__ act, const float* __restrict__ w, float* __restrict__ wav, int C, int T,
                                                        int kmul) {
-  extern __shared__ float sa[];  // [(TT + 6)][C]
-  constexpr int TT = 64;
-  const int b = blockIdx.y, t0 = blockIdx.x * TT;
-  const __nv_bfloat16* ab = act + (size_t)b * T * kmul * C;
-  for (int i = threadIdx.x; i < (TT + 6) * C; i += blockDim.x) {
-    const int rr = i / C, c = i - rr * C, t = t0 + rr - 3;
-    float v = 0.f;
-    if (t >= 0 && t < T) {
-      const __nv_bfloat16* row = ab + (size_t)t * kmul * C;
-      v = __bfloat162float(row[c]);
-      if (kmul == 3) v += __bfloat162float(row[C + c]);
+  const int lane = threadIdx.x & 31;
+  const int chunk = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int b = blockIdx.y, t0 = chunk * 32;
+  if (t0 >= T) return;
+  float acc[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+  for (int c0 = lane * 4; c0 < C; c0 += 128) {   // C = 128 in the shipped model: one pass
+    const __nv_bfloat16* ab = act + (size_t)b * T * kmul * C + c0;
+    float wk[7][4];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+      const float4 t = *reinterpret_cast<const float4*>(w + k * C + c0);
+      wk[k][0] = t.x; wk[k][1] = t.y; wk[k][2] = t.z; wk[k][3] = t.w;
     }
-    sa[i] = v;
+#pragma unroll
+    for (int rr = 0; rr < 38; ++rr) {       // input sample t0 - 3 + rr feeds outputs o = rr - k, k = 0..6 (tap k reads x[t + k - 3])
+      const int t = t0 - 3 + rr;
+      float x[4] = {0.f, 0.f, 0.f, 0.f};
+      if (t >= 0 && t < T) {
+        const __nv_bfloat16* row = ab + (size_t)t * kmul * C;
+        const uint2 u = __ldg(reinterpret_cast<const uint2*>(row));
+        x[0] = __uint_as_float(u.x << 16); x[1] = __uint_as_float(u.x & 0xffff0000u);
+        x[2] = __uint_as_float(u.y << 16); x[3] = __uint_as_float(u.y & 0xffff0000u);
+        if (kmul == 3) {  // split-bf16 operand: hi | lo | hi
+          const uint2 v = __ldg(reinterpret_cast<const uint2*>(row + C));
+          x[0] += __uint_as_float(v.x << 16); x[1] += __uint_as_float(v.x & 0xffff0000u);
+          x[2] += __uint_as_float(v.y << 16); x[3] += __uint_as_float(v.y & 0xffff0000u);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 7; ++k) {
+        const int o = rr - k;
+        if (o >= 0 && o < 32) acc[o] = fmaf(wk[k][0], x[0], fmaf(wk[k][1], x[1], fmaf(wk[k][2], x[2], fmaf(wk[k][3], x[3], acc[o]))));
+      }
+    }
   }
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int tt = warp; tt < TT; tt += 4) {
-    float s = 0.f;
-    for (int k = 0; k < 7; ++k)
-      for (int c = lane; c < C; c += 32) s = fmaf(w[k * C + c], sa[(tt + k) * C + c], s);
-    s = warp_sum(s);
-    if (lane == 0 && t0 + tt < T) wav[(size_t)b * T + t0 + tt] = s;
+  // transpose-reduction: after the five steps lane i holds the sum over lanes of acc[i]
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int j = 0; j < off; ++j) {
+      const float send = up ? acc[j] : acc[j + off];
+      const float keep = up ? acc[j + off] : acc[j];
+      acc[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
   }
+  if (t0 + lane < T) wav[(size_t)b * T + t0 + lane] = acc[0];
 }
 __global__ void fold_wave_w_kernel(const float* __restrict__ v, const float* __restrict__ g, const float* __restrict__ norms, float* __restrict__ w, int C) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;  // v [1, C, 7] -> w [7][C]
@@ -458,12 +488,10 @@ struct Vae {
       }
     }
     const int C0 = cout_s[nst - 1];
-    const size_t smem = (size_t)(64 + 6) * C0 * sizeof(float);
-    static bool set = false;
-    if (!set) { EZB_CUDA(cudaFuncSetAttribute(wave_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); set = true; }
-    dim3 g2((T + 63) / 64, B);
+    if (C0 % 4) return fail(EZB_ERR_UNSUPPORTED, "wave_out: %d channels in the last stage (multiple of 4 expected)", C0);
+    dim3 g2((T + 127) / 128, B);
     ++launch_counter();
-    wave_out_kernel<<<g2, 128, smem, st>>>(cur, out_w, wav, C0, T, kmul);
+    wave_out_kernel<<<g2, 128, 0, st>>>(cur, out_w, wav, C0, T, kmul);
     EZB_CUDA(cudaGetLastError());
     return EZB_OK;
   }
