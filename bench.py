@@ -133,6 +133,15 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cfg", action="store_true")
     a = ap.parse_args()
+    # stdout carries exactly ONE JSON line: library banners (e.g. "NCCL version ...") are sent to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
+
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
     config = dict(workload=f"C2/C3: EzAudio-XL, {STEPS_DDIM}-step DDIM, {SECONDS} s, {PROMPTS_PER_GPU} prompts/GPU, "
@@ -149,7 +158,7 @@ def main():
         audio_s = SECONDS
         line = dict(base, impl="reference", value=cb["value"], ms_per_step=1e3 * audio_s / cb["value"], dtype="f32", cpu_baseline=cb,
                     e2e=dict(value=cb["value"], unit="audio-s/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0, n_gpus=max(world, a.gpus))
-        print(json.dumps(line))
+        emit(line)
         return
 
     from ezaudio_b200 import _lib, api, synth, weights
@@ -279,7 +288,7 @@ def main():
     line["dit_step_ms"] = e0.elapsed_time(e1) / 10
     if not a.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_reference_leg()
-    print(json.dumps(line))
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
