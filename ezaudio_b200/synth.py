@@ -76,3 +76,29 @@ def synth_energy_audio(B, T, seed=9):
     audio = torch.randn(B, T, generator=g) * torch.logspace(-3, -0.5, B)[:, None]
     audio[0, T // 3: T // 2] = 0.0
     return audio * (0.5 + 0.5 * torch.sin(torch.arange(T) / 2400.0))[None]
+
+
+# transformers.T5Config fields of the text encoders the shipped configs name (ckpts/ezaudio-xl.yml / ezaudio-l.yml: google/flan-t5-xl, -large)
+T5_XL = dict(vocab_size=32128, d_model=2048, d_kv=64, num_heads=32, d_ff=5120, num_layers=24, relative_attention_num_buckets=32,
+             relative_attention_max_distance=128, layer_norm_epsilon=1e-6)
+T5_LARGE = dict(vocab_size=32128, d_model=1024, d_kv=64, num_heads=16, d_ff=2816, num_layers=24, relative_attention_num_buckets=32,
+                relative_attention_max_distance=128, layer_norm_epsilon=1e-6)
+
+
+def tiny_t5(d_kv=64, heads=4, layers=2):
+    return dict(vocab_size=512, d_model=192, d_kv=d_kv, num_heads=heads, d_ff=320, num_layers=layers, relative_attention_num_buckets=32,
+                relative_attention_max_distance=128, layer_norm_epsilon=1e-6)
+
+
+def synth_tokens(B, L, vocab, seed=11):
+    """Token ids + attention mask like tokenizer(..., padding='max_length'): row i keeps n_i = 5 + 7 i (capped) tokens, then pad id 0;
+    the last row is the empty prompt (EOS only)."""
+    g = torch.Generator().manual_seed(seed)
+    ids = torch.randint(2, vocab, (B, L), generator=g)
+    mask = torch.zeros(B, L, dtype=torch.long)
+    for i in range(B):
+        n = 1 if (i == B - 1 and B > 1) else min(L, 5 + 7 * i)
+        mask[i, :n] = 1
+        ids[i, n - 1] = 1  # EOS
+        ids[i, n:] = 0
+    return ids, mask

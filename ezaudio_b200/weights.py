@@ -213,6 +213,29 @@ def vae_encoder_param_shapes(enc_cfg: dict, prefix: str = "encoder.") -> "Ordere
     return out
 
 
+def t5_param_shapes(cfg) -> "OrderedDict[str, tuple]":
+    """State-dict keys / shapes of transformers.T5EncoderModel (the text encoder the reference loads, api/ezaudio.py:78-79) for a
+    gated-GELU T5 v1.1 / flan-T5 config dict: vocab_size, d_model, d_kv, num_heads, d_ff, num_layers, relative_attention_num_buckets."""
+    D, inner, F = cfg["d_model"], cfg["num_heads"] * cfg["d_kv"], cfg["d_ff"]
+    out = OrderedDict()
+    out["shared.weight"] = (cfg["vocab_size"], D)
+    for i in range(cfg["num_layers"]):
+        a = f"encoder.block.{i}.layer.0."
+        for n in ("q", "k", "v"):
+            out[a + f"SelfAttention.{n}.weight"] = (inner, D)
+        out[a + "SelfAttention.o.weight"] = (D, inner)
+        if i == 0:
+            out[a + "SelfAttention.relative_attention_bias.weight"] = (cfg["relative_attention_num_buckets"], cfg["num_heads"])
+        out[a + "layer_norm.weight"] = (D,)
+        f = f"encoder.block.{i}.layer.1."
+        out[f + "DenseReluDense.wi_0.weight"] = (F, D)
+        out[f + "DenseReluDense.wi_1.weight"] = (F, D)
+        out[f + "DenseReluDense.wo.weight"] = (D, F)
+        out[f + "layer_norm.weight"] = (D,)
+    out["encoder.final_layer_norm.weight"] = (D,)
+    return out
+
+
 def synthetic_state_dict(shapes, seed: int = 0, dtype=torch.float32) -> Dict[str, torch.Tensor]:
     """Deterministic random checkpoint (CPU generator; identical bits wherever the same torch
     build runs).  Every tensor the reference zero-initialises is drawn non-zero,
@@ -247,6 +270,8 @@ def synthetic_state_dict(shapes, seed: int = 0, dtype=torch.float32) -> Dict[str
                 gain = 0.3
             if "controlnet_zero_blocks" in k or "conv_out" in k:
                 gain = 0.5
+            if ".SelfAttention.q." in k:  # T5 folds the 1/sqrt(d_kv) of the (unscaled) attention into the query init
+                gain = 0.125
             t = rn(*shp, std=gain / math.sqrt(fan_in))
         else:
             raise KeyError(k)

@@ -302,6 +302,52 @@ def energy_extract(audio, hop_size=240, window_size=1920, min_db=-60.0, norm=Tru
     return gain_db.unsqueeze(-1)
 
 
+# --------------------------------------------------------------------------- T5 text encoder (the step before the path)
+def t5_relative_position_bucket(relative_position, num_buckets=32, max_distance=128):
+    """transformers T5Attention._relative_position_bucket, bidirectional branch (third-party dependency of the reference: `transformers`,
+    un-pinned in requirements.txt; 5.5.0 is installed here and generated the goldens).  Same float32 arithmetic, operation by operation."""
+    num_buckets //= 2
+    ret = (relative_position > 0).to(torch.long) * num_buckets
+    rp = torch.abs(relative_position)
+    max_exact = num_buckets // 2
+    is_small = rp < max_exact
+    large = max_exact + (torch.log(rp.float() / max_exact) / math.log(max_distance / max_exact) * (num_buckets - max_exact)).to(torch.long)
+    large = torch.min(large, torch.full_like(large, num_buckets - 1))
+    return ret + torch.where(is_small, rp, large)
+
+
+def t5_rms_norm(x, w, eps):
+    """T5LayerNorm: no mean subtraction, no bias, variance in fp32."""
+    return w * (x * torch.rsqrt(x.float().pow(2).mean(-1, keepdim=True) + eps))
+
+
+def t5_encode(sd: SD, cfg, input_ids, attention_mask):
+    """T5EncoderModel(input_ids=, attention_mask=).last_hidden_state as the reference calls it (src/inference.py:38-50; model loaded at
+    api/ezaudio.py:78-79): gated-GELU (gelu_new) T5 v1.1 / flan-T5 encoder, unscaled attention, relative position bias of block 0 shared by
+    every block, additive key mask.  (B, L) int64 ids, (B, L) 0/1 mask -> (B, L, d_model)."""
+    H, dk, eps = cfg["num_heads"], cfg["d_kv"], cfg.get("layer_norm_epsilon", 1e-6)
+    B, L = input_ids.shape
+    x = sd["shared.weight"][input_ids]
+    pos = torch.arange(L)
+    bucket = t5_relative_position_bucket(pos[None, :] - pos[:, None], cfg["relative_attention_num_buckets"],
+                                         cfg.get("relative_attention_max_distance", 128))   # [query, key]
+    bias = sd["encoder.block.0.layer.0.SelfAttention.relative_attention_bias.weight"][bucket].permute(2, 0, 1)[None]  # (1, H, L, L)
+    bias = bias + (1.0 - attention_mask[:, None, None, :].to(x.dtype)) * torch.finfo(x.dtype).min
+    for i in range(cfg["num_layers"]):
+        a = f"encoder.block.{i}.layer.0."
+        h = t5_rms_norm(x, sd[a + "layer_norm.weight"], eps)
+        q, k, v = (F.linear(h, sd[a + f"SelfAttention.{n}.weight"]).view(B, L, H, dk).transpose(1, 2) for n in ("q", "k", "v"))
+        w = torch.softmax((q @ k.transpose(-1, -2) + bias).float(), dim=-1).to(x.dtype)
+        o = (w @ v).transpose(1, 2).reshape(B, L, H * dk)
+        x = x + F.linear(o, sd[a + "SelfAttention.o.weight"])
+        f = f"encoder.block.{i}.layer.1."
+        h = t5_rms_norm(x, sd[f + "layer_norm.weight"], eps)
+        g = F.linear(h, sd[f + "DenseReluDense.wi_0.weight"])
+        g = 0.5 * g * (1.0 + torch.tanh(math.sqrt(2.0 / math.pi) * (g + 0.044715 * g.pow(3))))   # NewGELUActivation
+        x = x + F.linear(g * F.linear(h, sd[f + "DenseReluDense.wi_1.weight"]), sd[f + "DenseReluDense.wo.weight"])
+    return t5_rms_norm(x, sd["encoder.final_layer_norm.weight"], eps)
+
+
 # --------------------------------------------------------------------------- sampling loop
 class DDIM:
     """Restatement of diffusers.DDIMScheduler for ckpts/ezaudio-xl.yml:52-60 (scaled_linear,

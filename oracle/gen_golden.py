@@ -88,18 +88,35 @@ def energy_case(ref, name, B, T, seed, **kw):
     print(name, tuple(out.shape), float(out.mean()), float(out.min()))
 
 
+@torch.no_grad()
+def t5_case(ref, name, cfg, B, L, seed):
+    """transformers.T5EncoderModel (the text encoder class the reference instantiates, api/ezaudio.py:79) with the synthetic checkpoint."""
+    from transformers import T5Config, T5EncoderModel
+    sd = weights.synthetic_state_dict(weights.t5_param_shapes(cfg), seed)
+    m = T5EncoderModel(T5Config(feed_forward_proj="gated-gelu", tie_word_embeddings=False, dropout_rate=0.0, **cfg)).eval()
+    full = dict(sd)
+    full["encoder.embed_tokens.weight"] = sd["shared.weight"]
+    missing, unexpected = m.load_state_dict(full, strict=False)
+    assert not missing and not unexpected, (missing, unexpected)
+    ids, mask = synth.synth_tokens(B, L, cfg["vocab_size"])
+    out = m(input_ids=ids, attention_mask=mask).last_hidden_state
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), out=out.numpy(), sd_checksum=checksum(sd), ids_checksum=int(ids.sum()), seed=seed, B=B, L=L)
+    print(name, tuple(out.shape), float(out.std()), float(out.abs().max()))
+
+
 def main():
     ref = refimport.import_reference()
     assert ref is not None, "reference tree not found"
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
     only = set(sys.argv[1:])
-    global dit_case, controlnet_case, vae_case, vae_enc_case, energy_case
+    global dit_case, controlnet_case, vae_case, vae_enc_case, energy_case, t5_case
     if only:
         def filt(f):
             return lambda ref, name, *a, **k: f(ref, name, *a, **k) if name in only else None
         dit_case, controlnet_case, vae_case, vae_enc_case = filt(dit_case), filt(controlnet_case), filt(vae_case), filt(vae_enc_case)
         energy_case = filt(energy_case)
+        t5_case = filt(t5_case)
     dit_case(ref, "dit_tiny72", synth.tiny_model(72), B=2, L=40, Lc=12, seed=3, inpaint=False, tscalar=999)
     dit_case(ref, "dit_tiny72_inpaint", synth.tiny_model(72), B=3, L=52, Lc=12, seed=3, inpaint=True, tvec=[999, 500, 19])
     dit_case(ref, "dit_tiny64", synth.tiny_model(64, heads=4, depth=2), B=2, L=130, Lc=100, seed=4, inpaint=False, tscalar=259)
@@ -111,6 +128,9 @@ def main():
     energy_case(ref, "energy_api", B=3, T=24000 * 2, seed=9, hop_size=240, window_size=1920, padding="reflect", min_db=-60, norm=True)
     energy_case(ref, "energy_quant", B=2, T=5000, seed=10, hop_size=512, window_size=1024, padding="reflect", min_db=-80, norm=True,
                 quantize_levels=16)
+    t5_case(ref, "t5_tiny", synth.tiny_t5(), B=3, L=20, seed=12)
+    t5_case(ref, "t5_tiny_h3", synth.tiny_t5(d_kv=32, heads=6, layers=3), B=2, L=100, seed=13)
+    t5_case(ref, "t5_large", synth.T5_LARGE, B=2, L=100, seed=14)
     dit_case(ref, "dit_L_c1", synth.model_cfg("l"), B=1, L=256, Lc=100, seed=1, inpaint=False, tscalar=999)  # BASELINE config 1
     dit_case(ref, "dit_XL", synth.model_cfg("xl"), B=2, L=500, Lc=100, seed=2, inpaint=False, tscalar=479)
 

@@ -114,3 +114,18 @@ def test_energy_oracle_matches_reference_golden(name, kw):
     out = O.energy_extract(audio, **kw)
     assert out.shape == g["out"].shape
     assert float((out - torch.from_numpy(g["out"])).abs().max()) < 2e-5
+
+
+@pytest.mark.parametrize("name,cfg,B,L,seed", [("t5_tiny", synth.tiny_t5(), 3, 20, 12), ("t5_tiny_h3", synth.tiny_t5(d_kv=32, heads=6, layers=3), 2, 100, 13),
+                                               ("t5_large", synth.T5_LARGE, 2, 100, 14)])
+def test_t5_oracle_matches_transformers_golden(name, cfg, B, L, seed):
+    """T5 encoder restatement vs transformers.T5EncoderModel (5.5.0, the class the reference instantiates) on the synthetic checkpoint."""
+    g = helpers.load_golden(name)
+    sd = weights.synthetic_state_dict(weights.t5_param_shapes(cfg), seed)
+    ids, mask = synth.synth_tokens(B, L, cfg["vocab_size"])
+    assert int(ids.sum()) == int(g["ids_checksum"])
+    with torch.no_grad():
+        out = O.t5_encode(sd, cfg, ids, mask)
+    ref = torch.from_numpy(g["out"])
+    assert out.shape == ref.shape
+    assert float((out - ref).abs().max()) < 2e-4
