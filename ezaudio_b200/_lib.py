@@ -26,6 +26,11 @@ class VaeDesc(C.Structure):
                 ("enc_latent_dim", C.c_int32)]
 
 
+class T5Desc(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("vocab_size", "d_model", "d_kv", "num_heads", "d_ff", "num_layers", "num_buckets", "max_distance")] + \
+               [("eps", C.c_float)] + [(n, C.c_int32) for n in ("max_batch", "max_len", "precision")]
+
+
 class TestEpilogue(C.Structure):
     _fields_ = [("bias", C.c_void_p), ("bias_mod", C.c_int32), ("resid", C.c_void_p), ("ldr", C.c_int32),
                 ("gate", C.c_void_p), ("gate_bstride", C.c_int32), ("rows_per_batch", C.c_int32),
@@ -54,6 +59,11 @@ _SIGS = {
     "ezb_vae_finalize_weights": ([_VP, _VP], _I),
     "ezb_vae_decode": ([_VP, _VP, _VP, _I, _I, _VP], _I),
     "ezb_vae_encode": ([_VP, _VP, _VP, _VP, _I, _I, _VP], _I),
+    "ezb_t5_create": ([C.POINTER(_VP), C.POINTER(T5Desc), _I], _I),
+    "ezb_t5_destroy": ([_VP], _I),
+    "ezb_t5_load_weight": ([_VP, C.c_char_p, _VP, C.POINTER(C.c_int64), _I, _VP], _I),
+    "ezb_t5_finalize_weights": ([_VP, _VP], _I),
+    "ezb_t5_forward": ([_VP, _VP, _VP, _VP, _VP, _I, _I, _VP], _I),
     "ezb_energy_condition": ([_I, _VP, _VP, _I, _I, _I, _I, _F, _I, _I, _VP], _I),
     "ezb_set_option": ([C.c_char_p, _I], _I),
     "ezb_debug_read": ([C.POINTER(C.c_ulonglong)], _I),

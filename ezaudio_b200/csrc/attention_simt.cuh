@@ -1,4 +1,5 @@
-// fp32 CUDA-core attention: softmax(q k^T / sqrt(dh) [+ key mask]) v   (attention.py:107-110, mask attention.py:30-37).
+// fp32 CUDA-core attention: softmax(q k^T * scale [+ bias] [+ key mask]) v   (attention.py:107-110, mask attention.py:30-37;
+// with scale 1 and a relative-position bias: T5Attention).
 // Used by the bf16x3 parity mode (fp32-grade numerics) and as the on-device comparator of the tcgen05 kernel.
 // q,k,v fp32 [B,H,L,dh]; out bf16 [B, Lq, H*dh] token-major (A operand of the output projection).
 #pragma once
@@ -12,7 +13,8 @@ constexpr int SA_WARPS = 4;
 
 __global__ void __launch_bounds__(SA_WARPS * 32) attn_simt_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
                                                                   const uint8_t* __restrict__ key_mask, __nv_bfloat16* __restrict__ out, int H, int Lq,
-                                                                  int Lk, int dh, float scale, int kmul) {
+                                                                  int Lk, int dh, float scale, int kmul,
+                                                                  const float* __restrict__ bias = nullptr /* [H, Lq, Lk] added to the scores (T5) */) {
   extern __shared__ float sm[];
   const int ldk = dh | 1;  // odd pitch: conflict-free row-per-lane reads
   float* sK = sm;                       // [SA_TK][ldk]
@@ -53,6 +55,14 @@ __global__ void __launch_bounds__(SA_WARPS * 32) attn_simt_kernel(const float* _
         const float qv = qr[d];
         s0 = fmaf(qv, sK[lane * ldk + d], s0);
         s1 = fmaf(qv, sK[(lane + 32) * ldk + d], s1);
+      }
+      if (bias != nullptr) {
+        const int qrow = q0 + warp * SA_QW + qi;
+        if (qrow < Lq) {
+          const float* br = bias + ((size_t)h * Lq + qrow) * Lk + k0;
+          if (k0 + lane < Lk) s0 += br[lane];
+          if (k0 + lane + 32 < Lk) s1 += br[lane + 32];
+        }
       }
       s0 = ok0 ? s0 : -INFINITY;
       s1 = ok1 ? s1 : -INFINITY;

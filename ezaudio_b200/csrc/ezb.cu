@@ -4,6 +4,7 @@
 #include <algorithm>
 #include "dit.cuh"
 #include "vae.cuh"
+#include "t5.cuh"
 #include "host.cuh"
 
 using namespace ezb;
@@ -157,6 +158,32 @@ EZB_API int ezb_vae_finalize_weights(ezb_vae* h, void* stream) {
 EZB_API int ezb_vae_encode(ezb_vae* h, const float* audio, const float* noise, float* z, int B, int T, void* stream) {
   if (!h || !audio || !z) return fail(EZB_ERR_ARG, "ezb_vae_encode: null argument");
   return reinterpret_cast<Vae*>(h)->encode(audio, noise, z, B, T, ST(stream));
+}
+EZB_API int ezb_t5_create(ezb_t5** out, const ezb_t5_desc* desc, int device) {
+  if (!out || !desc) return fail(EZB_ERR_ARG, "ezb_t5_create: null argument");
+  EZB_CUDA(cudaSetDevice(device));
+  T5* h = new T5();
+  int rc = h->init(*desc, &device_ctx(device));
+  if (rc != 0) { delete h; return rc; }
+  *out = reinterpret_cast<ezb_t5*>(h);
+  return EZB_OK;
+}
+EZB_API int ezb_t5_destroy(ezb_t5* h) {
+  delete reinterpret_cast<T5*>(h);
+  return EZB_OK;
+}
+EZB_API int ezb_t5_load_weight(ezb_t5* h, const char* key, const float* data, const int64_t* shape, int ndim, void* stream) {
+  if (!h || !key || !data || !shape) return fail(EZB_ERR_ARG, "ezb_t5_load_weight: null argument");
+  return reinterpret_cast<T5*>(h)->load_weight(key, data, shape, ndim, ST(stream));
+}
+EZB_API int ezb_t5_finalize_weights(ezb_t5* h, void* stream) {
+  if (!h) return fail(EZB_ERR_ARG, "null handle");
+  (void)stream;
+  return reinterpret_cast<T5*>(h)->finalize();
+}
+EZB_API int ezb_t5_forward(ezb_t5* h, const int32_t* ids, const uint8_t* mask, const int32_t* buckets, float* out, int B, int L, void* stream) {
+  if (!h || !ids || !mask || !out) return fail(EZB_ERR_ARG, "ezb_t5_forward: null argument");
+  return reinterpret_cast<T5*>(h)->forward(ids, mask, buckets, out, B, L, ST(stream));
 }
 EZB_API int ezb_energy_condition(int device, const float* audio, float* out, int B, int T, int hop, int win, float min_db, int norm, int qlevels,
                                  void* stream) {

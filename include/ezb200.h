@@ -109,6 +109,28 @@ int ezb_vae_encode(ezb_vae* h, const float* audio, const float* noise, float* z,
 int ezb_energy_condition(int device, const float* audio, float* out, int B, int T, int hop_size, int window_size, float min_db, int norm,
                          int quantize_levels, void* stream);
 
+/* --- T5 (v1.1 / flan-T5, gated-GELU) text encoder: `text_encoder(input_ids=, attention_mask=).last_hidden_state`, src/inference.py:38-50;
+ * model class transformers.T5EncoderModel loaded at api/ezaudio.py:78-79 (the step before the denoiser path). */
+typedef struct ezb_t5 ezb_t5;
+typedef struct {
+  int32_t vocab_size, d_model, d_kv, num_heads, d_ff, num_layers;
+  int32_t num_buckets;   /* relative_attention_num_buckets (32) */
+  int32_t max_distance;  /* relative_attention_max_distance (128) */
+  float eps;             /* layer_norm_epsilon (1e-6) */
+  int32_t max_batch, max_len;
+  int32_t precision;     /* 0 = bf16 operands, 1 = bf16x3 (parity mode), as in ezb_dit_desc */
+} ezb_t5_desc;
+int ezb_t5_create(ezb_t5** out, const ezb_t5_desc* desc, int device);
+int ezb_t5_destroy(ezb_t5* h);
+/* keys of T5EncoderModel.state_dict(): shared.weight, encoder.block.{i}.layer.0.SelfAttention.{q,k,v,o}.weight, ...relative_attention_bias.weight
+ * (block 0), encoder.block.{i}.layer.{0,1}.layer_norm.weight, ...DenseReluDense.{wi_0,wi_1,wo}.weight, encoder.final_layer_norm.weight */
+int ezb_t5_load_weight(ezb_t5* h, const char* ref_key, const float* data, const int64_t* shape, int ndim, void* stream);
+int ezb_t5_finalize_weights(ezb_t5* h, void* stream);
+/* ids (B, L) int32, attention mask (B, L) uint8 (1 = token), out (B, L, d_model) fp32, all device pointers.  `buckets` (L, L) int32 device
+ * pointer = T5Attention._relative_position_bucket(key - query) as computed by the caller with the reference's own torch ops, or NULL to let
+ * the library compute it on the host in float32. */
+int ezb_t5_forward(ezb_t5* h, const int32_t* ids, const uint8_t* mask, const int32_t* buckets, float* out, int B, int L, void* stream);
+
 /* --- kernel-level hooks used by tests/ and profiling only (not part of the drop-in surface). */
 typedef struct {
   const float* bias; int32_t bias_mod;
