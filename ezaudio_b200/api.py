@@ -66,14 +66,56 @@ def _load_audio(path: str, sr: int) -> np.ndarray:
     return data
 
 
-def _load_t5(name: str, device):
+class HashTokenizer:
+    """Offline stand-in for T5Tokenizer (no sentencepiece vocabulary on disk, no network): words -> stable ids in [2, vocab), EOS = 1,
+    pad = 0; same call signature / outputs as the tokenizer call at src/inference.py:39-41."""
+
+    def __init__(self, vocab_size: int = 32128):
+        self.vocab_size = vocab_size
+
+    def __call__(self, text, max_length=100, padding="max_length", truncation=True, return_tensors="pt"):
+        from types import SimpleNamespace
+        import zlib
+        text = [text] if isinstance(text, str) else list(text)
+        ids = torch.zeros(len(text), max_length, dtype=torch.long)
+        mask = torch.zeros(len(text), max_length, dtype=torch.long)
+        for i, t in enumerate(text):
+            toks = [2 + zlib.crc32(w.encode()) % (self.vocab_size - 2) for w in t.lower().split()][: max_length - 1] + [1]
+            ids[i, : len(toks)] = torch.tensor(toks)
+            mask[i, : len(toks)] = 1
+        return SimpleNamespace(input_ids=ids, attention_mask=mask)
+
+
+class NativeTextEncoder:
+    """prompts -> (embeddings, mask) with a tokenizer and the native T5 encoder (ezaudio_b200.t5), i.e. src/inference.py:38-50."""
+
+    def __init__(self, tokenizer, encoder, max_length: int = 100, device="cuda"):
+        self.tokenizer, self.encoder, self.max_length, self.device = tokenizer, encoder, max_length, device
+
+    def __call__(self, prompts: Sequence[str]):
+        tb = self.tokenizer(list(prompts), max_length=self.max_length, padding="max_length", truncation=True, return_tensors="pt")
+        ids, mask = tb.input_ids.to(self.device), tb.attention_mask.to(self.device).bool()
+        return self.encoder(input_ids=ids, attention_mask=mask).last_hidden_state, mask
+
+
+def _load_t5(name: str, device, precision: str = "bf16", max_length: int = 100):
+    """api/ezaudio.py:78-79.  transformers is used for the tokenizer and for reading the checkpoint (CPU, I/O only); the encoder that runs
+    is the native one.  Returns (None, None) when the checkpoint is not on disk (there is no network here)."""
     try:
-        from transformers import T5EncoderModel, T5Tokenizer
+        from transformers import T5EncoderModel as HFT5
+        from transformers import T5Tokenizer
         tok = T5Tokenizer.from_pretrained(name, local_files_only=True)
-        enc = T5EncoderModel.from_pretrained(name, local_files_only=True).to(device).eval()
-        return tok, enc
+        hf = HFT5.from_pretrained(name, local_files_only=True)
     except Exception:
         return None, None
+    from .t5 import T5EncoderModel
+    c = hf.config
+    cfg = dict(vocab_size=c.vocab_size, d_model=c.d_model, d_kv=c.d_kv, num_heads=c.num_heads, d_ff=c.d_ff, num_layers=c.num_layers,
+               relative_attention_num_buckets=c.relative_attention_num_buckets,
+               relative_attention_max_distance=getattr(c, "relative_attention_max_distance", 128), layer_norm_epsilon=c.layer_norm_epsilon,
+               feed_forward_proj=c.feed_forward_proj)
+    enc = T5EncoderModel(cfg, precision=precision, max_batch=8, max_len=max_length, device=device).load_state_dict(hf.state_dict())
+    return tok, enc
 
 
 def _state_dict(path, shapes, key):
@@ -99,18 +141,12 @@ class _Base:
         self.tokenizer = self.text_encoder = None
         if text_encoder is not None:
             return text_encoder
-        tok, enc = _load_t5(params["text_encoder"]["model"], device)
+        ml = params["text_encoder"]["max_length"]
+        tok, enc = _load_t5(params["text_encoder"]["model"], device, max_length=ml)
         if tok is None:
             return None
         self.tokenizer, self.text_encoder = tok, enc
-        ml = params["text_encoder"]["max_length"]
-
-        def run(prompts):
-            tb = tok(list(prompts), max_length=ml, padding="max_length", truncation=True, return_tensors="pt")
-            ids, mask = tb.input_ids.to(device), tb.attention_mask.to(device).bool()
-            with torch.no_grad():
-                return enc(input_ids=ids, attention_mask=mask).last_hidden_state, mask
-        return run
+        return NativeTextEncoder(tok, enc, ml, device)
 
 
 class EzAudio(_Base):

@@ -80,4 +80,20 @@ if "C5" in a.configs:
     tflop = (100 * 4 * 2528 + 2 * 3 * (499.4 + 499.3)) / 1e3
     res["C5"] = dict(workload="XL inpainting, 30 s (L=1500), 100 steps, 2 prompts on 1 GPU, CFG 3.5 (effective batch 4), VAE encode + decode, host waveform out",
                      ms_per_job=ms, audio_s_per_s=60 / (ms * 1e-3), algorithmic_tflop=tflop, tensor_roofline_frac=tflop / (ms * 1e-3) / peak)
+if "T5" in a.configs:
+    # the step before the path: flan-T5-XL encoder, 4 prompts + the empty negative prompt, 100 tokens each
+    from ezaudio_b200 import weights
+    from ezaudio_b200.t5 import T5EncoderModel
+    cfg = synth.T5_XL
+    sd = weights.synthetic_state_dict(weights.t5_param_shapes(cfg), 15)
+    t5 = T5EncoderModel(cfg, max_batch=5, max_len=100, device=dev).load_state_dict(sd)
+    del sd
+    ids, mask = synth.synth_tokens(5, 100, cfg["vocab_size"])
+    ids, mask = ids.to(dev), mask.to(dev)
+    ms, out = timed(lambda: t5(input_ids=ids, attention_mask=mask).last_hidden_state, 5)
+    assert out.shape == (5, 100, 2048) and torch.isfinite(out).all()
+    wbytes = 2 * 24 * (3 * 2048 * 2048 + 2048 * 2048 + 3 * 5120 * 2048)
+    gflop = 2 * 500 * 24 * (4 * 2048 * 2048 + 3 * 5120 * 2048) / 1e9
+    res["T5"] = dict(workload="flan-T5-XL encoder (24 layers, d_model 2048), 5 prompts x 100 tokens, bf16 operands", ms_per_encode=ms,
+                     weight_bytes=wbytes, hbm_GBps=wbytes / (ms * 1e-3) / 1e9, gflop=gflop, note="weight-bandwidth bound: every linear reads its bf16 weight once for 500 rows")
 print(json.dumps(res))

@@ -103,3 +103,22 @@ def test_energy_condition_kernel_matches_reference(name, kw):
     got = energy_condition(long.cuda(), hop_size=240, window_size=1920, min_db=-60, norm=True).cpu()
     want = O.energy_extract(long, 240, 1920, -60.0, True)
     assert got.shape == (4, 1, 1000) and float((got[:, 0] - want[..., 0]).abs().max()) < 2e-5
+
+
+def test_generate_audio_from_text_with_native_t5(monkeypatch):
+    """`generate_audio(str)` with nothing but native kernels between the string and the waveform: tokenizer stand-in -> T5 encoder
+    (ezb_t5_forward) -> DiT loop -> VAE decode.  The T5 width must match the denoiser's context_dim (udit.py:94)."""
+    from ezaudio_b200 import api, weights
+    from ezaudio_b200.t5 import T5EncoderModel
+    tiny = _tiny_params()
+    monkeypatch.setattr(config, "load_params", lambda name, path=None, table=None: tiny)
+    tcfg = dict(synth.tiny_t5(), d_model=tiny["model"]["context_dim"])
+    t5 = T5EncoderModel(tcfg, max_batch=4, max_len=16).load_state_dict(weights.synthetic_state_dict(weights.t5_param_shapes(tcfg), 12))
+    enc = api.NativeTextEncoder(api.HashTokenizer(tcfg["vocab_size"]), t5, 16)
+    e, m = enc(["a dog barks twice", ""])
+    assert e.shape == (2, 16, tcfg["d_model"]) and m.sum(1).tolist() == [5, 1]
+    ez = api.EzAudio("s3_xl", ckpt_path="synthetic:3", vae_path="synthetic:6", text_encoder=enc, max_batch=2, max_length_s=2)
+    sr, wav = ez.generate_audio("a dog barks twice", length=1, ddim_steps=4, random_seed=7)
+    assert sr == 24000 and wav.shape == (24000,) and np.isfinite(wav).all()
+    _, other = ez.generate_audio("heavy rain on a tin roof", length=1, ddim_steps=4, random_seed=7)
+    assert not np.array_equal(wav, other)   # the text actually conditions the result
