@@ -49,6 +49,8 @@ class T5EncoderModel:
                         max_distance=cfg.get("relative_attention_max_distance", 128), eps=cfg.get("layer_norm_epsilon", 1e-6),
                         max_batch=max_batch, max_len=max_len, precision=PRECISIONS[precision])
         self._buckets = {}
+        self._graphs = {}     # (nb, L) -> (graph, static ids, static mask, static out): ~250 small launches replayed as one graph
+        self.use_graphs = True
         self.h = C.c_void_p()
         with torch.cuda.device(self.dev_index):
             _lib.check(_lib.lib().ezb_t5_create(C.byref(self.h), C.byref(d), self.dev_index))
@@ -98,9 +100,33 @@ class T5EncoderModel:
         with torch.cuda.device(self.dev_index):
             for b0 in range(0, B, self.max_batch):
                 nb = min(self.max_batch, B - b0)
-                _lib.check(_lib.lib().ezb_t5_forward(self.h, _lib.ptr(ids[b0:b0 + nb]), _lib.ptr(mask[b0:b0 + nb]), _lib.ptr(self._buckets[L]),
-                                                     C.c_void_p(out[b0:b0 + nb].data_ptr()), nb, L, _lib.stream_ptr()))
+                if self.use_graphs:
+                    g, s_ids, s_mask, s_out = self._graph(nb, L)
+                    s_ids.copy_(ids[b0:b0 + nb])
+                    s_mask.copy_(mask[b0:b0 + nb])
+                    g.replay()
+                    out[b0:b0 + nb].copy_(s_out)
+                else:
+                    self._run(ids[b0:b0 + nb], mask[b0:b0 + nb], out[b0:b0 + nb], nb, L)
         return _Output(out)
+
+    def _run(self, ids, mask, out, nb, L):
+        _lib.check(_lib.lib().ezb_t5_forward(self.h, _lib.ptr(ids), _lib.ptr(mask), _lib.ptr(self._buckets[L]), C.c_void_p(out.data_ptr()), nb, L,
+                                             _lib.stream_ptr()))
+
+    def _graph(self, nb, L):
+        key = (nb, L)
+        if key not in self._graphs:
+            s_ids = torch.zeros(nb, L, dtype=torch.int32, device=self.device)
+            s_mask = torch.ones(nb, L, dtype=torch.uint8, device=self.device)
+            s_out = torch.empty(nb, L, self.config["d_model"], device=self.device, dtype=torch.float32)
+            self._run(s_ids, s_mask, s_out, nb, L)   # warm-up outside capture: tensor maps, function attributes
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._run(s_ids, s_mask, s_out, nb, L)
+            self._graphs[key] = (g, s_ids, s_mask, s_out)
+        return self._graphs[key]
 
     forward = __call__
 
