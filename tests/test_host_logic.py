@@ -120,3 +120,34 @@ def test_prompt_sharding_two_ranks_gloo(n_total):
     assert res[0][1] + res[1][1] == [f"p{i}" for i in range(n_total)]
     for _, _, col in res:
         assert col == [float(i) for i in range(n_total)]
+
+
+def test_t5_bucket_table_host_logic_matches_oracle_and_transformers():
+    """The (L, L) relative-position bucket table the Python mirror hands to ezb_t5_forward: equal to the oracle's restatement and, when
+    transformers is importable, to T5Attention._relative_position_bucket itself (same float32 truncations at the boundaries 16, 32, 64)."""
+    import torch
+    from ezaudio_b200.t5 import relative_position_buckets
+    from oracle import ezaudio_oracle as O
+    for L in (1, 7, 100, 300):
+        pos = torch.arange(L)
+        rp = pos[None, :] - pos[:, None]
+        got = relative_position_buckets(L, 32, 128).long()
+        assert torch.equal(got, O.t5_relative_position_bucket(rp, 32, 128))
+        try:
+            from transformers.models.t5.modeling_t5 import T5Attention
+        except Exception:
+            continue
+        assert torch.equal(got, T5Attention._relative_position_bucket(rp, bidirectional=True, num_buckets=32, max_distance=128))
+    assert got.min() >= 0 and got.max() <= 31
+
+
+def test_hash_tokenizer_contract():
+    """Stand-in for T5Tokenizer(text, max_length=, padding='max_length', truncation=True, return_tensors='pt') (src/inference.py:39-41)."""
+    from ezaudio_b200.api import HashTokenizer
+    tok = HashTokenizer(32128)
+    out = tok(["a dog barks", "", "x " * 200], max_length=100, padding="max_length", truncation=True, return_tensors="pt")
+    assert out.input_ids.shape == (3, 100) and out.attention_mask.sum(1).tolist() == [4, 1, 100]
+    assert out.input_ids[1, 0] == 1 and out.input_ids[0, 3] == 1 and out.input_ids[2, 99] == 1          # EOS closes every prompt
+    assert int(out.input_ids.max()) < 32128 and int(out.input_ids[0, 4:].abs().sum()) == 0             # pad id 0
+    again = tok("a dog barks", max_length=100)
+    assert again.input_ids[0].tolist() == out.input_ids[0].tolist()                                     # stable across calls
