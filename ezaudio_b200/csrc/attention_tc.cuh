@@ -329,13 +329,13 @@ inline int attention_tc(Device& dev, cudaStream_t st, const __nv_bfloat16* q, co
   const int grid = p.n_items < dev.num_sms ? p.n_items : dev.num_sms;
   if (dh == 64) {
     const int smem = AttnSmem<64>::total(dvp);
-    static bool set = false;
-    if (!set) { EZB_CUDA(cudaFuncSetAttribute(attn_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem<64>::total(80))); set = true; }
+    static bool set[16] = {};  // function attributes are per device
+    if (!set[dev.id & 15]) { EZB_CUDA(cudaFuncSetAttribute(attn_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem<64>::total(80))); set[dev.id & 15] = true; }
     EZB_TRY(launch_k(attn_tc_kernel<64>, dim3(grid), dim3(AT_THREADS), smem, st, 1, *tq, *tk, *tv, *tqt, *tkt, p));
   } else {
     const int smem = AttnSmem<72>::total(dvp);
-    static bool set = false;
-    if (!set) { EZB_CUDA(cudaFuncSetAttribute(attn_tc_kernel<72>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem<72>::total(80))); set = true; }
+    static bool set[16] = {};
+    if (!set[dev.id & 15]) { EZB_CUDA(cudaFuncSetAttribute(attn_tc_kernel<72>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem<72>::total(80))); set[dev.id & 15] = true; }
     EZB_TRY(launch_k(attn_tc_kernel<72>, dim3(grid), dim3(AT_THREADS), smem, st, 1, *tq, *tk, *tv, *tqt, *tkt, p));
   }
   return EZB_OK;

@@ -442,8 +442,8 @@ struct Dit {
     const float scale = 1.0f / sqrtf((float)dh);
     if (!use_tc_attention) {
       const size_t smem = attn_simt_smem(dh);
-      static bool set = false;
-      if (!set) { EZB_CUDA(cudaFuncSetAttribute(attn_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); set = true; }
+      static bool set[16] = {};  // function attributes are per device
+      if (!set[dev->id & 15]) { EZB_CUDA(cudaFuncSetAttribute(attn_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); set[dev->id & 15] = true; }
       dim3 grid((Lq + SA_WARPS * SA_QW - 1) / (SA_WARPS * SA_QW), B * H);
       ++launch_counter();
       attn_simt_kernel<<<grid, SA_WARPS * 32, smem, st>>>(q32_, k32_, v32_, mask, attn_out, H, Lq, Lk, dh, scale, kmul);

@@ -243,8 +243,8 @@ struct T5 {
     EZB_CUDA(cudaGetLastError());
     EpiLinearParams z;
     memset(&z, 0, sizeof z);
-    static bool attr = false;
-    if (!attr) { EZB_CUDA(cudaFuncSetAttribute(attn_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); attr = true; }
+    static bool attr[16] = {};  // function attributes are per device
+    if (!attr[dev->id & 15]) { EZB_CUDA(cudaFuncSetAttribute(attn_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); attr[dev->id & 15] = true; }
     for (int i = 0; i < nl; ++i) {
       const Layer& w = layers[i];
       ++launch_counter();
