@@ -98,6 +98,18 @@ class NativeTextEncoder:
         return self.encoder(input_ids=ids, attention_mask=mask).last_hidden_state, mask
 
 
+def save_wav(path: str, audio, sr: int = 24000) -> None:
+    """soundfile.write(path, audio, sr) stand-in for the step after the path (t2a_demo.py:13,20, controlnet_demo.py:15): float32 mono WAV
+    written with scipy (soundfile is not in this image).  Accepts the (sr, ndarray) tuple the API methods return as `audio`."""
+    from scipy.io import wavfile
+    if isinstance(audio, tuple):
+        sr, audio = audio
+    a = np.asarray(audio, dtype=np.float32).reshape(-1)
+    if not np.isfinite(a).all():
+        raise ValueError("save_wav: non-finite samples")
+    wavfile.write(path, int(sr), a)
+
+
 def _load_t5(name: str, device, precision: str = "bf16", max_length: int = 100):
     """api/ezaudio.py:78-79.  transformers is used for the tokenizer and for reading the checkpoint (CPU, I/O only); the encoder that runs
     is the native one.  Returns (None, None) when the checkpoint is not on disk (there is no network here)."""

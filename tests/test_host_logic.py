@@ -4,6 +4,7 @@ import os
 import re
 import sys
 
+import numpy as np
 import pytest
 import torch
 
@@ -151,3 +152,22 @@ def test_hash_tokenizer_contract():
     assert int(out.input_ids.max()) < 32128 and int(out.input_ids[0, 4:].abs().sum()) == 0             # pad id 0
     again = tok("a dog barks", max_length=100)
     assert again.input_ids[0].tolist() == out.input_ids[0].tolist()                                     # stable across calls
+
+
+def test_wav_io_round_trip(tmp_path):
+    """save_wav / _load_audio (the I/O either side of the path: t2a_demo.py:13, api/ezaudio.py:146): float32 round trip, int16 input,
+    stereo down-mix and 48 k -> 24 k resampling."""
+    from scipy.io import wavfile
+    from ezaudio_b200.api import _load_audio, save_wav
+    t = np.arange(24000) / 24000.0
+    x = (0.5 * np.sin(2 * np.pi * 440 * t)).astype(np.float32)
+    p = str(tmp_path / "a.wav")
+    save_wav(p, (24000, x))
+    assert np.array_equal(_load_audio(p, 24000), x)
+    wavfile.write(str(tmp_path / "b.wav"), 24000, (x * 32767).astype(np.int16))
+    assert np.abs(_load_audio(str(tmp_path / "b.wav"), 24000) - x).max() < 1e-4
+    t48 = np.arange(48000) / 48000.0
+    st = np.stack([0.5 * np.sin(2 * np.pi * 440 * t48), 0.5 * np.sin(2 * np.pi * 440 * t48)], 1).astype(np.float32)
+    wavfile.write(str(tmp_path / "c.wav"), 48000, st)
+    y = _load_audio(str(tmp_path / "c.wav"), 24000)
+    assert y.shape == (24000,) and np.abs(y[200:-200] - x[200:-200]).max() < 5e-3
