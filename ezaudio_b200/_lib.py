@@ -52,7 +52,8 @@ _SIGS = {
     "ezb_dit_set_timesteps": ([_VP, C.POINTER(C.c_int64), _I, _VP], _I),
     "ezb_dit_forward": ([_VP, _VP, _VP, _VP, C.POINTER(C.c_int32), _I, C.POINTER(_VP), _VP, _I, _I, _VP], _I),
     "ezb_controlnet_forward": ([_VP, _VP, _VP, _VP, C.POINTER(C.c_int32), _I, _VP, _F, C.POINTER(_VP), _I, _I, _VP], _I),
-    "ezb_cfg_ddim_step": ([_VP, _VP, _VP, _I, _I, _I, _F, _F, C.POINTER(C.c_float), _VP], _I),
+    "ezb_cfg_ddim_step": ([_I, _VP, _VP, _VP, _I, _I, _I, _F, _F, C.POINTER(C.c_float), _VP], _I),
+    "ezb_option_epoch": ([], C.c_ulonglong),
     "ezb_vae_create": ([C.POINTER(_VP), C.POINTER(VaeDesc), _I], _I),
     "ezb_vae_destroy": ([_VP], _I),
     "ezb_vae_load_weight": ([_VP, C.c_char_p, _VP, C.POINTER(C.c_int64), _I, _VP], _I),

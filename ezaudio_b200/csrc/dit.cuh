@@ -7,7 +7,6 @@
 #include <vector>
 
 #include "attention_simt.cuh"
-#include "attention_tc.cuh"
 #include "attention_tc4.cuh"
 #include "host.cuh"
 
@@ -450,8 +449,7 @@ struct Dit {
       EZB_CUDA(cudaGetLastError());
       return EZB_OK;
     }
-    if (opt_attn4()) return attention_tc4(*dev, st, q16_, k16_, vt16_, mask, attn_out, B, H, Lq, Lk, Lkpad, dh, DHP, DVP, scale);
-    return attention_tc(*dev, st, q16_, k16_, vt16_, mask, attn_out, B, H, Lq, Lk, Lkpad, dh, DHP, DVP, scale);
+    return attention_tc4(*dev, st, q16_, k16_, vt16_, mask, attn_out, B, H, Lq, Lk, Lkpad, dh, DHP, DVP, scale);
   }
 
   // ---------------------------------------------------------------- step-invariant precompute
@@ -459,6 +457,7 @@ struct Dit {
     if (!finalized) return fail(EZB_ERR_STATE, "weights not finalized");
     if (Be < 1 || Be > d.max_batch || Lc < 1 || Lc > d.max_ctx_len) return fail(EZB_ERR_SHAPE, "set_context: Be %d Lc %d exceed workspace", Be, Lc);
     const int Mc = Be * Lc, cd = d.context_dim;
+    dev->tmaps.trim();
     ctx_Be = Be; ctx_Lc = Lc; ctx_Lpad = (Lc + 7) / 8 * 8;
     EZB_CUDA(cudaMemcpyAsync(ctx_mask, mask, (size_t)Mc, cudaMemcpyDeviceToDevice, st));
     EZB_TRY(ln(st, ctx, cd, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0, 1, act, Mc));  // cast only
@@ -488,10 +487,13 @@ struct Dit {
   int set_timesteps(const int64_t* ts, int n, cudaStream_t st) {
     if (!finalized) return fail(EZB_ERR_STATE, "weights not finalized");
     if (n < 1 || n > d.max_timesteps) return fail(EZB_ERR_SHAPE, "set_timesteps: n %d exceeds max_timesteps %d", n, d.max_timesteps);
-    std::vector<float> tf(n);
-    for (int i = 0; i < n; ++i) tf[i] = (float)ts[i];
-    EZB_CUDA(cudaMemcpyAsync(t_vals, tf.data(), n * sizeof(float), cudaMemcpyHostToDevice, st));
-    EZB_CUDA(cudaStreamSynchronize(st));  // tf is a stack-owned staging buffer
+    for (int i0 = 0; i0 < n; i0 += 240) {  // values travel by value in the kernel parameters: no host staging buffer, no synchronisation
+      TimestepChunk c;
+      const int m = n - i0 < 240 ? n - i0 : 240;
+      for (int i = 0; i < 240; ++i) c.v[i] = i < m ? (float)ts[i0 + i] : 0.f;
+      ++launch_counter();
+      fill_timesteps_kernel<<<1, 256, 0, st>>>(t_vals + i0, c, m);
+    }
     ++launch_counter();
     timestep_embed_kernel<<<(n * 128 + 255) / 256, 256, 0, st>>>(t_vals, t_emb, n);
     EZB_TRY(small_lin(st, t_emb, 256, te_w0, te_b0, nullptr, 0, t_h, D, n, D, 256, 1, 1.f));
@@ -613,7 +615,6 @@ struct Dit {
   int check_call(int Be, int L) {
     if (!finalized) return fail(EZB_ERR_STATE, "weights not finalized");
     if (Be < 1 || Be > d.max_batch || L < 1 || L > d.max_len) return fail(EZB_ERR_SHAPE, "Be %d / L %d exceed workspace (%d, %d)", Be, L, d.max_batch, d.max_len);
-    if (L < 32) return fail(EZB_ERR_SHAPE, "L %d: at least 32 latent frames are required (epilogues assume a warp's 32 rows span <= 2 clips)", L);
     if (Be != ctx_Be) return fail(EZB_ERR_STATE, "batch %d differs from the context set by ezb_dit_set_context (%d)", Be, ctx_Be);
     return EZB_OK;
   }
@@ -622,6 +623,7 @@ struct Dit {
               cudaStream_t st) {
     if (d.is_controlnet) return fail(EZB_ERR_STATE, "ezb_dit_forward called on a controlnet handle");
     EZB_TRY(check_call(Be, L));
+    dev->tmaps.trim();
     const float *modr, *modf;
     int mbs, mbsf;
     EZB_TRY(select_mod(st, tidx, tall, Be, &modr, &modf, &mbs, &mbsf));
@@ -664,6 +666,7 @@ inline int Dit::controlnet_forward(const float* x, const float* gt, const uint8_
                                    float* const* skips_out, int Be, int L, cudaStream_t st) {
   if (!d.is_controlnet) return fail(EZB_ERR_STATE, "ezb_controlnet_forward called on a DiT handle");
   EZB_TRY(check_call(Be, L));
+  dev->tmaps.trim();
   const float *modr, *modf;
   int mbs, mbsf;
   EZB_TRY(select_mod(st, tidx, tall, Be, &modr, &modf, &mbs, &mbsf));

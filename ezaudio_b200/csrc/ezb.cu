@@ -123,16 +123,15 @@ EZB_API int ezb_controlnet_forward(ezb_dit* h, const float* x, const float* gt, 
   if (!h || !x || !condition || !skips_out) return fail(EZB_ERR_ARG, "ezb_controlnet_forward: null argument");
   return reinterpret_cast<Dit*>(h)->controlnet_forward(x, gt, gt_mask, tidx, tall, condition, scale, skips_out, Be, L, ST(stream));
 }
-EZB_API int ezb_cfg_ddim_step(const float* model_out, float* latents, const float* noise, int B, int C, int L, float gs, float gr,
+EZB_API int ezb_cfg_ddim_step(int device, const float* model_out, float* latents, const float* noise, int B, int C, int L, float gs, float gr,
                               const float* coef, void* stream) {
-  if (!model_out || !latents || !coef || B < 1) return fail(EZB_ERR_ARG, "ezb_cfg_ddim_step: bad argument");
+  if (!model_out || !latents || !coef || B < 1 || C < 1 || L < 1) return fail(EZB_ERR_ARG, "ezb_cfg_ddim_step: bad argument");
+  if (coef[4] != 0.f && !noise) return fail(EZB_ERR_ARG, "ezb_cfg_ddim_step: sigma != 0 needs a noise tensor");
+  EZB_CUDA(cudaSetDevice(device));
   const int n = C * L;
   const float* uncond = gs != 0.f ? model_out + (size_t)B * n : nullptr;
-  ++launch_counter();
-  cfg_ddim_kernel<<<B, 1024, 0, ST(stream)>>>(model_out, uncond, latents, coef[4] != 0.f ? noise : nullptr, n, gs, gr, coef[0], coef[1], coef[2],
-                                              coef[3], coef[4]);
-  EZB_CUDA(cudaGetLastError());
-  return EZB_OK;
+  return launch_k(cfg_ddim_kernel, dim3(B * CFG_CLUSTER), dim3(1024), 0, ST(stream), CFG_CLUSTER, model_out, uncond, latents,
+                  coef[4] != 0.f ? noise : (const float*)nullptr, n, gs, gr, coef[0], coef[1], coef[2], coef[3], coef[4]);
 }
 EZB_API int ezb_vae_create(ezb_vae** out, const ezb_vae_desc* desc, int device) {
   if (!out || !desc) return fail(EZB_ERR_ARG, "ezb_vae_create: null argument");
@@ -220,22 +219,20 @@ EZB_API int ezb_test_attention(int device, const void* q, const void* k, const v
     return EZB_OK;
   }
   const int dhp = (dh + 63) / 64 * 64, dvp = (dh + 15) / 16 * 16, lkpad = (Lk + 7) / 8 * 8;
-  if (opt_attn4())
-    return attention_tc4(device_ctx(device), ST(stream), reinterpret_cast<const __nv_bfloat16*>(q), reinterpret_cast<const __nv_bfloat16*>(k),
-                         reinterpret_cast<const __nv_bfloat16*>(v), key_mask, reinterpret_cast<__nv_bfloat16*>(out), B, H, Lq, Lk, lkpad, dh, dhp, dvp, scale);
-  return attention_tc(device_ctx(device), ST(stream), reinterpret_cast<const __nv_bfloat16*>(q), reinterpret_cast<const __nv_bfloat16*>(k),
-                      reinterpret_cast<const __nv_bfloat16*>(v), key_mask, reinterpret_cast<__nv_bfloat16*>(out), B, H, Lq, Lk, lkpad, dh, dhp, dvp, scale);
+  return attention_tc4(device_ctx(device), ST(stream), reinterpret_cast<const __nv_bfloat16*>(q), reinterpret_cast<const __nv_bfloat16*>(k),
+                       reinterpret_cast<const __nv_bfloat16*>(v), key_mask, reinterpret_cast<__nv_bfloat16*>(out), B, H, Lq, Lk, lkpad, dh, dhp, dvp, scale);
 }
 
 
 // runtime switches (A/B testing): "pair_gemm" 0/1 -- read when a handle is created
+EZB_API unsigned long long ezb_option_epoch(void) { return option_epoch(); }
 EZB_API int ezb_set_option(const char* name, int value) {
+  ++option_epoch();   // captured CUDA graphs bake the kernel selection in: the host layer keys its graph cache on this counter
   if (name && !strcmp(name, "pair_gemm")) { opt_pair_gemm() = value; return EZB_OK; }
   if (name && !strcmp(name, "pdl")) { opt_pdl() = value; return EZB_OK; }
   if (name && !strcmp(name, "swap_ab")) { opt_swap_ab() = value; return EZB_OK; }
   if (name && !strcmp(name, "qkv3")) { opt_qkv3() = value; return EZB_OK; }
   if (name && !strcmp(name, "attn_poly")) { opt_attn_poly() = value; return EZB_OK; }
-  if (name && !strcmp(name, "attn4")) { opt_attn4() = value; return EZB_OK; }
   if (name && !strcmp(name, "rope_mufu")) { opt_rope_mufu() = value; return EZB_OK; }
   if (name && !strcmp(name, "gemm_debug")) {  // cycle counters of CTA 0 of every pair-GEMM launch (accumulated)
     if (value && !gemm_dbg_buf()) { EZB_CUDA(cudaMalloc(&gemm_dbg_buf(), 64)); EZB_CUDA(cudaMemset(gemm_dbg_buf(), 0, 64)); }

@@ -133,7 +133,11 @@ __device__ __forceinline__ void rows_generic(const EpiLinearParams& ep, const Ro
     float v0 = (acc.x + c.b0) * osc, v1 = (acc.y + c.b1) * osc;
     if (ep.resid != nullptr) {
       if (ep.gate != nullptr) {
-        const float2 g = row >= c.brow ? c.g1 : c.g0;
+        float2 g = row >= c.brow ? c.g1 : c.g0;
+        if (ep.rows_per_batch < 32) {  // short clips (L < 32, api/ezaudio.py:160-172 crops to any length): a warp's rows span > 2 batch items
+          g = *reinterpret_cast<const float2*>(ep.gate + (size_t)(row / ep.rows_per_batch) * ep.gate_bstride + col);
+          g.x = 1.0f - g.x; g.y = 1.0f - g.y;
+        }
         v0 = x[rr].x + g.x * v0;
         v1 = x[rr].y + g.y * v1;
       } else {
@@ -208,7 +212,7 @@ struct EpiLinear {
       if (col_ok) {
         const int c16 = ep.phase_cols > 0 ? (col / ep.phase_cols) * ep.phase_ld16 + col % ep.phase_cols : col;
         const int code = (ep.resid != nullptr ? 1 : 0) | (ep.gate != nullptr ? 2 : 0) | (ep.out_f32 != nullptr ? 4 : 0) | (ep.out_bf16 != nullptr ? 8 : 0) |
-                         (ep.act << 4) | ((ep.split_stride > 0 || ep.out_scale != 0.f) ? 256 : 0);
+                         (ep.act << 4) | ((ep.split_stride > 0 || ep.out_scale != 0.f || (ep.gate != nullptr && ep.rows_per_batch < 32)) ? 256 : 0);
         const RowCtx rc{st, lane, nv, row0, brow, b0, b1, g0, g1, sa0, sa1, sb0, sb1,
                         ep.out_f32 != nullptr ? ep.out_f32 + (size_t)row0 * ep.ld32 + col : nullptr, ep.ld32,
                         ep.out_bf16 != nullptr ? ep.out_bf16 + (size_t)row0 * ep.ld16 + c16 : nullptr, ep.ld16};
@@ -378,7 +382,9 @@ struct EpiLinearT {
         for (int j = 0; j < 32; ++j) {
           if (j >= nt) break;
           float v = __uint_as_float(r[j]) + bias;
-          if (ep.resid != nullptr) v = fmaf((t0 + j >= btok) ? g1 : g0, v, x[j]);
+          float gj = (t0 + j >= btok) ? g1 : g0;
+          if (ep.gate != nullptr && ep.rows_per_batch < 32) gj = 1.0f - ep.gate[(size_t)((t0 + j) / ep.rows_per_batch) * ep.gate_bstride + f];
+          if (ep.resid != nullptr) v = fmaf(gj, v, x[j]);
           o[(size_t)j * ep.ld32] = v;
         }
       }

@@ -97,6 +97,8 @@ struct T5 {
   float *x = nullptr, *qkv32 = nullptr, *q32 = nullptr, *k32 = nullptr, *v32 = nullptr, *u32 = nullptr, *bias = nullptr;
   __nv_bfloat16 *act = nullptr, *attn = nullptr, *mid = nullptr;
   int32_t *ids_d = nullptr, *bucket_d = nullptr;
+  int bucket_L = -1;                 // length the device bucket table currently holds
+  std::vector<int32_t> bucket_h;     // its host staging copy
   bool finalized = false;
 
   ~T5() {
@@ -230,10 +232,11 @@ struct T5 {
     if (B < 1 || L < 1 || B > d.max_batch || L > d.max_len) return fail(EZB_ERR_SHAPE, "t5: B=%d L=%d (max %d, %d)", B, L, d.max_batch, d.max_len);
     const int M = B * L;
     if (buckets == nullptr) {
-      std::vector<int32_t> hb;
-      host_buckets(L, hb);
-      EZB_CUDA(cudaMemcpyAsync(bucket_d, hb.data(), hb.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-      EZB_CUDA(cudaStreamSynchronize(st));  // hb is a stack object
+      if (bucket_L != L) {  // the table depends on L only: built on the host in float32 (bit-compatible with the reference's torch ops) once per length;
+        host_buckets(L, bucket_h);  // the staging vector lives in the handle, so the copy needs no synchronisation
+        EZB_CUDA(cudaMemcpyAsync(bucket_d, bucket_h.data(), bucket_h.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        bucket_L = L;
+      }
       buckets = bucket_d;
     }
     auto grid = [](size_t n) { return (unsigned)((n + 255) / 256); };

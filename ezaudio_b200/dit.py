@@ -23,6 +23,7 @@ def _as_f32c(t: torch.Tensor) -> torch.Tensor:
 
 class _Handle:
     """Owns one ezb_dit handle (a DiT or a ControlNet)."""
+    _serial = 0
 
     def __init__(self, cfg: dict, controlnet: Optional[dict], precision: str, max_batch: int, max_len: int,
                  max_ctx_len: int, max_timesteps: int, device):
@@ -54,6 +55,8 @@ class _Handle:
         self.loaded = False
         self._ctx_key = None
         self._ts: List[int] = []
+        _Handle._serial += 1
+        self.serial = _Handle._serial   # identifies this handle in graph-cache keys (id() values are recycled)
 
     def __del__(self):
         try:
@@ -89,6 +92,7 @@ class _Handle:
         with torch.cuda.device(self.dev_index):
             _lib.check(_lib.lib().ezb_dit_set_context(self.h, _lib.ptr(ctx), _lib.ptr(m), B, Lc, _lib.stream_ptr()))
         self._keep = (ctx, m)
+        self._ctx_key = None   # a direct set_context invalidates whatever ensure_context cached
 
     def set_timesteps(self, ts: Sequence[int]):
         ts = [int(t) for t in ts]
@@ -104,6 +108,7 @@ class _Handle:
         if key != self._ctx_key:
             self.set_context(context, context_mask)
             self._ctx_key = key
+            self._ctx_refs = (context, context_mask)   # keep the originals alive: the key is made of their addresses
 
     def ensure_timesteps(self, timesteps: torch.Tensor, B: int):
         tv = [int(timesteps)] * B if timesteps.dim() == 0 else [int(v) for v in timesteps.tolist()]
@@ -195,8 +200,9 @@ class MaskDiT:
         arr = (C.c_int32 * Be)(*tidx)
         sk = None
         if controlnet_skips:
-            sk = (C.c_void_p * len(controlnet_skips))(*[_as_f32c(s).data_ptr() for s in controlnet_skips])
-            self._keep_sk = controlnet_skips
+            sks = [_as_f32c(s).to(self.device) for s in controlnet_skips]   # converted copies are kept alive until the next call
+            sk = (C.c_void_p * len(sks))(*[s.data_ptr() for s in sks])
+            self._keep_sk = sks
         with torch.cuda.device(h.dev_index):
             _lib.check(_lib.lib().ezb_dit_forward(h.h, _lib.ptr(x), _lib.ptr(gtc), _lib.ptr(m8), arr, 0, sk, _lib.ptr(out), Be, L,
                                                   _lib.stream_ptr()))

@@ -37,19 +37,39 @@ def encode_text(tokenizer, text_encoder, params, text_raw, neg_text, device):
 
 def _ddim_step(model_out, latents, noise, B, Cc, L, gs, gr, coef):
     arr = (C.c_float * 5)(*coef)
-    _lib.check(_lib.lib().ezb_cfg_ddim_step(_lib.ptr(model_out), _lib.ptr(latents), _lib.ptr(noise), B, Cc, L, float(gs or 0.0), float(gr or 0.0),
+    _lib.check(_lib.lib().ezb_cfg_ddim_step(latents.device.index, _lib.ptr(model_out), _lib.ptr(latents), _lib.ptr(noise), B, Cc, L, float(gs or 0.0), float(gr or 0.0),
                                             arr, _lib.stream_ptr()))
 
 
 @torch.no_grad()
 def sample_latents(unet, noise_scheduler, text, text_mask, uncond_text=None, uncond_mask=None, gt=None, gt_mask=None,
                    audio_frames=500, guidance_scale=3, guidance_rescale=0.0, ddim_steps=50, eta=1, random_seed=2024,
-                   controlnet=None, condition=None, conditioning_scale=1.0, init_noise=None, step_noise=None, device="cuda",
-                   use_graphs=True):
+                   controlnet=None, condition=None, conditioning_scale=1.0, init_noise=None, step_noise=None, device=None,
+                   use_graphs=True, paste_gt=True):
     """Denoising loop on cached text embeddings.  text (B,Lc,ctx) / text_mask (B,Lc); uncond_* (1 or B rows) when
     guidance_scale is truthy.  gt / gt_mask (B,C,L) for inpainting.  Returns the final latents (B,C,L) fp32 on device.
-    `init_noise` / `step_noise` inject the RNG draws (parity tests); otherwise per-prompt generators are used."""
-    device = torch.device(device)
+    `init_noise` / `step_noise` inject the RNG draws (parity tests); otherwise per-prompt generators are used.
+    `paste_gt`: apply the final `pred[~gt_mask] = gt[~gt_mask]` here (standalone use); `inference()` passes False and pastes after
+    scale_shift_re like src/inference.py:102-105."""
+    dev_index = unet._h.dev_index   # the loop runs where the denoiser's weights live
+    if device is not None:
+        d = torch.device(device)
+        if d.type != "cuda" or (d.index is not None and d.index != dev_index):
+            raise ValueError(f"sample_latents(device={d}) but the denoiser lives on cuda:{dev_index}")
+    device = torch.device("cuda", dev_index)
+    # every launch below (noise draws, the C-ABI calls, graph capture and replay) targets `device`, whatever the caller's current device is
+    with torch.cuda.device(device):
+        lat = _sample_latents_on_device(unet, noise_scheduler, text, text_mask, uncond_text, uncond_mask, gt, gt_mask, audio_frames, guidance_scale,
+                                        guidance_rescale, ddim_steps, eta, random_seed, controlnet, condition, conditioning_scale, init_noise,
+                                        step_noise, device, use_graphs)
+        if gt is not None and paste_gt:
+            lat = torch.where(gt_mask.to(device).bool().expand_as(lat), lat, gt.to(device=device, dtype=lat.dtype))
+        return lat
+
+
+def _sample_latents_on_device(unet, noise_scheduler, text, text_mask, uncond_text, uncond_mask, gt, gt_mask, audio_frames, guidance_scale,
+                              guidance_rescale, ddim_steps, eta, random_seed, controlnet, condition, conditioning_scale, init_noise, step_noise,
+                              device, use_graphs):
     B = text.shape[0]
     Cc = unet.cfg["out_chans"]
     L = int(audio_frames)
@@ -102,8 +122,11 @@ def sample_latents(unet, noise_scheduler, text, text_mask, uncond_text=None, unc
 
     # ---- the loop.  Every step is the same launch sequence on static buffers, so each step index is captured once into a
     # CUDA graph (per shape / schedule) and replayed: ~500 kernel launches per step collapse into one graph launch.
-    key = (B, L, tuple(timesteps), use_cfg, float(guidance_scale or 0.0), float(guidance_rescale or 0.0), float(eta or 0.0), gt is not None,
-           id(controlnet) if controlnet is not None else 0, float(conditioning_scale))
+    # Everything a captured launch sequence bakes in: shapes (incl. the context length, which fixes the cross-attention K/V layout and
+    # tensor maps), the schedule, the guidance constants, which ControlNet handle (its serial, not id(): ids are recycled) and the
+    # library's option epoch (ezb_set_option changes kernel selection).
+    key = (B, Be, L, int(ctx.shape[1]), tuple(timesteps), use_cfg, float(guidance_scale or 0.0), float(guidance_rescale or 0.0), float(eta or 0.0),
+           gt is not None, controlnet._h.serial if controlnet is not None else 0, float(conditioning_scale), int(_lib.lib().ezb_option_epoch()))
     cache = unet.__dict__.setdefault("_loop_cache", {})
     st = cache.get(key) if use_graphs else None
     if st is None:
@@ -166,10 +189,7 @@ def sample_latents(unet, noise_scheduler, text, text_mask, uncond_text=None, unc
         else:
             st["graphs"][i].replay()
             L_.ezb_launch_count_add(st["launches"][i])
-    latents = lat.clone()
-    if gt is not None:  # src/inference.py:104-105: pred[~gt_mask] = gt[~gt_mask]
-        latents = torch.where(gt_mask.to(device).bool().expand_as(latents), latents, gt)
-    return latents
+    return lat.clone()   # the inpainting paste happens after scale_shift_re, in inference() (src/inference.py:102-105)
 
 
 @torch.no_grad()
@@ -186,6 +206,8 @@ def inference(autoencoder, unet, gt, gt_mask, tokenizer, text_encoder, params, n
     else:  # src/inference.py:51-53
         raise ValueError("either tokenizer/text_encoder or text_embeds is required (the denoiser is text-conditioned)")
     latents = sample_latents(unet, noise_scheduler, text, text_mask, uncond_text, uncond_mask, gt, gt_mask, audio_frames, guidance_scale,
-                             guidance_rescale, ddim_steps, eta, random_seed, controlnet, condition, conditioning_scale, device=device)
+                             guidance_rescale, ddim_steps, eta, random_seed, controlnet, condition, conditioning_scale, device=device, paste_gt=False)
     pred = scale_shift_re(latents, params["autoencoder"]["scale"], params["autoencoder"]["shift"])
+    if gt is not None:  # src/inference.py:104-105: pred[~gt_mask] = gt[~gt_mask], with the raw gt, after the rescale
+        pred = torch.where(gt_mask.to(pred.device).bool().expand_as(pred), pred, gt.to(device=pred.device, dtype=pred.dtype))
     return autoencoder(embedding=pred)

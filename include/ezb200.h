@@ -7,7 +7,9 @@
  *
  * Conventions: plain pointers and sizes, no torch types.  Every device pointer is owned by the caller (PyTorch) and
  * must stay valid until the stream-ordered call has executed.  All work is enqueued on the cudaStream_t passed as
- * `stream` (void*); no call synchronises the device unless stated.  A handle is not re-entrant.  Returns 0 on success,
+ * `stream` (void*).  The per-step entry points (set_context, set_timesteps, forward, controlnet_forward, cfg_ddim_step, decode,
+ * encode, energy_condition, t5_forward) never synchronise and are safe inside CUDA-graph capture; the load-time ones (create,
+ * load_weight, finalize_weights) may synchronise the device.  A handle is not re-entrant.  Returns 0 on success,
  * a negative ezb_status otherwise; ezb_last_error() gives the message of the calling thread's last failure.
  */
 #ifndef EZB200_H
@@ -74,8 +76,8 @@ int ezb_controlnet_forward(ezb_dit* h, const float* x, const float* gt, const ui
 /* --- fused classifier-free guidance + rescale + DDIM update (src/inference.py:12-23,88-100; diffusers DDIMScheduler.step
  * restated).  model_out holds B text rows followed by B uncond rows when guidance_scale != 0, else B
  * rows.  coef = {sqrt(a_t), sqrt(1-a_t), sqrt(a_prev), sqrt(1-a_prev-sigma^2), sigma}; noise (B,C,L) may be NULL when
- * sigma == 0.  latents updated in place. */
-int ezb_cfg_ddim_step(const float* model_out, float* latents, const float* noise, int B, int C, int L, float guidance_scale,
+ * sigma == 0.  latents updated in place.  `device`: the CUDA device the pointers live on (the call makes it current). */
+int ezb_cfg_ddim_step(int device, const float* model_out, float* latents, const float* noise, int B, int C, int L, float guidance_scale,
                       float guidance_rescale, const float* coef5_host, void* stream);
 
 /* --- VAE decoder: OobleckDecoder.forward (stable_vae/models/autoencoders.py:149-190) behind
@@ -149,6 +151,8 @@ int ezb_test_attention(int device, const void* q, const void* k, const void* vt,
 
 /* runtime switch for A/B measurements: "pair_gemm" (1 = cta_group::2 256-row tiles, default; 0 = single-CTA 128x128) */
 int ezb_set_option(const char* name, int value);
+/* incremented by every ezb_set_option call: hosts that cache captured CUDA graphs key them on it (options change kernel selection) */
+unsigned long long ezb_option_epoch(void);
 /* debugging aid: with option "gemm_debug"=1, CTA 0 of each pair-GEMM accumulates cycle counters; this reads and resets them */
 int ezb_debug_read(unsigned long long* out8);
 /* accounting: kernels launched by this library so far (process-wide); per-GEMM CUDA-event timing for bench.py's roofline leg */

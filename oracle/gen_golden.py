@@ -38,7 +38,7 @@ def dit_case(ref, name, cfg, B, L, Lc, seed, inpaint, tscalar=None, tvec=None):
 
 
 @torch.no_grad()
-def controlnet_case(ref, name, cfg, B, L, Lc, seed):
+def controlnet_case(ref, name, cfg, B, L, Lc, seed, skip_stride=1):
     cn = synth.CONTROLNET
     sd = weights.synthetic_state_dict(weights.dit_param_shapes(cfg), seed)
     sd_cn = weights.synthetic_state_dict(weights.controlnet_param_shapes(cfg, cn), seed + 1)
@@ -51,9 +51,10 @@ def controlnet_case(ref, name, cfg, B, L, Lc, seed):
     x257, _ = m(x, t, ctx, context_mask=mask, forward_model=False)
     skips = c(x257, t, ctx, context_mask=mask, condition=cond, conditioning_scale=0.8)
     out = m.model(x257, t, ctx, context_mask=mask, controlnet_skips=list(skips))
-    np.savez_compressed(os.path.join(OUT, name + ".npz"), out=out.numpy(), skip0=skips[0].numpy(),
-                        skip_last=skips[-1].numpy(), sd_checksum=checksum(sd) + checksum(sd_cn), seed=seed,
-                        B=B, L=L, Lc=Lc)
+    # config-scale cases keep every `skip_stride`-th token row of the two stored skips (a full XL skip is 4.6 MB)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), out=out.numpy(), skip0=skips[0][:, ::skip_stride].numpy(),
+                        skip_last=skips[-1][:, ::skip_stride].numpy(), sd_checksum=checksum(sd) + checksum(sd_cn), seed=seed,
+                        B=B, L=L, Lc=Lc, skip_stride=skip_stride)
     print(name, tuple(out.shape), float(out.std()), float(skips[-1].std()))
 
 
@@ -133,6 +134,11 @@ def main():
     t5_case(ref, "t5_large", synth.T5_LARGE, B=2, L=100, seed=14)
     dit_case(ref, "dit_L_c1", synth.model_cfg("l"), B=1, L=256, Lc=100, seed=1, inpaint=False, tscalar=999)  # BASELINE config 1
     dit_case(ref, "dit_XL", synth.model_cfg("xl"), B=2, L=500, Lc=100, seed=2, inpaint=False, tscalar=479)
+    # ---- configuration-scale cases (BASELINE configs C4 / C5 and the 10-s codec the benchmark times)
+    controlnet_case(ref, "controlnet_XL", synth.model_cfg("xl"), B=2, L=500, Lc=100, seed=2, skip_stride=10)      # C4 shapes (B_eff = 2)
+    dit_case(ref, "dit_XL_inpaint_30s", synth.model_cfg("xl"), B=2, L=1500, Lc=100, seed=2, inpaint=True, tvec=[989, 9])  # C5 shapes
+    vae_case(ref, "vae_full_10s", synth.VAE_DECODER, B=2, L=500, seed=6)
+    vae_enc_case(ref, "vae_enc_full_10s", synth.VAE_ENCODER, B=1, T=480 * 500, seed=8)
 
 
 if __name__ == "__main__":

@@ -15,6 +15,7 @@ DIT_CASES = {
     "dit_tiny64": (lambda: synth.tiny_model(64, heads=4, depth=2), dict(B=2, L=130, Lc=100, seed=4, inpaint=False)),
     "dit_L_c1": (lambda: synth.model_cfg("l"), dict(B=1, L=256, Lc=100, seed=1, inpaint=False)),
     "dit_XL": (lambda: synth.model_cfg("xl"), dict(B=2, L=500, Lc=100, seed=2, inpaint=False)),
+    "dit_XL_inpaint_30s": (lambda: synth.model_cfg("xl"), dict(B=2, L=1500, Lc=100, seed=2, inpaint=True)),   # BASELINE config C5 shapes
 }
 
 

@@ -17,7 +17,7 @@ def _ref(q, k, v, mask):
     return o.permute(0, 2, 1, 3).reshape(q.shape[0], q.shape[2], -1)
 
 
-@pytest.mark.parametrize("impl", [0, 1, 4])  # 4 = impl 1 with the two-tile ping-pong kernel (attention_tc4.cuh)
+@pytest.mark.parametrize("impl", [0, 1])  # 0 = fp32 CUDA-core kernel (parity mode), 1 = tcgen05 two-tile ping-pong kernel (attention_tc4.cuh)
 @pytest.mark.parametrize("B,H,Lq,Lk,dh,masked", [(2, 4, 500, 500, 72, False), (2, 3, 256, 256, 64, False), (3, 2, 500, 100, 72, True),
                                                  (2, 2, 40, 12, 72, True), (1, 2, 130, 130, 64, False), (1, 16, 1500, 1500, 72, False),
                                                  (2, 2, 37, 100, 64, True), (8, 16, 500, 500, 72, False), (2, 5, 700, 700, 72, "grow")])
@@ -30,8 +30,6 @@ def test_attention(impl, B, H, Lq, Lk, dh, masked):
     if masked == "grow":  # scores grow by orders of magnitude from key block to key block: exercises the in-place O rescale
         k = k * torch.linspace(0.2, 3.0, Lk, device="cuda")[None, None, :, None]
         masked = False
-    attn4 = impl == 4
-    impl = 1 if attn4 else impl
     mask = None
     if masked:
         mask = torch.zeros(B, Lk, dtype=torch.uint8, device="cuda")
@@ -53,17 +51,10 @@ def test_attention(impl, B, H, Lq, Lk, dh, masked):
         vt[:, :, Lk:] = 7.0  # beyond the true length: must never be read
         args = (qb, kb, vt)
         ref = _ref(q.bfloat16().float(), k.bfloat16().float(), v.bfloat16().float(), mask)
-    _lib.check(L.ezb_set_option(b"attn4", int(attn4)))
-    try:
-        _run(L, _lib, args, mask, out, B, H, Lq, Lk, dh, impl)
-    finally:
-        _lib.check(L.ezb_set_option(b"attn4", ATTN4_DEFAULT))
+    _run(L, _lib, args, mask, out, B, H, Lq, Lk, dh, impl)
     torch.cuda.synchronize()
     err = (out.float() - ref).abs().max().item()
     assert math.isfinite(err) and err < (2e-2 if impl == 0 else 3e-2), err
-
-
-ATTN4_DEFAULT = 1
 
 
 def _run(L, _lib, args, mask, out, B, H, Lq, Lk, dh, impl):

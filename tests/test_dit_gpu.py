@@ -31,16 +31,17 @@ def _run_case(name, precision):
     ref = torch.from_numpy(g["out"])
     err = (out.cpu() - ref).abs()
     assert torch.isfinite(out).all()
+    print(f"[parity] {name} [{precision}]: max-abs {float(err.max()):.3e} mean-abs {float(err.mean()):.3e} (ref std {float(ref.std()):.3f})")
     return float(err.max()), float(err.mean())
 
 
-@pytest.mark.parametrize("name", ["dit_tiny72", "dit_tiny72_inpaint", "dit_tiny64", "dit_L_c1"])
+@pytest.mark.parametrize("name", ["dit_tiny72", "dit_tiny72_inpaint", "dit_tiny64", "dit_L_c1", "dit_XL", "dit_XL_inpaint_30s"])
 def test_dit_parity_mode_matches_reference(name):
     mx, mean = _run_case(name, "bf16x3")
     assert mx < TOL["bf16x3"][0] and mean < TOL["bf16x3"][1], (mx, mean)
 
 
-@pytest.mark.parametrize("name", ["dit_tiny72", "dit_tiny72_inpaint", "dit_tiny64", "dit_L_c1", "dit_XL"])
+@pytest.mark.parametrize("name", ["dit_tiny72", "dit_tiny72_inpaint", "dit_tiny64", "dit_L_c1", "dit_XL", "dit_XL_inpaint_30s"])
 def test_dit_fast_mode_within_bf16_floor(name):
     mx, mean = _run_case(name, "bf16")
     assert mx < TOL["bf16"][0] and mean < TOL["bf16"][1], (mx, mean)

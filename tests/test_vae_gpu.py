@@ -12,7 +12,8 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("precision,rel", [("bf16x3", 1e-3), ("bf16", 6e-2)])
-@pytest.mark.parametrize("name,dcfg,B,L", [("vae_tiny", synth.tiny_vae(16), 2, 9), ("vae_full", synth.VAE_DECODER, 1, 12)])
+@pytest.mark.parametrize("name,dcfg,B,L", [("vae_tiny", synth.tiny_vae(16), 2, 9), ("vae_full", synth.VAE_DECODER, 1, 12),
+                                           ("vae_full_10s", synth.VAE_DECODER, 2, 500)])   # the 10-s decode bench.py times
 def test_vae_decode_matches_reference(name, dcfg, B, L, precision, rel):
     from ezaudio_b200.vae import OobleckDecoder
     g = helpers.load_golden(name)
@@ -24,12 +25,14 @@ def test_vae_decode_matches_reference(name, dcfg, B, L, precision, rel):
     ref = torch.from_numpy(g["out"])
     assert wav.shape == ref.shape
     err = float((wav.cpu() - ref).abs().max())
+    print(f"[parity] {name} [{precision}]: max-abs {err:.3e} (|ref|max {float(ref.abs().max()):.3e})")
     assert err < rel * float(ref.abs().max()) + 1e-5, (err, float(ref.abs().max()))
 
 
 @pytest.mark.parametrize("precision,rel", [("bf16x3", 1e-3), ("bf16", 6e-2)])
 @pytest.mark.parametrize("name,cfgs,B,L", [("vae_enc_tiny", (synth.tiny_vae_encoder(16), synth.tiny_vae(16)), 2, 9),
-                                           ("vae_enc_full", (synth.VAE_ENCODER, synth.VAE_DECODER), 1, 12)])
+                                           ("vae_enc_full", (synth.VAE_ENCODER, synth.VAE_DECODER), 1, 12),
+                                           ("vae_enc_full_10s", (synth.VAE_ENCODER, synth.VAE_DECODER), 1, 500)])
 def test_vae_encode_matches_reference(name, cfgs, B, L, precision, rel):
     """OobleckEncoder (strided implicit-GEMM convs) + VAE bottleneck vs the UNMODIFIED reference encoder's golden output
     (mean | scale), with injected noise for the sampling formula (bottleneck.py:66-70)."""
