@@ -352,6 +352,7 @@ struct Dit {
   // ---------------------------------------------------------------- launch helpers
   int ln(cudaStream_t st, const float* x, int D1, const float* x2, const float* x3, int D2, const float* w, const float* b, const float* shift,
          const float* scale, int mod_bstride, int rows_per_batch, bf16* out, int M) {
+    if (opt_skip() & 1) return EZB_OK;
     LnParams p;
     p.x = x; p.x2 = x2; p.x3 = x3; p.D1 = D1; p.D2 = D2; p.w = w; p.b = b; p.shift = shift; p.scale = scale; p.mod_bstride = mod_bstride;
     p.rows_per_batch = rows_per_batch; p.out = out; p.kmul = kmul; p.M = M;
@@ -367,9 +368,11 @@ struct Dit {
     return e;
   }
   int lin(cudaStream_t st, const bf16* A, int K, const bf16* W, int M, int N, const EpiLinearParams& e) {
+    if ((opt_skip() & 8) && e.out_f32 != nullptr && e.out_bf16 == nullptr) return EZB_OK;
     // fp32-output layers (residual / gated-residual / plain): swap-AB 128 x 256 tiles -- one full wave for N = 1152 at M = 4000
     if (pair && swap_ab && kmul == 1 && e.out_bf16 == nullptr && e.out_f32 != nullptr && e.out_scale == 0.f && e.bias_mod == 0 && M >= 512)
-      return gemm_swapped<EpiLinearT<256>>(*dev, st, A, K, W, K, M, N, K, e);
+      return opt_swap_mc() ? gemm_swapped_mc<EpiLinearT<256>, 3>(*dev, st, A, K, W, K, M, N, K, e)
+                           : gemm_swapped<EpiLinearT<256>>(*dev, st, A, K, W, K, M, N, K, e);
     if (pair) return gemm2<128, EpiLinear<128>>(*dev, st, A, kmul * K, W, kmul * K, M, N, kmul * K, e);
     return gemm<128, EpiLinear<128>>(*dev, st, A, kmul * K, W, kmul * K, M, N, kmul * K, e);
   }
@@ -405,6 +408,7 @@ struct Dit {
   // Q/K/V projection with the fused per-head LN + RoPE + attention-layout epilogue (fast mode)
   int lin_heads(cudaStream_t st, const bf16* A, const bf16* W, int M, int N, const int* kinds, const float (*nq)[96], const float (*nk)[96], bool rope,
                 int L, bf16* qo, bf16* ko, bf16* vto, int Lpad) {
+    if (opt_skip() & 4) return EZB_OK;
     EpiHeadsParams e;
     memset(&e, 0, sizeof e);
     for (int i = 0; i < dh && i < 72; ++i) {
@@ -439,6 +443,7 @@ struct Dit {
   int attention(cudaStream_t st, const float* q32_, const float* k32_, const float* v32_, const bf16* q16_, const bf16* k16_, const bf16* vt16_,
                 const uint8_t* mask, int B, int Lq, int Lk, int Lkpad) {
     const float scale = 1.0f / sqrtf((float)dh);
+    if (opt_skip() & 2) return EZB_OK;
     if (!use_tc_attention) {
       const size_t smem = attn_simt_smem(dh);
       static bool set[16] = {};  // function attributes are per device
@@ -594,7 +599,8 @@ struct Dit {
     {
       EpiGegluParams g;
       g.bias = w.b_mlp1; g.out_bf16 = mid; g.ld16 = kmul * inner; g.split_stride = kmul == 3 ? inner : 0;
-      if (geglu_bn == 256) EZB_TRY((gemm2<256, EpiGeglu<256>>(*dev, st, act, kmul * D, w.mlp1, kmul * D, M, 2 * inner, kmul * D, g)));
+      if (opt_skip() & 16) {}
+      else if (geglu_bn == 256) EZB_TRY((gemm2<256, EpiGeglu<256>>(*dev, st, act, kmul * D, w.mlp1, kmul * D, M, 2 * inner, kmul * D, g)));
       else EZB_TRY((gemm<128, EpiGeglu<128>>(*dev, st, act, kmul * D, w.mlp1, kmul * D, M, 2 * inner, kmul * D, g)));
       EpiLinearParams e = epi();
       e.bias = w.b_mlp2; e.resid = x_out; e.ldr = D; e.gate = m + 5 * D; e.gate_bstride = mbs; e.rows_per_batch = L; e.out_f32 = x_out; e.ld32 = D;

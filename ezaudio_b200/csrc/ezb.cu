@@ -50,6 +50,7 @@ __attribute__((visibility("default"))) int ezb_test_gemm(int device, const void*
   if (epi_kind == 20) {  // swap-AB: 128 features x 256 tokens tiles, fp32 output
     if (cp) return fail(EZB_ERR_UNSUPPORTED, "swap-AB GEMM has no conv addressing");
     EpiLinearParams p = to_epi(e);
+    if (opt_swap_mc()) return gemm_swapped_mc<EpiLinearT<256>, 3>(dev, st, a, lda, w, ldw, M, N, K, p);
     return gemm_swapped<EpiLinearT<256>>(dev, st, a, lda, w, ldw, M, N, K, p);
   }
   if (epi_kind == 10 || epi_kind == 11) {  // CTA-pair kernel (bn is the pair tile's N)
@@ -232,6 +233,8 @@ EZB_API int ezb_set_option(const char* name, int value) {
   if (name && !strcmp(name, "pdl")) { opt_pdl() = value; return EZB_OK; }
   if (name && !strcmp(name, "swap_ab")) { opt_swap_ab() = value; return EZB_OK; }
   if (name && !strcmp(name, "qkv3")) { opt_qkv3() = value; return EZB_OK; }
+  if (name && !strcmp(name, "skip")) { opt_skip() = value; return EZB_OK; }
+  if (name && !strcmp(name, "swap_mc")) { opt_swap_mc() = value; return EZB_OK; }
   if (name && !strcmp(name, "attn_poly")) { opt_attn_poly() = value; return EZB_OK; }
   if (name && !strcmp(name, "rope_mufu")) { opt_rope_mufu() = value; return EZB_OK; }
   if (name && !strcmp(name, "gemm_debug")) {  // cycle counters of CTA 0 of every pair-GEMM launch (accumulated)

@@ -411,11 +411,18 @@ struct GemmCfg {
   static_assert(STAGES >= 3, "smem budget");
 };
 
-template <int BN, class Epi>
+// MC > 1: launched as clusters of MC CTAs with consecutive blockIdx.x = consecutive M tiles of the SAME N tile (host guarantees
+// num_m_tiles % MC == 0, gridDim.x % MC == 0 and num_tiles % MC == 0, so the CTAs of a cluster walk the same number of tiles in step).
+// The N-side operand tile (BN rows x 64 columns) is then fetched ONCE per cluster: tmB is a map with 32-row boxes, CTA rank r issues the
+// sub-boxes j = r, r + MC, ... with .multicast::cluster, every CTA still expects the full A + B bytes on its own `full` barrier, and a
+// stage is free again only when all MC consumers have released it (`empty` counts MC multicast commits).
+template <int BN, class Epi, int MC = 1>
 __global__ void __launch_bounds__((GemmCfg<BN, Epi, false>::THREADS), 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmShape g,
                     const typename Epi::Params ep) {
   static_assert(BN % 16 == 0 && BN >= 64 && BN <= 256, "BN");
+  static_assert(MC >= 1 && MC <= 8 && (MC == 1 || BN % 32 == 0), "MC");
+  constexpr uint16_t MC_MASK = static_cast<uint16_t>((1u << MC) - 1u);
   using SM = GemmCfg<BN, Epi, false>;
   constexpr int STAGES = SM::STAGES;
   constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
@@ -441,7 +448,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tma_prefetch_desc(&tmB);
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 1);
+      mbar_init(&empty[i], MC);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
@@ -452,6 +459,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
+  if (MC > 1) cluster_sync_all();  // peers multicast into our stages and arrive on our barriers: they must exist first
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_launch();
@@ -480,7 +488,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               tma_load_3d(sA + stage * SM::A_BYTES, &tmA, &full[stage], cb * GEMM_BK, t0 + (tap - g.center) * g.dilation, bidx);
             }
           }
-          tma_load_2d(sB + stage * SM::B_BYTES, &tmB, &full[stage], kb * GEMM_BK, n0);
+          if (MC == 1) {
+            tma_load_2d(sB + stage * SM::B_BYTES, &tmB, &full[stage], kb * GEMM_BK, n0);
+          } else {
+            for (int j = (int)cluster_ctarank(); j < BN / 32; j += MC)
+              tma_load_2d_mc(sB + stage * SM::B_BYTES + j * 4096, &tmB, &full[stage], kb * GEMM_BK, n0 + j * 32, MC_MASK);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -501,7 +514,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const uint64_t bd = umma_desc_sw128(smem_u32(sB + stage * SM::B_BYTES));
 #pragma unroll
           for (int k = 0; k < GEMM_BK / 16; ++k) umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
-          umma_commit(&empty[stage]);
+          if (MC == 1) umma_commit(&empty[stage]);
+          else umma_commit_mc(&empty[stage], MC_MASK);
           if (kb == g.num_k_blocks - 1) umma_commit(&tfull[acc]);
         }
         __syncwarp();
@@ -542,6 +556,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
   tc_fence_before();
   __syncthreads();
+  if (MC > 1) cluster_sync_all();  // nobody leaves while a peer may still multicast into this CTA or arrive on its barriers
   if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 

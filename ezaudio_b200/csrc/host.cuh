@@ -180,6 +180,12 @@ inline int& opt_attn_poly() {
   static int v = 0;  // measured: 27.3 us vs 25.9 us (self, XL) with one exp2 in four on the FMA pipe -- the softmax warps are issue-bound, not MUFU-bound
   return v;
 }
+// profiling only: bit mask of kernel classes NOT launched (results are garbage, timing shows each class's in-situ cost under graph replay + PDL):
+// 1 LayerNorm passes, 2 attention, 4 QKV / cross-Q heads GEMMs, 8 fp32-output linears (proj, cross-proj, MLP-out, skip), 16 GEGLU GEMM
+inline int& opt_skip() {
+  static int v = 0;
+  return v;
+}
 inline unsigned long long& option_epoch() {
   static unsigned long long v = 0;
   return v;
@@ -270,6 +276,63 @@ int gemm_swapped(Device& dev, cudaStream_t st, const __nv_bfloat16* A, int lda, 
   EZB_TRY(dev.tmaps.get2d(W, (uint64_t)K, (uint64_t)N_features, (uint64_t)ldw, GEMM_BM, &tA));
   EZB_TRY(dev.tmaps.get2d(A, (uint64_t)K, (uint64_t)M_tokens, (uint64_t)lda, BN, &tB));
   return launch_gemm_t<BN, Epi>(dev, st, tA, tB, g, ep);
+}
+
+// Swap-AB launch with the activation tile multicast across clusters of MC feature tiles (gemm_tcgen05_kernel<.., MC>): the one-wave
+// swap-AB GEMMs are L2-feed bound (48 KB per CTA per k-block); sharing the 32 KB token tile between MC = 3 CTAs leaves 26.7 KB.
+// Falls back to the plain launch whenever the shape does not split into whole clusters or the device cannot host them in one wave.
+inline int& opt_swap_mc() {
+  static int v = 0;   // NOT validated on hardware yet (written at the end of round 1 without GPU time): off by default
+  return v;
+}
+template <class Epi, int MC>
+int gemm_swapped_mc(Device& dev, cudaStream_t st, const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, int M_tokens, int N_features, int K,
+                    const typename Epi::Params& ep) {
+  constexpr int BN = 256;
+  const int mt = (N_features + GEMM_BM - 1) / GEMM_BM, nt = (M_tokens + BN - 1) / BN, tiles = mt * nt;
+  auto kern = gemm_tcgen05_kernel<BN, Epi, MC>;
+  constexpr int smem = GemmCfg<BN, Epi, false>::BYTES;
+  constexpr int GEMM_THREADS = GemmCfg<BN, Epi, false>::THREADS;
+  static int max_clusters[16] = {};   // 0 = not queried yet, -1 = unusable
+  int& mc = max_clusters[dev.id & 15];
+  if (mc == 0) {
+    mc = -1;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) == cudaSuccess) {
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof cfg);
+      cfg.gridDim = dim3(MC * 64); cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = smem;
+      cudaLaunchAttribute at;
+      at.id = cudaLaunchAttributeClusterDimension; at.val.clusterDim.x = MC; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+      cfg.attrs = &at; cfg.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) == cudaSuccess && n > 0) mc = n;
+    }
+    (void)cudaGetLastError();
+  }
+  if (mc <= 0 || (mt % MC) || tiles > mc * MC || (K % 8) || (lda % 8) || (ldw % 8))
+    return gemm_swapped<Epi>(dev, st, A, lda, W, ldw, M_tokens, N_features, K, ep);
+  GemmShape g;
+  memset(&g, 0, sizeof g);
+  g.M = N_features; g.N = M_tokens;
+  g.num_m_tiles = mt; g.num_n_tiles = nt;
+  g.num_k_blocks = (K + GEMM_BK - 1) / GEMM_BK;
+  const CUtensorMap *tA, *tB;
+  EZB_TRY(dev.tmaps.get2d(W, (uint64_t)K, (uint64_t)N_features, (uint64_t)ldw, GEMM_BM, &tA));
+  EZB_TRY(dev.tmaps.get2d(A, (uint64_t)K, (uint64_t)M_tokens, (uint64_t)lda, 32, &tB));   // 32-row boxes: the multicast granule
+  GemmProf& gp = gemm_prof();
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (gp.on) {
+    if (gp.used + 2 > gp.ev.size()) {
+      for (int i = 0; i < 2; ++i) { cudaEvent_t e; EZB_CUDA(cudaEventCreate(&e)); gp.ev.push_back(e); }
+    }
+    e0 = gp.ev[gp.used]; e1 = gp.ev[gp.used + 1];
+    gp.used += 2;
+    gp.flops.push_back(2.0 * (double)g.M * (double)g.N * (double)g.num_k_blocks * GEMM_BK);
+    EZB_CUDA(cudaEventRecord(e0, st));
+  }
+  EZB_TRY(launch_k(kern, dim3(tiles), dim3(GEMM_THREADS), smem, st, MC, *tA, *tB, g, ep));   // one tile per CTA, whole clusters
+  if (gp.on) EZB_CUDA(cudaEventRecord(e1, st));
+  return EZB_OK;
 }
 
 // CTA-pair GEMM launch: 256 x BN tiles, cluster (2,1,1), one pair per TPC.

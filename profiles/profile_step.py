@@ -63,4 +63,17 @@ for i in range(20):
     step(i)
 e1.record()
 torch.cuda.synchronize()
-print(f"opts {a.opt}: {e0.elapsed_time(e1) / 20:.3f} ms per eager DiT step (+CFG/DDIM)")
+eager_ms = e0.elapsed_time(e1) / 20
+# the same step replayed from a CUDA graph (what the sampling loop does): no host launch cost at all
+g = torch.cuda.CUDAGraph()
+with torch.cuda.graph(g):
+    step(0)
+for _ in range(3):
+    g.replay()
+torch.cuda.synchronize()
+e0.record()
+for i in range(20):
+    g.replay()
+e1.record()
+torch.cuda.synchronize()
+print(f"opts {a.opt}: {eager_ms:.3f} ms per eager DiT step (+CFG/DDIM), {e0.elapsed_time(e1) / 20:.3f} ms per graph replay")

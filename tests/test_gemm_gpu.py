@@ -168,3 +168,27 @@ def test_swap_ab_gemm_gated_residual(M, N, K, L):
     x3 = x.clone()
     _run(A, W, _epi(bias=bias, resid=x3, ldr=N, out_f32=x3, ld32=N), M, N, K, 256, kind=20)
     assert (x3 - (x + ref_mm)).abs().max().item() < tol
+
+
+@pytest.mark.parametrize("M,N,K,L", [(4000, 1152, 1152, 500), (4000, 1152, 4608, 500), (2000, 1152, 1152, 500), (4000, 1024, 1024, 500)])
+def test_swap_ab_multicast_matches_plain(M, N, K, L):
+    """wip: clusters of 3 feature tiles share the activation tile (TMA multicast).  Shapes that do not split into whole clusters
+    (N = 1024: 8 feature tiles) or do not fit one wave must fall back and still be right."""
+    from ezaudio_b200 import _lib
+    L_ = _lib.lib()
+    g = torch.Generator(device="cuda").manual_seed(M + N + K + 1)
+    A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    W = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    x = torch.randn(M, N, device="cuda", generator=g)
+    ref = x + A.float() @ W.float().t() + bias
+    tol = 3e-3 * max(1.0, math.sqrt(K / 1024))
+    _lib.check(L_.ezb_set_option(b"swap_mc", 1))
+    try:
+        for _ in range(3):   # stage / phase wrap-around across launches
+            x2 = x.clone()
+            _run(A, W, _epi(bias=bias, resid=x2, ldr=N, out_f32=x2, ld32=N), M, N, K, 256, kind=20)
+            torch.cuda.synchronize()
+            assert (x2 - ref).abs().max().item() < tol
+    finally:
+        _lib.check(L_.ezb_set_option(b"swap_mc", 0))
