@@ -66,6 +66,9 @@ _SIGS = {
     "ezb_t5_finalize_weights": ([_VP, _VP], _I),
     "ezb_t5_forward": ([_VP, _VP, _VP, _VP, _VP, _I, _I, _VP], _I),
     "ezb_energy_condition": ([_I, _VP, _VP, _I, _I, _I, _I, _F, _I, _I, _VP], _I),
+    "ezb_wave_prepare": ([_I, _VP, _VP, _I, _I, _I, _I, _F, _VP], _I),
+    "ezb_wave_splice": ([_I, _VP, C.c_longlong, _VP, C.c_longlong, C.c_longlong, _VP], _I),
+    "ezb_wave_to_pcm16": ([_I, _VP, _VP, C.c_longlong, _VP], _I),
     "ezb_set_option": ([C.c_char_p, _I], _I),
     "ezb_debug_read": ([C.POINTER(C.c_ulonglong)], _I),
     "ezb_launch_count": ([], C.c_ulonglong),

@@ -15,7 +15,7 @@ from typing import Callable, List, Optional, Sequence, Union
 import numpy as np
 import torch
 
-from . import _lib, config, weights
+from . import _lib, config, post, weights
 from ._lib import EzbError
 from .dit import DiTControlNet, MaskDiT
 from .inference import inference
@@ -213,21 +213,22 @@ class EzAudio(_Base):
             guidance_scale = None
             print("empyt input")
         mask_end = mask_start + mask_length
-        gt = _load_audio(gt_file, sr)
-        gt = gt / (np.max(np.abs(gt)) + 1e-9)
-        audio_length = len(gt) / sr
+        gt_raw = _load_audio(gt_file, sr) if isinstance(gt_file, str) else np.asarray(gt_file, dtype=np.float32)
+        audio_length = len(gt_raw) / sr
         mask_start = min(mask_start, audio_length)
-        if mask_end > audio_length:  # outpainting
-            gt = np.pad(gt, (0, round((mask_end - audio_length) * sr)), "constant")
-            audio_length = len(gt) / sr
-        output_audio = gt.copy()
-        gt_t = torch.tensor(gt).unsqueeze(0).unsqueeze(1).to(self.device)
+        n_total = len(gt_raw)
+        if mask_end > audio_length:  # outpainting: zero padding up to the end of the mask
+            n_total += round((mask_end - audio_length) * sr)
+            audio_length = n_total / sr
+        # the clip goes to the device ONCE: peak-normalise + pad there (ezb_wave_prepare = api/ezaudio.py:147,152-154 on the device)
+        output_audio = post.prepare_wave(torch.from_numpy(gt_raw).to(self.device).unsqueeze(0), n_total, normalize=True)[0]
         boundary = min((mask_end - mask_start) / 2, boundary)
         start_idx = max(mask_start - boundary, 0)
         end_idx = min(mask_end + boundary, audio_length)
         mask_start -= start_idx
         mask_end -= start_idx
-        gt_t = gt_t[:, :, round(start_idx * sr):round(end_idx * sr)]
+        s0, s1 = round(start_idx * sr), round(end_idx * sr)
+        gt_t = output_audio[s0:s1].clone().view(1, 1, -1)
         gt_latent = self.autoencoder(audio=gt_t)  # OobleckEncoder + stochastic VAE bottleneck (global RNG, bottleneck.py:69)
         B, D, L = gt_latent.shape
         gt_mask = torch.zeros(B, D, L, device=self.device)
@@ -239,10 +240,10 @@ class EzAudio(_Base):
         embeds = self._text_embeds([text], [""])
         pred = inference(self.autoencoder, self.unet, gt_latent, gt_mask, None, None, self.params, self.noise_scheduler, [text], None, L,
                          guidance_scale, guidance_rescale, ddim_steps, eta, random_seed, self.device, text_embeds=embeds)
-        pred = pred.cpu().numpy().squeeze(0).squeeze(0)
-        pred = pred[:round((end_idx - start_idx) * sr)]
-        output_audio[round(start_idx * sr):round(end_idx * sr)] = pred
-        return sr, output_audio
+        # trim + paste on the device (ezb_wave_splice = api/ezaudio.py:198-203), one download of the finished clip
+        n = min(round((end_idx - start_idx) * sr), pred.shape[-1], n_total - s0)
+        post.splice_wave(output_audio, pred[0, 0], s0, n)
+        return sr, output_audio.cpu().numpy()
 
 
 def energy_condition(audio: torch.Tensor, hop_size=240, window_size=1920, padding="reflect", min_db=-60, norm=True, quantize_levels=None,
@@ -295,14 +296,11 @@ class EzAudio_ControlNet(_Base):
         """api/controlnet.py:113-161.  `audio_path` may also be a float32 numpy waveform at the model sample rate."""
         sr = self.params["autoencoder"]["sr"]
         gt = _load_audio(audio_path, sr) if isinstance(audio_path, str) else np.asarray(audio_path, dtype=np.float32)
-        gt = gt / (np.max(np.abs(gt)) + 1e-9)
-        if surpass_noise > 0:
-            gt[np.abs(gt) <= surpass_noise] = 0
         original_length = len(gt)
         num_samples = int(10 * sr)
         audio_frames = round(num_samples / sr * self.params["autoencoder"]["latent_sr"])
-        gt = np.pad(gt, (0, num_samples - len(gt)), "constant") if len(gt) < num_samples else gt[:num_samples]
-        gt_audio = torch.tensor(gt).unsqueeze(0).to(self.device)
+        # normalise, noise-gate and pad / crop to 10 s on the device (ezb_wave_prepare = api/controlnet.py:119-136)
+        gt_audio = post.prepare_wave(torch.from_numpy(gt).to(self.device).unsqueeze(0), num_samples, normalize=True, gate=float(surpass_noise or 0))
         # the reference encodes gt_audio only to read its latent SHAPE (api/controlnet.py:141-142): (1, 128, audio_frames)
         cond_kw = {k: v for k, v in self.params["conditioner"].items() if k != "condition_type"}
         condition = energy_condition(gt_audio, **cond_kw)

@@ -578,3 +578,54 @@ __global__ void __launch_bounds__(1024) energy_kernel(const float* __restrict__ 
   }
 }
 }  // namespace ezb
+
+namespace ezb {
+// ---------------------------------------------------------------------------------------------------------------------------------
+// Waveform pre / post-processing around the path, device-side so that clips never bounce through the host:
+//   wave_prepare : gt / (max|gt| + 1e-9), optional noise gate |x| <= thr -> 0, pad / crop to T_out   (api/ezaudio.py:147,
+//                  api/controlnet.py:119-133).  One CTA per clip: block max-abs reduction, then a scaled copy.
+//   wave_splice  : output_audio[start : start + n] = pred[:n]                                         (api/ezaudio.py:198-203)
+//   wave_to_pcm16: float -> 16-bit PCM with saturation (soundfile.write's default WAV subtype)         (t2a_demo.py:13,20)
+// All three are HBM-bound copies: 4-8 bytes per sample.
+__global__ void __launch_bounds__(1024) wave_prepare_kernel(const float* __restrict__ in, float* __restrict__ out, int T_in, int T_out, float eps,
+                                                            float gate, int normalize) {
+  __shared__ float red[32];
+  __shared__ float inv_s;
+  const int b = blockIdx.x;
+  const float* a = in + (size_t)b * T_in;
+  float inv = 1.f;
+  if (normalize) {
+    float m = 0.f;
+    for (int i = threadIdx.x; i < T_in; i += blockDim.x) m = fmaxf(m, fabsf(a[i]));
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float mx = red[0];
+      for (int w = 1; w < (int)(blockDim.x >> 5); ++w) mx = fmaxf(mx, red[w]);
+      inv_s = mx + eps;
+    }
+    __syncthreads();
+    inv = inv_s;
+  }
+  float* o = out + (size_t)b * T_out;
+  for (int i = threadIdx.x; i < T_out; i += blockDim.x) {
+    float v = 0.f;
+    if (i < T_in) {
+      v = normalize ? a[i] / inv : a[i];   // a true division like numpy's (not a reciprocal multiply): bit-identical to the reference's float32 result
+      if (gate > 0.f && fabsf(v) <= gate) v = 0.f;
+    }
+    o[i] = v;
+  }
+}
+__global__ void wave_splice_kernel(float* __restrict__ dst, const float* __restrict__ src, long long start, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[start + i] = src[i];
+}
+__global__ void wave_to_pcm16_kernel(const float* __restrict__ in, int16_t* __restrict__ out, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = fminf(fmaxf(in[i] * 32768.0f, -32768.0f), 32767.0f);
+  out[i] = (int16_t)__float2int_rn(v);
+}
+}  // namespace ezb

@@ -199,6 +199,33 @@ EZB_API int ezb_energy_condition(int device, const float* audio, float* out, int
   EZB_CUDA(cudaGetLastError());
   return EZB_OK;
 }
+EZB_API int ezb_wave_prepare(int device, const float* in, float* out, int B, int T_in, int T_out, int normalize, float gate, void* stream) {
+  if (!in || !out || B < 1 || T_in < 1 || T_out < 1) return fail(EZB_ERR_ARG, "ezb_wave_prepare: bad argument");
+  EZB_CUDA(cudaSetDevice(device));
+  ++launch_counter();
+  wave_prepare_kernel<<<B, 1024, 0, ST(stream)>>>(in, out, T_in, T_out, 1e-9f, gate, normalize);
+  EZB_CUDA(cudaGetLastError());
+  return EZB_OK;
+}
+EZB_API int ezb_wave_splice(int device, float* dst, long long dst_len, const float* src, long long start, long long n, void* stream) {
+  if (!dst || !src) return fail(EZB_ERR_ARG, "ezb_wave_splice: null pointer");
+  if (start < 0 || n < 0 || start + n > dst_len) return fail(EZB_ERR_SHAPE, "ezb_wave_splice: [%lld, %lld) outside a clip of %lld samples", start, start + n, dst_len);
+  if (n == 0) return EZB_OK;
+  EZB_CUDA(cudaSetDevice(device));
+  ++launch_counter();
+  wave_splice_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ST(stream)>>>(dst, src, start, n);
+  EZB_CUDA(cudaGetLastError());
+  return EZB_OK;
+}
+EZB_API int ezb_wave_to_pcm16(int device, const float* in, int16_t* out, long long n, void* stream) {
+  if (!in || !out || n < 0) return fail(EZB_ERR_ARG, "ezb_wave_to_pcm16: bad argument");
+  if (n == 0) return EZB_OK;
+  EZB_CUDA(cudaSetDevice(device));
+  ++launch_counter();
+  wave_to_pcm16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ST(stream)>>>(in, out, n);
+  EZB_CUDA(cudaGetLastError());
+  return EZB_OK;
+}
 EZB_API int ezb_vae_decode(ezb_vae* h, const float* z, float* wav, int B, int L, void* stream) {
   if (!h || !z || !wav) return fail(EZB_ERR_ARG, "ezb_vae_decode: null argument");
   return reinterpret_cast<Vae*>(h)->decode(z, wav, B, L, ST(stream));

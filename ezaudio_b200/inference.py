@@ -80,9 +80,14 @@ def _sample_latents_on_device(unet, noise_scheduler, text, text_mask, uncond_tex
     gens = None
     if init_noise is None:
         gens = []
+        per_prompt = isinstance(random_seed, (list, tuple))   # one seed per prompt (batching front-end): prompt i ~ Generator(seed_i)
+        if per_prompt and len(random_seed) != B:
+            raise ValueError(f"random_seed lists one seed per prompt: got {len(random_seed)} for {B} prompts")
         for i in range(B):
             g = torch.Generator(device=device)
-            if random_seed is not None:
+            if per_prompt:
+                g.manual_seed(int(random_seed[i]))
+            elif random_seed is not None:
                 g.manual_seed(int(random_seed) + i)
             else:
                 g.seed()

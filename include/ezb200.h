@@ -111,6 +111,17 @@ int ezb_vae_encode(ezb_vae* h, const float* audio, const float* noise, float* z,
 int ezb_energy_condition(int device, const float* audio, float* out, int B, int T, int hop_size, int window_size, float min_db, int norm,
                          int quantize_levels, void* stream);
 
+/* --- waveform pre / post-processing around the path, device pointers, fp32 mono clips.
+ * ezb_wave_prepare: per clip  x <- x / (max|x| + 1e-9) when normalize != 0 (api/ezaudio.py:147, api/controlnet.py:119), samples with
+ *   |x| <= gate zeroed when gate > 0 (`surpass_noise`, api/controlnet.py:121-124), then zero-padded or cropped from T_in to T_out samples
+ *   (api/controlnet.py:131-136).  in (B,T_in), out (B,T_out).
+ * ezb_wave_splice: dst[start : start+n] = src[0 : n] -- the paste of the regenerated chunk into the original clip (api/ezaudio.py:198-203).
+ * ezb_wave_to_pcm16: round(x * 32768) saturated to int16 -- the sample format soundfile.write(path, audio, sr) produces by default for
+ *   WAV (t2a_demo.py:13,20). */
+int ezb_wave_prepare(int device, const float* in, float* out, int B, int T_in, int T_out, int normalize, float gate, void* stream);
+int ezb_wave_splice(int device, float* dst, long long dst_len, const float* src, long long start, long long n, void* stream);
+int ezb_wave_to_pcm16(int device, const float* in, int16_t* out, long long n, void* stream);
+
 /* --- T5 (v1.1 / flan-T5, gated-GELU) text encoder: `text_encoder(input_ids=, attention_mask=).last_hidden_state`, src/inference.py:38-50;
  * model class transformers.T5EncoderModel loaded at api/ezaudio.py:78-79 (the step before the denoiser path). */
 typedef struct ezb_t5 ezb_t5;
