@@ -24,6 +24,10 @@ struct BlockW {
   bf16* zero_w = nullptr;
   float* zero_b = nullptr;
   float h_nq[2][96] = {}, h_nk[2][96] = {}, h_cnq[2][96] = {}, h_cnk[2][96] = {};  // host copies [weight|bias][dh] of the per-head LayerNorms
+  // folded-LayerNorm tables (gemm.cuh FoldIn / FoldOut): per timestep [T][.] for the modulated sites 1 (norm1 -> QKV) and 3 (norm3 -> GEGLU),
+  // static for site 2 (norm2 -> cross-Q) and the skip path (skip_norm -> skip_linear)
+  float *g1 = nullptr, *u1 = nullptr, *v1 = nullptr, *g3 = nullptr, *u3 = nullptr, *v3 = nullptr, *u2 = nullptr, *v2 = nullptr, *us = nullptr, *vs = nullptr;
+  float2 *st_skip = nullptr, *st_a = nullptr, *st_b = nullptr, *st_out = nullptr;   // per-row partial sums written by the residual-stream GEMMs
   // per-clip cross-attention K / V^T caches
   float *kc32 = nullptr, *vc32 = nullptr;
   bf16 *kc16 = nullptr, *vtc16 = nullptr;
@@ -36,6 +40,12 @@ struct WeightSpec {
 };
 
 constexpr int KP_PATCH_ALIGN = 8;
+
+struct FoldCtx {
+  bool on = false;
+  int t = 0;                  // timestep index (uniform over the batch)
+  const float2* st_x = nullptr;
+};
 
 struct Dit {
   ezb_dit_desc d;
@@ -71,6 +81,15 @@ struct Dit {
   bool fused_heads = false;
   bool pair = true;       // CTA-pair (cta_group::2) GEMMs
   bool swap_ab = true;    // swap-AB tiles for the fp32-output N = D layers
+  // LayerNorm folded into the neighbouring GEMMs (fast mode, uniform timestep): see gemm.cuh
+  bool fold_cfg = false;  // handle built with the fold tables / buffers
+  int fold_T = 0;         // timesteps the per-timestep tables hold
+  int fold_n = 0;         // timesteps currently tabulated (0: tables not valid for the current schedule)
+  int st_slots = 0, n_qkv = 0;
+  size_t st_ld = 0;
+  float *gc_G = nullptr, *gc_C = nullptr, *gF = nullptr, *uF = nullptr, *vF = nullptr;
+  float2* st_x0 = nullptr;
+  std::vector<bf16*> cat;   // MaskDiT: per in-block [Mx, 2D] = [x of the paired out-block * snw[:D] | this block's output * snw[D:]]; ControlNet: [Mx, D] plain cast
   int geglu_bn = 128;     // N-tile of the GEGLU GEMM: packing group = geglu_bn / 2
   int qkv3_bn = 0;        // >0: self-attention QKV weight packed three heads per N-tile of this width (EpiHeads<DH,3>)
 
@@ -298,6 +317,29 @@ struct Dit {
         EZB_TRY(alloc(&blk[i].vtc16, (size_t)d.max_batch * H * DVP * Lcp));
       }
     }
+    // ---- folded LayerNorm: tables + operand / statistics buffers
+    fold_cfg = opt_fold() != 0 && d.precision == 0 && pair && swap_ab && fused_heads && D <= 2304 / 2;
+    if (fold_cfg) {
+      fold_T = d.max_timesteps < 128 ? d.max_timesteps : 128;
+      st_slots = (D + 31) / 32;
+      st_ld = Mx;
+      n_qkv = qkv3_bn > 0 ? H * qkv3_bn : 3 * D;
+      const size_t FT = fold_T;
+      EZB_TRY(alloc(&gc_G, FT * 2 * D)); EZB_TRY(alloc(&gc_C, FT * 2 * D));
+      EZB_TRY(alloc(&st_x0, (size_t)st_slots * st_ld));
+      cat.resize(half);
+      for (int i = 0; i < half; ++i) EZB_TRY(alloc(&cat[i], Mx * (d.is_controlnet ? D : 2 * D)));
+      for (int i = 0; i < nblk; ++i) {
+        BlockW& w = blk[i];
+        EZB_TRY(alloc(&w.g1, FT * D)); EZB_TRY(alloc(&w.u1, FT * n_qkv)); EZB_TRY(alloc(&w.v1, FT * n_qkv));
+        EZB_TRY(alloc(&w.g3, FT * D)); EZB_TRY(alloc(&w.u3, FT * 2 * inner)); EZB_TRY(alloc(&w.v3, FT * 2 * inner));
+        EZB_TRY(alloc(&w.u2, (size_t)D)); EZB_TRY(alloc(&w.v2, (size_t)D));
+        if (!d.is_controlnet && i > half) { EZB_TRY(alloc(&w.us, (size_t)D)); EZB_TRY(alloc(&w.vs, (size_t)D)); }
+        EZB_TRY(alloc(&w.st_skip, (size_t)st_slots * st_ld)); EZB_TRY(alloc(&w.st_a, (size_t)st_slots * st_ld));
+        EZB_TRY(alloc(&w.st_b, (size_t)st_slots * st_ld)); EZB_TRY(alloc(&w.st_out, (size_t)st_slots * st_ld));
+      }
+      if (!d.is_controlnet) { EZB_TRY(alloc(&gF, FT * D)); EZB_TRY(alloc(&uF, FT * C)); EZB_TRY(alloc(&vF, FT * C)); }
+    }
     const size_t T = d.max_timesteps;
     EZB_TRY(alloc(&t_vals, T)); EZB_TRY(alloc(&t_emb, T * 256)); EZB_TRY(alloc(&t_h, T * D)); EZB_TRY(alloc(&t_tok, T * D));
     EZB_TRY(alloc(&t_ada, T * 6 * D)); EZB_TRY(alloc(&t_lora, T * 6 * r));
@@ -345,7 +387,48 @@ struct Dit {
       EZB_CUDA(cudaGetLastError());
       EZB_CUDA(cudaDeviceSynchronize());
     }
+    if (fold_cfg) {  // static sites: norm2 -> cross-Q and skip_norm -> skip_linear (no modulation: G = weight, C = bias)
+      for (int i = 0; i < nblk; ++i) {
+        BlockW& w = blk[i];
+        EZB_TRY(fold_uv(0, w.cq, D, w.n2w, w.n2b, nullptr, w.u2, w.v2, D, D, 1));
+        if (w.us) EZB_TRY(fold_uv(0, w.skip, 2 * D, w.snw, w.snb, nullptr, w.us, w.vs, D, 2 * D, 1));
+      }
+      EZB_CUDA(cudaDeviceSynchronize());
+    }
     finalized = true;
+    return EZB_OK;
+  }
+  int fold_uv(cudaStream_t st, const bf16* W, int ldw, const float* G, const float* Cc, const float* add_v, float* U, float* V, int N, int K, int R) {
+    if (K > 72 * 32) return fail(EZB_ERR_UNSUPPORTED, "fold_uv: K %d", K);
+    ++launch_counter();
+    fold_uv_kernel<<<(N + 7) / 8, 256, 0, st>>>(W, ldw, G, Cc, add_v, U, V, N, K, R);
+    EZB_CUDA(cudaGetLastError());
+    return EZB_OK;
+  }
+  // per-timestep tables of the modulated sites (called at the end of set_timesteps)
+  int build_fold_tables(int n, cudaStream_t st) {
+    fold_n = 0;
+    if (!fold_cfg || n > fold_T) return EZB_OK;
+    const int ldm = nblk * 6 * D;
+    auto gc = [&](const float* w_, const float* b_, const float* shift, const float* scale, int ld, float* G) -> int {
+      ++launch_counter();
+      fold_gc_kernel<<<(n * D + 255) / 256, 256, 0, st>>>(w_, b_, shift, scale, ld, G, gc_C, n, D);
+      EZB_CUDA(cudaGetLastError());
+      return EZB_OK;
+    };
+    for (int i = 0; i < nblk; ++i) {
+      BlockW& w = blk[i];
+      const float* m = mod + (size_t)i * 6 * D;   // [t] stride ldm: shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp
+      EZB_TRY(gc(w.n1w, w.n1b, m + 0 * D, m + 1 * D, ldm, w.g1));
+      EZB_TRY(fold_uv(st, w.qkv, D, w.g1, gc_C, nullptr, w.u1, w.v1, n_qkv, D, n));
+      EZB_TRY(gc(w.n3w, w.n3b, m + 3 * D, m + 4 * D, ldm, w.g3));
+      EZB_TRY(fold_uv(st, w.mlp1, D, w.g3, gc_C, w.b_mlp1, w.u3, w.v3, 2 * inner, D, n));   // v3 carries the (packed) GEGLU bias
+    }
+    if (!d.is_controlnet) {  // FinalBlock: shift, scale = time_ada_final.chunk(2) (blocks.py:204)
+      EZB_TRY(gc(fn_w, fn_b, mod_final, mod_final + D, 2 * D, gF));
+      EZB_TRY(fold_uv(st, w_final, D, gF, gc_C, nullptr, uF, vF, C, D, n));
+    }
+    fold_n = n;
     return EZB_OK;
   }
 
@@ -370,11 +453,25 @@ struct Dit {
   int lin(cudaStream_t st, const bf16* A, int K, const bf16* W, int M, int N, const EpiLinearParams& e) {
     if ((opt_skip() & 8) && e.out_f32 != nullptr && e.out_bf16 == nullptr) return EZB_OK;
     // fp32-output layers (residual / gated-residual / plain): swap-AB 128 x 256 tiles -- one full wave for N = 1152 at M = 4000
-    if (pair && swap_ab && kmul == 1 && e.out_bf16 == nullptr && e.out_f32 != nullptr && e.out_scale == 0.f && e.bias_mod == 0 && M >= 512)
+    const bool folded = e.fin.u != nullptr || e.fout.st != nullptr;   // fold epilogues exist in the swap-AB kernel only
+    if (pair && swap_ab && kmul == 1 && e.out_bf16 == nullptr && e.out_f32 != nullptr && e.out_scale == 0.f && e.bias_mod == 0 && (M >= 512 || folded))
       return opt_swap_mc() ? gemm_swapped_mc<EpiLinearT<256>, 3>(*dev, st, A, K, W, K, M, N, K, e)
                            : gemm_swapped<EpiLinearT<256>>(*dev, st, A, K, W, K, M, N, K, e);
+    if (folded) return fail(EZB_ERR_STATE, "folded LayerNorm epilogue requested on a GEMM that is not a swap-AB launch");
     if (pair) return gemm2<128, EpiLinear<128>>(*dev, st, A, kmul * K, W, kmul * K, M, N, kmul * K, e);
     return gemm<128, EpiLinear<128>>(*dev, st, A, kmul * K, W, kmul * K, M, N, kmul * K, e);
+  }
+  FoldIn fold_in(const float2* st0, const float2* st1, int width, const float* u, const float* v) {
+    FoldIn f;
+    memset(&f, 0, sizeof f);
+    f.st0 = st0; f.st1 = st1; f.slots0 = st_slots; f.slots1 = st1 ? st_slots : 0; f.ld_st = (int)st_ld; f.inv_dim = 1.0f / (float)width; f.u = u; f.v = v;
+    return f;
+  }
+  FoldOut fold_out(float2* stp, bf16* a0, int ld0, const float* g0, bf16* a1 = nullptr, int ld1 = 0, const float* g1 = nullptr) {
+    FoldOut f;
+    memset(&f, 0, sizeof f);
+    f.st = stp; f.ld_st = (int)st_ld; f.a0 = a0; f.ld0 = ld0; f.g0 = g0; f.a1 = a1; f.ld1 = ld1; f.g1 = g1;
+    return f;
   }
   int small_lin(cudaStream_t st, const float* in, int ld_in, const float* W, const float* bias, const float* add, int ld_add, float* out, int ld_out, int R,
                 int N, int K, int act, float scale) {
@@ -407,10 +504,11 @@ struct Dit {
   }
   // Q/K/V projection with the fused per-head LN + RoPE + attention-layout epilogue (fast mode)
   int lin_heads(cudaStream_t st, const bf16* A, const bf16* W, int M, int N, const int* kinds, const float (*nq)[96], const float (*nk)[96], bool rope,
-                int L, bf16* qo, bf16* ko, bf16* vto, int Lpad) {
+                int L, bf16* qo, bf16* ko, bf16* vto, int Lpad, const FoldIn* fin = nullptr) {
     if (opt_skip() & 4) return EZB_OK;
     EpiHeadsParams e;
     memset(&e, 0, sizeof e);
+    if (fin) e.fin = *fin;
     for (int i = 0; i < dh && i < 72; ++i) {
       if (nq) { e.nw[0][i] = nq[0][i]; e.nb[0][i] = nq[1][i]; }
       if (nk) { e.nw[1][i] = nk[0][i]; e.nb[1][i] = nk[1][i]; }
@@ -515,7 +613,7 @@ struct Dit {
     }
     EZB_CUDA(cudaGetLastError());
     n_timesteps = n;
-    return EZB_OK;
+    return build_fold_tables(n, st);
   }
 
   // modulation rows for this call: uniform timestep -> point into the table (batch stride 0); else gather per sample
@@ -543,23 +641,54 @@ struct Dit {
 
   // ---------------------------------------------------------------- one DiT block (blocks.py:120-160)
   // x_in: residual stream entering; x_out: buffer the block's first residual write goes to (later ops update it in place).
-  int block(cudaStream_t st, int i, const float* x_in, float* x_out, const float* skip, const float* cskip, const float* modr, int mbs, int Be, int L) {
+  // Fold mode (fc.on): no LayerNorm pass is launched.  On entry `act` (or, for an out-block, the left half of cat[si]) already holds
+  // bf16(x_in * g) and fc.st_x the row statistics of x_in, both written by the GEMM that produced x_in; every residual-stream GEMM of
+  // the block does the same for the LayerNorm that follows it (gemm.cuh FoldIn / FoldOut).
+  // what reads the OUTPUT of block i: operand buffer(s) + multiplier(s) for the MLP-out epilogue
+  FoldOut block_output_fold(int i, int t) {
+    BlockW& w = blk[i];
+    if (d.is_controlnet) {  // next in-block's norm1 (if any) + the zero-linear of this block (plain cast)
+      if (i + 1 < half) return fold_out(w.st_out, act, D, blk[i + 1].g1 + (size_t)t * D, cat[i], D, nullptr);
+      return fold_out(w.st_out, cat[i], D, nullptr);
+    }
+    if (i < half) {   // in-block: norm1 of block i+1, and the skip half of the out-block that pops skip i
+      const int ob = half + 1 + (half - 1 - i);
+      return fold_out(w.st_out, act, D, blk[i + 1].g1 + (size_t)t * D, cat[i] + D, 2 * D, blk[ob].snw + D);
+    }
+    if (i < nblk - 1) {  // mid / out-block followed by an out-block: the x half of its concatenated skip_norm input
+      const int si = half - 1 - (i + 1 - half - 1);
+      return fold_out(w.st_out, cat[si], 2 * D, blk[i + 1].snw);
+    }
+    return fold_out(w.st_out, act, D, gF + (size_t)t * D);   // last block: FinalBlock norm
+  }
+  int block(cudaStream_t st, int i, const float* x_in, float* x_out, const float* skip, const float* cskip, const float* modr, int mbs, int Be, int L,
+            FoldCtx fc = FoldCtx()) {
     BlockW& w = blk[i];
     const int M = Be * L;
     const float* m = modr + (size_t)i * 6 * D;  // shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp (blocks.py:132-133)
+    const float2* st1 = fc.st_x;                // statistics of the tensor norm1 sees
     if (skip) {  // out-blocks: x = skip_linear(LN_2D(cat[x, skip (+ controlnet skip)]))  (blocks.py:124-128, udit.py:345-348)
-      EZB_TRY(ln(st, x_in, D, skip, cskip, D, w.snw, w.snb, nullptr, nullptr, 0, L, act, M));
+      const int si = half - 1 - (i - half - 1);
       EpiLinearParams e = epi();
       e.bias = w.b_skip; e.out_f32 = x_out; e.ld32 = D;
-      EZB_TRY(lin(st, act, 2 * D, w.skip, M, D, e));
+      const bf16* A = act;
+      if (fc.on && cskip == nullptr) {   // both halves of cat[si] and their statistics are in place
+        A = cat[si];
+        e.fin = fold_in(fc.st_x, blk[si].st_out, 2 * D, w.us, w.vs);
+      } else {
+        EZB_TRY(ln(st, x_in, D, skip, cskip, D, w.snw, w.snb, nullptr, nullptr, 0, L, act, M));
+      }
+      if (fc.on) { e.fout = fold_out(w.st_skip, act, D, w.g1 + (size_t)fc.t * D); st1 = w.st_skip; }
+      EZB_TRY(lin(st, A, 2 * D, w.skip, M, D, e));
       x_in = x_out;
     }
     // --- self-attention (blocks.py:137-141)
-    EZB_TRY(ln(st, x_in, D, nullptr, nullptr, 0, w.n1w, w.n1b, m + 0 * D, m + 1 * D, mbs, L, act, M));
+    if (!fc.on) EZB_TRY(ln(st, x_in, D, nullptr, nullptr, 0, w.n1w, w.n1b, m + 0 * D, m + 1 * D, mbs, L, act, M));
     if (fused_heads) {
       const int kinds[3] = {0, 1, 2};
       const int Lp = (L + 7) / 8 * 8;
-      EZB_TRY(lin_heads(st, act, w.qkv, M, 3 * D, kinds, w.h_nq, w.h_nk, true, L, q16, k16, vt16, Lp));
+      FoldIn f1 = fold_in(st1, nullptr, D, w.u1 + (size_t)fc.t * n_qkv, w.v1 + (size_t)fc.t * n_qkv);
+      EZB_TRY(lin_heads(st, act, w.qkv, M, 3 * D, kinds, w.h_nq, w.h_nk, true, L, q16, k16, vt16, Lp, fc.on ? &f1 : nullptr));
       EZB_TRY(attention(st, q32, k32, v32, q16, k16, vt16, nullptr, Be, L, L, Lp));
     } else {
       EZB_TRY(lin_to_qkv(st, act, D, w.qkv, M, 3 * D));
@@ -573,13 +702,15 @@ struct Dit {
     {
       EpiLinearParams e = epi();
       e.bias = w.b_proj; e.resid = x_in; e.ldr = D; e.gate = m + 2 * D; e.gate_bstride = mbs; e.rows_per_batch = L; e.out_f32 = x_out; e.ld32 = D;
+      if (fc.on) e.fout = fold_out(w.st_a, act, D, w.n2w);   // norm2 has no modulation: g = its weight
       EZB_TRY(lin(st, attn_out, D, w.proj, M, D, e));
     }
     // --- cross-attention (blocks.py:147-151): no modulation, no gate
-    EZB_TRY(ln(st, x_out, D, nullptr, nullptr, 0, w.n2w, w.n2b, nullptr, nullptr, 0, L, act, M));
+    if (!fc.on) EZB_TRY(ln(st, x_out, D, nullptr, nullptr, 0, w.n2w, w.n2b, nullptr, nullptr, 0, L, act, M));
     if (fused_heads) {
       const int kinds[1] = {0};
-      EZB_TRY(lin_heads(st, act, w.cq, M, D, kinds, w.h_cnq, nullptr, false, L, q16, nullptr, nullptr, 0));
+      FoldIn f2 = fold_in(w.st_a, nullptr, D, w.u2, w.v2);
+      EZB_TRY(lin_heads(st, act, w.cq, M, D, kinds, w.h_cnq, nullptr, false, L, q16, nullptr, nullptr, 0, fc.on ? &f2 : nullptr));
       EZB_TRY(attention(st, q32, w.kc32, w.vc32, q16, w.kc16, w.vtc16, ctx_mask, Be, L, ctx_Lc, ctx_Lpad));
     } else {
       EZB_TRY(lin_to_qkv(st, act, D, w.cq, M, D));
@@ -592,30 +723,44 @@ struct Dit {
     {
       EpiLinearParams e = epi();
       e.bias = w.b_cproj; e.resid = x_out; e.ldr = D; e.out_f32 = x_out; e.ld32 = D;
+      if (fc.on) e.fout = fold_out(w.st_b, act, D, w.g3 + (size_t)fc.t * D);
       EZB_TRY(lin(st, attn_out, D, w.cproj, M, D, e));
     }
     // --- GEGLU MLP (blocks.py:155-156; modules.py:263-277,366)
-    EZB_TRY(ln(st, x_out, D, nullptr, nullptr, 0, w.n3w, w.n3b, m + 3 * D, m + 4 * D, mbs, L, act, M));
+    if (!fc.on) EZB_TRY(ln(st, x_out, D, nullptr, nullptr, 0, w.n3w, w.n3b, m + 3 * D, m + 4 * D, mbs, L, act, M));
     {
       EpiGegluParams g;
+      memset(&g, 0, sizeof g);
       g.bias = w.b_mlp1; g.out_bf16 = mid; g.ld16 = kmul * inner; g.split_stride = kmul == 3 ? inner : 0;
+      if (fc.on) g.fin = fold_in(w.st_b, nullptr, D, w.u3 + (size_t)fc.t * 2 * inner, w.v3 + (size_t)fc.t * 2 * inner);
       if (opt_skip() & 16) {}
       else if (geglu_bn == 256) EZB_TRY((gemm2<256, EpiGeglu<256>>(*dev, st, act, kmul * D, w.mlp1, kmul * D, M, 2 * inner, kmul * D, g)));
       else EZB_TRY((gemm<128, EpiGeglu<128>>(*dev, st, act, kmul * D, w.mlp1, kmul * D, M, 2 * inner, kmul * D, g)));
       EpiLinearParams e = epi();
       e.bias = w.b_mlp2; e.resid = x_out; e.ldr = D; e.gate = m + 5 * D; e.gate_bstride = mbs; e.rows_per_batch = L; e.out_f32 = x_out; e.ld32 = D;
+      if (fc.on) e.fout = block_output_fold(i, fc.t);
       EZB_TRY(lin(st, mid, inner, w.mlp2, M, D, e));
     }
     return EZB_OK;
   }
 
-  int embed(cudaStream_t st, const float* x, const float* gt, const uint8_t* gt_mask, const float* resid, int Be, int L) {
+  int embed(cudaStream_t st, const float* x, const float* gt, const uint8_t* gt_mask, const float* resid, int Be, int L, const FoldCtx& fc = FoldCtx()) {
     dim3 grid((L + 31) / 32, (2 * C) / 32, Be), blockd(32, 8);
     if ((2 * C) % 32) return fail(EZB_ERR_UNSUPPORTED, "latent_chans must be a multiple of 16");
     EZB_TRY(launch_k(patch_pack_kernel, grid, blockd, 0, st, 1, x, gt, gt_mask, (const float*)mask_embed, a_patch, Be, C, L, Kp, kmul));
     EpiLinearParams e = epi();
     e.bias = b_patch; e.out_f32 = x0; e.ld32 = D; e.resid = resid; e.ldr = D;
+    if (fc.on) e.fout = fold_out(st_x0, act, D, blk[0].g1 + (size_t)fc.t * D);
     return lin(st, a_patch, Kp, w_patch, Be * L, D, e);
+  }
+  // fold mode for this call: tables valid for the schedule and one timestep for the whole batch
+  FoldCtx fold_ctx(int mbs, const float* modr) {
+    FoldCtx fc;
+    if (fold_cfg && fold_n > 0 && mbs == 0) {
+      const int t = (int)((modr - mod) / ((size_t)nblk * 6 * D));
+      if (t >= 0 && t < fold_n) { fc.on = true; fc.t = t; }
+    }
+    return fc;
   }
 
   int check_call(int Be, int L) {
@@ -633,24 +778,30 @@ struct Dit {
     const float *modr, *modf;
     int mbs, mbsf;
     EZB_TRY(select_mod(st, tidx, tall, Be, &modr, &modf, &mbs, &mbsf));
-    EZB_TRY(embed(st, x, gt, gt_mask, nullptr, Be, L));
+    FoldCtx fc = fold_ctx(mbs, modr);
+    EZB_TRY(embed(st, x, gt, gt_mask, nullptr, Be, L, fc));
     const float* xc = x0;
+    fc.st_x = st_x0;
     for (int i = 0; i < half; ++i) {
-      EZB_TRY(block(st, i, xc, skips[i], nullptr, nullptr, modr, mbs, Be, L));
+      EZB_TRY(block(st, i, xc, skips[i], nullptr, nullptr, modr, mbs, Be, L, fc));
       xc = skips[i];
+      fc.st_x = blk[i].st_out;
     }
-    EZB_TRY(block(st, half, xc, xa, nullptr, nullptr, modr, mbs, Be, L));
+    EZB_TRY(block(st, half, xc, xa, nullptr, nullptr, modr, mbs, Be, L, fc));
     xc = xa;
+    fc.st_x = blk[half].st_out;
     for (int j = 0; j < half; ++j) {
       const int si = half - 1 - j;  // skips.pop()
-      EZB_TRY(block(st, half + 1 + j, xc, xb, skips[si], cskips ? cskips[si] : nullptr, modr, mbs, Be, L));
+      EZB_TRY(block(st, half + 1 + j, xc, xb, skips[si], cskips ? cskips[si] : nullptr, modr, mbs, Be, L, fc));
       xc = xb;
+      fc.st_x = blk[half + 1 + j].st_out;
     }
     // FinalBlock (blocks.py:199-211): shift, scale = time_ada_final.chunk(2)
     const int M = Be * L;
-    EZB_TRY(ln(st, xc, D, nullptr, nullptr, 0, fn_w, fn_b, modf, modf + D, mbsf, L, act, M));
+    if (!fc.on) EZB_TRY(ln(st, xc, D, nullptr, nullptr, 0, fn_w, fn_b, modf, modf + D, mbsf, L, act, M));
     EpiLinearParams e = epi();
     e.bias = b_final; e.out_f32 = ybuf; e.ld32 = C;
+    if (fc.on) e.fin = fold_in(fc.st_x, nullptr, D, uF + (size_t)fc.t * C, vF + (size_t)fc.t * C);
     EZB_TRY(lin(st, act, D, w_final, M, C, e));
     dim3 grid((L + 31) / 32, Be);
     if (C % 4) return fail(EZB_ERR_UNSUPPORTED, "final conv: %d channels (multiple of 4 expected)", C);
@@ -689,18 +840,23 @@ inline int Dit::controlnet_forward(const float* x, const float* gt, const uint8_
   EZB_TRY(conv(cs_t0, cs_c0_w, cs_c0_b, cs_t1, c0 + 1, c0, T, c0 + 1, T, 3, 1, 1, 1, 0));    // conv3 + SiLU (mask channel == 0)
   EZB_TRY(conv(cs_t1, cs_c1_w, cs_c1_b, cs_t2, c0 + 1, c0 + 1, T, c1, L, 3, 2, 1, 1, 0));    // conv3 stride 2 + SiLU
   EZB_TRY(conv(cs_t2, cs_out_w, cs_out_b, cond_emb, c1, c1, L, D, L, 1, 1, 0, 0, 1));        // conv_out -> (B,L,D)
-  EZB_TRY(embed(st, x, gt, gt_mask, cond_emb, Be, L));                                       // x = patch_embed(x) + condition
+  FoldCtx fc = fold_ctx(mbs, modr);
+  EZB_TRY(embed(st, x, gt, gt_mask, cond_emb, Be, L, fc));                                   // x = patch_embed(x) + condition
   const float* xc = x0;
   const int M = Be * L;
+  fc.st_x = st_x0;
   for (int i = 0; i < half; ++i) {
-    EZB_TRY(block(st, i, xc, skips[i], nullptr, nullptr, modr, mbs, Be, L));
+    EZB_TRY(block(st, i, xc, skips[i], nullptr, nullptr, modr, mbs, Be, L, fc));
     xc = skips[i];
+    fc.st_x = blk[i].st_out;
   }
   for (int i = 0; i < half; ++i) {  // zero-linears * conditioning_scale (controlnet.py:311-313)
-    EZB_TRY(ln(st, skips[i], D, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0, L, act, M));
+    const bf16* A = act;
+    if (fc.on) A = cat[i];          // plain bf16 cast of the block output, written by its MLP-out epilogue
+    else EZB_TRY(ln(st, skips[i], D, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0, L, act, M));
     EpiLinearParams e = epi();
     e.bias = blk[i].zero_b; e.out_scale = cscale; e.out_f32 = skips_out[i]; e.ld32 = D;
-    EZB_TRY(lin(st, act, D, blk[i].zero_w, M, D, e));
+    EZB_TRY(lin(st, A, D, blk[i].zero_w, M, D, e));
   }
   return EZB_OK;
 }

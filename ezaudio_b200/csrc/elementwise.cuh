@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(256) ln_mod_cast_kernel(const LnParams p) {
 // Register-resident variant for the hot shapes (single source, D = 128 * NCH): the row is read once, both moments come
 // from registers (two-pass formula, same numerics as above), 8-byte bf16 stores.  One warp per row, 4 rows per 128-thread block.
 template <int NCH>
-__global__ void __launch_bounds__(128) ln_mod_cast_reg_kernel(const LnParams p) {
+__global__ void __launch_bounds__(128, 8) ln_mod_cast_reg_kernel(const LnParams p) {  // <= 64 registers: 8 CTAs per SM, so M = 4000 rows are ONE wave (79 registers gave 6 CTAs per SM = 888 of the 1000 CTAs, i.e. a second, nearly empty wave)
   pdl_launch();
   pdl_wait();
   const int row = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
@@ -502,6 +502,41 @@ __global__ void __launch_bounds__(1024) cfg_ddim_kernel(const float* __restrict_
     float prev = c2 * x0 + c3 * eps;
     if (z) prev += c4 * z[i];
     x[i] = prev;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Tables of the folded LayerNorm (gemm.cuh, FoldIn / FoldOut), built once per schedule by ezb_dit_set_timesteps:
+//   G[t][k] = w[k] (1 + scale_t[k]),  C[t][k] = b[k] (1 + scale_t[k]) + shift_t[k]            (fold_gc_kernel; no modulation: G = w, C = b)
+//   U[t][n] = sum_k G[t][k] W[n][k],  V[t][n] = sum_k C[t][k] W[n][k] (+ bias[n])             (fold_uv_kernel; W = the PACKED bf16 weight the
+//   GEMM itself multiplies with, so U and V are in the GEMM's own column order and consistent with its operand rounding)
+__global__ void fold_gc_kernel(const float* __restrict__ w, const float* __restrict__ b, const float* __restrict__ shift, const float* __restrict__ scale,
+                               int ld_mod, float* __restrict__ G, float* __restrict__ Cc, int R, int D) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R * D) return;
+  const int r = i / D, k = i - r * D;
+  const float sc = scale ? scale[(size_t)r * ld_mod + k] : 0.f, sh = shift ? shift[(size_t)r * ld_mod + k] : 0.f;
+  G[i] = w[k] * (1.f + sc);
+  Cc[i] = b[k] * (1.f + sc) + sh;
+}
+__global__ void __launch_bounds__(256) fold_uv_kernel(const __nv_bfloat16* __restrict__ W, int ldw, const float* __restrict__ G, const float* __restrict__ Cc,
+                                                      const float* __restrict__ add_v, float* __restrict__ U, float* __restrict__ V, int N, int K, int R) {
+  const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (n >= N) return;
+  constexpr int MAXK = 72;  // K <= 2304 (the normalised width: D, or 2 D on the skip path)
+  float w[MAXK];
+#pragma unroll
+  for (int i = 0; i < MAXK; ++i) { const int k = lane + 32 * i; w[i] = k < K ? __bfloat162float(W[(size_t)n * ldw + k]) : 0.f; }
+  const float add = add_v ? add_v[n] : 0.f;
+  for (int r = 0; r < R; ++r) {
+    float su = 0.f, sv = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXK; ++i) {
+      const int k = lane + 32 * i;
+      if (k < K) { su = fmaf(w[i], G[(size_t)r * K + k], su); sv = fmaf(w[i], Cc[(size_t)r * K + k], sv); }
+    }
+    su = warp_sum(su); sv = warp_sum(sv);
+    if (lane == 0) { U[(size_t)r * N + n] = su; V[(size_t)r * N + n] = sv + add; }
   }
 }
 

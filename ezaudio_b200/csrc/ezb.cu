@@ -22,6 +22,7 @@ Device& device_ctx(int device) {
 }
 EpiLinearParams to_epi(const ezb_test_epilogue* e) {
   EpiLinearParams p;
+  memset(&p, 0, sizeof p);
   p.bias = e->bias; p.bias_mod = e->bias_mod; p.resid = e->resid; p.ldr = e->ldr; p.gate = e->gate;
   p.gate_bstride = e->gate_bstride; p.rows_per_batch = e->rows_per_batch; p.out_f32 = e->out_f32; p.ld32 = e->ld32;
   p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(e->out_bf16); p.ld16 = e->ld16; p.split_stride = e->split_stride;
@@ -61,6 +62,7 @@ __attribute__((visibility("default"))) int ezb_test_gemm(int device, const void*
       if (bn == 256) return gemm2<256, EpiLinear<256>>(dev, st, a, lda, w, ldw, M, N, K, p);
     } else {
       EpiGegluParams p;
+      memset(&p, 0, sizeof p);
       p.bias = e->bias; p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(e->out_bf16); p.ld16 = e->ld16; p.split_stride = e->split_stride;
       if (bn == 256) return gemm2<256, EpiGeglu<256>>(dev, st, a, lda, w, ldw, M, N, K, p);
     }
@@ -73,6 +75,7 @@ __attribute__((visibility("default"))) int ezb_test_gemm(int device, const void*
     if (bn == 256) return gemm<256, EpiLinear<256>>(dev, st, a, lda, w, ldw, M, N, K, p, cp);
   } else if (epi_kind == 1) {
     EpiGegluParams p;
+    memset(&p, 0, sizeof p);
     p.bias = e->bias; p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(e->out_bf16); p.ld16 = e->ld16; p.split_stride = e->split_stride;
     if (bn == 128) return gemm<128, EpiGeglu<128>>(dev, st, a, lda, w, ldw, M, N, K, p, cp);
     if (bn == 256) return gemm<256, EpiGeglu<256>>(dev, st, a, lda, w, ldw, M, N, K, p, cp);
@@ -260,6 +263,7 @@ EZB_API int ezb_set_option(const char* name, int value) {
   if (name && !strcmp(name, "pdl")) { opt_pdl() = value; return EZB_OK; }
   if (name && !strcmp(name, "swap_ab")) { opt_swap_ab() = value; return EZB_OK; }
   if (name && !strcmp(name, "qkv3")) { opt_qkv3() = value; return EZB_OK; }
+  if (name && !strcmp(name, "ln_fold")) { opt_fold() = value; return EZB_OK; }
   if (name && !strcmp(name, "skip")) { opt_skip() = value; return EZB_OK; }
   if (name && !strcmp(name, "swap_mc")) { opt_swap_mc() = value; return EZB_OK; }
   if (name && !strcmp(name, "attn_poly")) { opt_attn_poly() = value; return EZB_OK; }

@@ -40,6 +40,54 @@ struct GemmShape {
 
 enum { ACT_NONE = 0, ACT_SILU = 1, ACT_SNAKE = 2 };
 
+// ---------------------------------------------------------------------------------------------------------------
+// LayerNorm folded into the GEMMs on either side of it (fast mode; blocks.py:137,149,155 and modules.py:15-16):
+//     h = ((x - mu) * rstd) * g + c,   g = w (1 + scale), c = b (1 + scale) + shift        (LayerNorm affine + AdaLN modulate)
+//     h W^T = rstd * ( (x g) W^T  -  mu * u ) + v,      u[n] = sum_k g[k] W[n,k],  v[n] = sum_k c[k] W[n,k]
+// The GEMM that WRITES the residual stream x (FoldOut) also writes A = bf16(x * g) -- the operand of the GEMM that follows the
+// LayerNorm -- and per-row partial sums (sum x, sum x^2), one slot per 32-feature lane group: slot-major [slots][ld_st], fixed
+// summation order, so the result is deterministic.  The GEMM that FOLLOWS the LayerNorm (FoldIn) turns the partials into (mu, rstd)
+// per row and applies the per-row affine to its accumulator.  No LayerNorm pass, no extra launch; u, v come from per-timestep tables.
+struct FoldIn {
+  const float2* st0;   // partials of the row (or of the first half of a concatenated row); null: no fold
+  const float2* st1;   // second source (skip path: LayerNorm over [x | skip]) or null
+  int slots0, slots1, ld_st;
+  float inv_dim;       // 1 / (normalised width)
+  const float* u;      // [N] in this GEMM's (packed) output-column order
+  const float* v;
+};
+struct FoldOut {
+  float2* st;          // null: nothing to emit
+  int ld_st;
+  __nv_bfloat16* a0; int ld0; const float* g0;   // a0[token, f] = bf16(x * g0[f])  (g0 null: plain cast)
+  __nv_bfloat16* a1; int ld1; const float* g1;   // optional second consumer of the same x (null: none)
+};
+__device__ __forceinline__ void fold_row_stats(const FoldIn& f, int row, float& rstd, float& nmr) {
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll 4
+  for (int s = 0; s < f.slots0; ++s) { const float2 p = f.st0[(size_t)s * f.ld_st + row]; s1 += p.x; s2 += p.y; }
+#pragma unroll 4
+  for (int s = 0; s < f.slots1; ++s) { const float2 p = f.st1[(size_t)s * f.ld_st + row]; s1 += p.x; s2 += p.y; }
+  const float mean = s1 * f.inv_dim;
+  const float var = fmaxf(s2 * f.inv_dim - mean * mean, 0.f);
+  rstd = rsqrtf(var + 1e-5f);
+  nmr = -mean * rstd;
+}
+// x[j] (j = 0..31) per lane -> lane L ends with sum over the 32 lanes of x[L]: 31 shuffles instead of 32 x 5
+__device__ __forceinline__ float warp_transpose_sum(float (&x)[32], int lane) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < o; ++i) {
+      const float send = up ? x[i] : x[i + o];
+      const float keep = up ? x[i + o] : x[i];
+      x[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  return x[0];
+}
+
 // out_f32 receives the pre-activation value, out_bf16 the post-activation one (either may be null).
 struct EpiLinearParams {
   const float* bias;       // [N] or [bias_mod]
@@ -60,6 +108,8 @@ struct EpiLinearParams {
   float out_scale;         // v = (acc + bias) * out_scale (before residual); 0 is treated as 1
   int phase_cols;          // >0 (conv-transpose): bf16 column = (col / phase_cols) * phase_ld16 + col % phase_cols
   int phase_ld16;
+  FoldIn fin;              // swap-AB epilogue only: LayerNorm folded in / out (see above)
+  FoldOut fout;
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -241,6 +291,7 @@ struct EpiGegluParams {
   __nv_bfloat16* out_bf16;
   int ld16;
   int split_stride;
+  FoldIn fin;         // LayerNorm folded into this GEMM (fin.v already contains the bias)
 };
 __device__ __forceinline__ float rcp_approx(float x) {
   float r;
@@ -276,6 +327,9 @@ struct EpiGeglu {
   template <class Wait>
   static __device__ __forceinline__ void run(const Params& ep, float* st, uint32_t taddr_row, int row0, int nvalid, int n0, int N, int lane, int c_begin,
                                              int c_end, Wait wait) {
+    const bool fold = ep.fin.u != nullptr;
+    float rstd = 1.f, nmr = 0.f;
+    if (fold && lane < nvalid) fold_row_stats(ep.fin, row0 + lane, rstd, nmr);   // before the accumulator wait
     wait();
     // c_begin/c_end are expressed in accumulator columns of the whole tile: map them to output-feature ranges
     const int f_begin = c_begin / 2, f_end = c_end / 2;
@@ -310,6 +364,20 @@ struct EpiGeglu {
         tmem_ld_32x32(taddr_row + c + q4 * 32, h);
         tmem_ld_32x32(taddr_row + HALF + c + q4 * 32, g);
         tmem_ld_wait();
+        if (fold) {   // warp-uniform: h = rstd * acc - rstd * mu * u + (v + bias)
+          const float* bh = ep.fin.v + n0 + c + q4 * 32;
+          const float* bg = ep.fin.v + n0 + HALF + c + q4 * 32;
+          const float* uh = ep.fin.u + n0 + c + q4 * 32;
+          const float* ug = ep.fin.u + n0 + HALF + c + q4 * 32;
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            const float o0 = geglu_fast(fmaf(__uint_as_float(h[j]), rstd, fmaf(nmr, __ldg(uh + j), __ldg(bh + j))),
+                                        fmaf(__uint_as_float(g[j]), rstd, fmaf(nmr, __ldg(ug + j), __ldg(bg + j))));
+            const float o1 = geglu_fast(fmaf(__uint_as_float(h[j + 1]), rstd, fmaf(nmr, __ldg(uh + j + 1), __ldg(bh + j + 1))),
+                                        fmaf(__uint_as_float(g[j + 1]), rstd, fmaf(nmr, __ldg(ug + j + 1), __ldg(bg + j + 1))));
+            pk[q4 * 16 + j / 2] = pack_bf16(o0, o1);
+          }
+        } else {
         const float* bh = ep.bias + n0 + c + q4 * 32;
         const float* bg = ep.bias + n0 + HALF + c + q4 * 32;
 #pragma unroll
@@ -317,6 +385,7 @@ struct EpiGeglu {
           const float o0 = geglu_fast(__uint_as_float(h[j]) + __ldg(bh + j), __uint_as_float(g[j]) + __ldg(bg + j));
           const float o1 = geglu_fast(__uint_as_float(h[j + 1]) + __ldg(bh + j + 1), __uint_as_float(g[j + 1]) + __ldg(bg + j + 1));
           pk[q4 * 16 + j / 2] = pack_bf16(o0, o1);
+        }
         }
       }
       __syncwarp();
@@ -352,6 +421,13 @@ struct EpiLinearT {
     const int f = row0 + lane;                 // output feature of this thread
     const bool f_ok = lane < nvalid;
     const float bias = (ep.bias != nullptr && f_ok) ? ep.bias[f] : 0.f;
+    const bool fold_in = ep.fin.u != nullptr, fold_out = ep.fout.st != nullptr && nvalid > 0;
+    float uf = 0.f, vf = 0.f, ga = 1.f, gb = 1.f;
+    if (fold_in && f_ok) { uf = ep.fin.u[f]; vf = ep.fin.v[f]; }
+    if (fold_out && f_ok) {
+      if (ep.fout.g0 != nullptr) ga = ep.fout.g0[f];
+      if (ep.fout.a1 != nullptr && ep.fout.g1 != nullptr) gb = ep.fout.g1[f];
+    }
     bool waited = false;
 #pragma unroll 1
     for (int c = c_begin; c < c_end; c += 32) {
@@ -371,22 +447,57 @@ struct EpiLinearT {
         g0 = 1.0f - ep.gate[(size_t)b0i * ep.gate_bstride + f];
         if (btok < t0 + nt) g1 = 1.0f - ep.gate[(size_t)(b0i + 1) * ep.gate_bstride + f];
       }
+      float rs_l = 1.f, nm_l = 0.f;            // LayerNorm statistics of token t0 + lane (fold-in)
+      if (fold_in && lane < nt) fold_row_stats(ep.fin, t0 + lane, rs_l, nm_l);
       if (!waited) { wait(); waited = true; }
       uint32_t r[32];
       __syncwarp();
       tmem_ld_32x32(taddr_row + c, r);
       tmem_ld_wait();
+      float val[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float acc = __uint_as_float(r[j]);
+        if (fold_in) {                           // warp-uniform branch; the shuffles run on all lanes
+          const float rs = __shfl_sync(0xffffffffu, rs_l, j), nm = __shfl_sync(0xffffffffu, nm_l, j);
+          acc = fmaf(acc, rs, fmaf(nm, uf, vf));
+        }
+        float v = acc + bias;
+        float gj = (t0 + j >= btok) ? g1 : g0;
+        if (ep.gate != nullptr && ep.rows_per_batch < 32 && f_ok && j < nt) gj = 1.0f - ep.gate[(size_t)((t0 + j) / ep.rows_per_batch) * ep.gate_bstride + f];
+        if (ep.resid != nullptr) v = fmaf(gj, v, x[j]);
+        val[j] = (f_ok && j < nt) ? v : 0.f;
+      }
       if (f_ok) {
         float* o = ep.out_f32 + (size_t)t0 * ep.ld32 + f;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           if (j >= nt) break;
-          float v = __uint_as_float(r[j]) + bias;
-          float gj = (t0 + j >= btok) ? g1 : g0;
-          if (ep.gate != nullptr && ep.rows_per_batch < 32) gj = 1.0f - ep.gate[(size_t)((t0 + j) / ep.rows_per_batch) * ep.gate_bstride + f];
-          if (ep.resid != nullptr) v = fmaf(gj, v, x[j]);
-          o[(size_t)j * ep.ld32] = v;
+          o[(size_t)j * ep.ld32] = val[j];
         }
+        if (fold_out) {                          // operand(s) of the GEMM(s) behind the LayerNorm(s) that read this x
+          __nv_bfloat16* a = ep.fout.a0 + (size_t)t0 * ep.fout.ld0 + f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (j >= nt) break;
+            a[(size_t)j * ep.fout.ld0] = __float2bfloat16_rn(val[j] * ga);
+          }
+          if (ep.fout.a1 != nullptr) {
+            __nv_bfloat16* a2 = ep.fout.a1 + (size_t)t0 * ep.fout.ld1 + f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (j >= nt) break;
+              a2[(size_t)j * ep.fout.ld1] = __float2bfloat16_rn(val[j] * gb);
+            }
+          }
+        }
+      }
+      if (fold_out) {                            // per-token partial sums over this warp's 32 features -> slot row0 / 32
+        float sq[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) sq[j] = val[j] * val[j];
+        const float s1 = warp_transpose_sum(val, lane), s2 = warp_transpose_sum(sq, lane);
+        if (lane < nt) ep.fout.st[(size_t)(row0 >> 5) * ep.fout.ld_st + t0 + lane] = make_float2(s1, s2);
       }
     }
     if (!waited) wait();
@@ -581,6 +692,7 @@ struct EpiHeadsParams {
   int rope_kinds;              // bit k set: apply RoPE to kind k
   __nv_bfloat16* out[3];       // per kind: q rows, k rows, v^T
   int ld_qk, dvp, Lpad;
+  FoldIn fin;                  // LayerNorm (+ AdaLN modulate) of the block input folded into this projection
 };
 
 // HPT = 2: tile = two adjacent heads of the reference column order (N-tile 2*dh).  HPT = 3: the packed QKV layout -- the
@@ -595,9 +707,12 @@ struct EpiHeads {
   template <class Wait>
   static __device__ __forceinline__ void run(const Params& ep, float* st, uint32_t taddr_row, int row0, int nvalid, int n0, int N, int lane, int c_begin,
                                              int c_end, Wait wait) {
-    wait();
     const int row = row0 + lane;
     const bool row_ok = lane < nvalid;
+    const bool fold = ep.fin.u != nullptr;
+    float f_rstd = 1.f, f_nmr = 0.f;
+    if (fold && row_ok) fold_row_stats(ep.fin, row, f_rstd, f_nmr);   // issued before the accumulator wait
+    wait();
     const int b = row_ok ? row / ep.L : 0, l = row_ok ? row - b * ep.L : 0;
     {
       const int hh = c_begin / (BN / HPT);    // this warp's head inside the tile
@@ -621,6 +736,18 @@ struct EpiHeads {
       float v[DH];
 #pragma unroll
       for (int i = 0; i < DH; ++i) v[i] = __uint_as_float(r[i]);
+      if (fold) {  // warp-uniform: per-row affine of the folded LayerNorm; u, v are the same for every row (uniform 16-byte loads)
+        const float4* u4 = reinterpret_cast<const float4*>(ep.fin.u + n0 + hh * DH);
+        const float4* v4 = reinterpret_cast<const float4*>(ep.fin.v + n0 + hh * DH);
+#pragma unroll
+        for (int i = 0; i < DH / 4; ++i) {
+          const float4 uu = __ldg(u4 + i), vv = __ldg(v4 + i);
+          v[4 * i] = fmaf(v[4 * i], f_rstd, fmaf(f_nmr, uu.x, vv.x));
+          v[4 * i + 1] = fmaf(v[4 * i + 1], f_rstd, fmaf(f_nmr, uu.y, vv.y));
+          v[4 * i + 2] = fmaf(v[4 * i + 2], f_rstd, fmaf(f_nmr, uu.z, vv.z));
+          v[4 * i + 3] = fmaf(v[4 * i + 3], f_rstd, fmaf(f_nmr, uu.w, vv.w));
+        }
+      }
       const size_t bh = (size_t)b * ep.H + head;
       if (kind < 2) {
         float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};

@@ -186,6 +186,11 @@ inline int& opt_skip() {
   static int v = 0;
   return v;
 }
+// LayerNorm folded into the neighbouring GEMMs (gemm.cuh FoldIn / FoldOut); read when a handle is created
+inline int& opt_fold() {
+  static int v = 0;
+  return v;
+}
 inline unsigned long long& option_epoch() {
   static unsigned long long v = 0;
   return v;
