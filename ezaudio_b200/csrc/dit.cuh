@@ -667,28 +667,31 @@ struct Dit {
     const int M = Be * L;
     const float* m = modr + (size_t)i * 6 * D;  // shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp (blocks.py:132-133)
     const float2* st1 = fc.st_x;                // statistics of the tensor norm1 sees
+    bool fold1 = fc.on;                         // norm1 folded?
     if (skip) {  // out-blocks: x = skip_linear(LN_2D(cat[x, skip (+ controlnet skip)]))  (blocks.py:124-128, udit.py:345-348)
       const int si = half - 1 - (i - half - 1);
       EpiLinearParams e = epi();
       e.bias = w.b_skip; e.out_f32 = x_out; e.ld32 = D;
-      const bf16* A = act;
       if (fc.on && cskip == nullptr) {   // both halves of cat[si] and their statistics are in place
-        A = cat[si];
         e.fin = fold_in(fc.st_x, blk[si].st_out, 2 * D, w.us, w.vs);
-      } else {
+        e.fout = fold_out(w.st_skip, act, D, w.g1 + (size_t)fc.t * D);
+        st1 = w.st_skip;
+        EZB_TRY(lin(st, cat[si], 2 * D, w.skip, M, D, e));
+      } else {  // ControlNet skips are added to the skip half before the norm: LayerNorm kernels for skip_norm and norm1 of this block
+        // (`act` is this GEMM's own operand here, so its epilogue cannot also write the norm1 operand into it)
         EZB_TRY(ln(st, x_in, D, skip, cskip, D, w.snw, w.snb, nullptr, nullptr, 0, L, act, M));
+        EZB_TRY(lin(st, act, 2 * D, w.skip, M, D, e));
+        fold1 = false;
       }
-      if (fc.on) { e.fout = fold_out(w.st_skip, act, D, w.g1 + (size_t)fc.t * D); st1 = w.st_skip; }
-      EZB_TRY(lin(st, A, 2 * D, w.skip, M, D, e));
       x_in = x_out;
     }
     // --- self-attention (blocks.py:137-141)
-    if (!fc.on) EZB_TRY(ln(st, x_in, D, nullptr, nullptr, 0, w.n1w, w.n1b, m + 0 * D, m + 1 * D, mbs, L, act, M));
+    if (!fold1) EZB_TRY(ln(st, x_in, D, nullptr, nullptr, 0, w.n1w, w.n1b, m + 0 * D, m + 1 * D, mbs, L, act, M));
     if (fused_heads) {
       const int kinds[3] = {0, 1, 2};
       const int Lp = (L + 7) / 8 * 8;
       FoldIn f1 = fold_in(st1, nullptr, D, w.u1 + (size_t)fc.t * n_qkv, w.v1 + (size_t)fc.t * n_qkv);
-      EZB_TRY(lin_heads(st, act, w.qkv, M, 3 * D, kinds, w.h_nq, w.h_nk, true, L, q16, k16, vt16, Lp, fc.on ? &f1 : nullptr));
+      EZB_TRY(lin_heads(st, act, w.qkv, M, 3 * D, kinds, w.h_nq, w.h_nk, true, L, q16, k16, vt16, Lp, fold1 ? &f1 : nullptr));
       EZB_TRY(attention(st, q32, k32, v32, q16, k16, vt16, nullptr, Be, L, L, Lp));
     } else {
       EZB_TRY(lin_to_qkv(st, act, D, w.qkv, M, 3 * D));

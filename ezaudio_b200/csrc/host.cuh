@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -188,7 +189,7 @@ inline int& opt_skip() {
 }
 // LayerNorm folded into the neighbouring GEMMs (gemm.cuh FoldIn / FoldOut); read when a handle is created
 inline int& opt_fold() {
-  static int v = 0;
+  static int v = [] { const char* e = getenv("EZB_LN_FOLD"); return e ? atoi(e) : 0; }();   // environment override for A/B runs of whole programs
   return v;
 }
 inline unsigned long long& option_epoch() {
