@@ -8,6 +8,7 @@
 
 #include "attention_simt.cuh"
 #include "attention_tc4.cuh"
+#include "attention_tc5.cuh"
 #include "host.cuh"
 
 namespace ezb {
@@ -159,7 +160,9 @@ struct Dit {
       return fail(EZB_ERR_UNSUPPORTED, "unsupported dims: D %d dh %d inner %d ctx %d depth %d", D, dh, inner, d.context_dim, d.depth);
     if (d.max_batch < 1 || d.max_batch > 256 || d.max_len < 1 || d.max_ctx_len < 1 || d.max_timesteps < 1) return fail(EZB_ERR_ARG, "workspace bounds");
     Kp = (2 * C + 1 + KP_PATCH_ALIGN - 1) / KP_PATCH_ALIGN * KP_PATCH_ALIGN;
-    DHP = (dh + 63) / 64 * 64;
+    // q / k row pitch: dh = 72 rows are 80 elements (160 bytes: 64 columns behind a SWIZZLE_128B box + a 16-column SWIZZLE_32B tail box, TMA only
+    // needs 16-byte strides); the round-1 pitch of 128 moved 1.56x the algorithmic bytes (ncu dram__bytes_read 43.2 MB vs 27.6 MB)
+    DHP = dh == 72 ? (opt_dhp80() ? 80 : 128) : (dh + 63) / 64 * 64;
     DVP = (dh + 15) / 16 * 16;
     use_tc_attention = (d.precision == 0);
     blk.resize(nblk);
@@ -552,6 +555,7 @@ struct Dit {
       EZB_CUDA(cudaGetLastError());
       return EZB_OK;
     }
+    if (opt_attn5()) return attention_tc5(*dev, st, q16_, k16_, vt16_, mask, attn_out, B, H, Lq, Lk, Lkpad, dh, DHP, DVP, scale);
     return attention_tc4(*dev, st, q16_, k16_, vt16_, mask, attn_out, B, H, Lq, Lk, Lkpad, dh, DHP, DVP, scale);
   }
 

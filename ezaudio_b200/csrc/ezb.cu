@@ -249,7 +249,13 @@ EZB_API int ezb_test_attention(int device, const void* q, const void* k, const v
     EZB_CUDA(cudaGetLastError());
     return EZB_OK;
   }
-  const int dhp = (dh + 63) / 64 * 64, dvp = (dh + 15) / 16 * 16, lkpad = (Lk + 7) / 8 * 8;
+  // impl 1 / 5: q, k rows of `dhp` elements: 64-multiple (round-1 layout) or, with impl >= 100 (impl - 100 = kernel), 80 for dh = 72
+  int dhp = (dh + 63) / 64 * 64;
+  if (impl >= 100) { impl -= 100; if (dh == 72) dhp = 80; }
+  const int dvp = (dh + 15) / 16 * 16, lkpad = (Lk + 7) / 8 * 8;
+  if (impl == 5 || (impl == 1 && opt_attn5()))
+    return attention_tc5(device_ctx(device), ST(stream), reinterpret_cast<const __nv_bfloat16*>(q), reinterpret_cast<const __nv_bfloat16*>(k),
+                         reinterpret_cast<const __nv_bfloat16*>(v), key_mask, reinterpret_cast<__nv_bfloat16*>(out), B, H, Lq, Lk, lkpad, dh, dhp, dvp, scale);
   return attention_tc4(device_ctx(device), ST(stream), reinterpret_cast<const __nv_bfloat16*>(q), reinterpret_cast<const __nv_bfloat16*>(k),
                        reinterpret_cast<const __nv_bfloat16*>(v), key_mask, reinterpret_cast<__nv_bfloat16*>(out), B, H, Lq, Lk, lkpad, dh, dhp, dvp, scale);
 }
@@ -263,6 +269,8 @@ EZB_API int ezb_set_option(const char* name, int value) {
   if (name && !strcmp(name, "pdl")) { opt_pdl() = value; return EZB_OK; }
   if (name && !strcmp(name, "swap_ab")) { opt_swap_ab() = value; return EZB_OK; }
   if (name && !strcmp(name, "qkv3")) { opt_qkv3() = value; return EZB_OK; }
+  if (name && !strcmp(name, "attn5")) { opt_attn5() = value; return EZB_OK; }
+  if (name && !strcmp(name, "dhp80")) { opt_dhp80() = value; return EZB_OK; }
   if (name && !strcmp(name, "ln_fold")) { opt_fold() = value; return EZB_OK; }
   if (name && !strcmp(name, "skip")) { opt_skip() = value; return EZB_OK; }
   if (name && !strcmp(name, "swap_mc")) { opt_swap_mc() = value; return EZB_OK; }

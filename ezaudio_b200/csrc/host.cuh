@@ -187,6 +187,10 @@ inline int& opt_skip() {
   static int v = 0;
   return v;
 }
+inline int& opt_dhp80() {
+  static int v = [] { const char* e = getenv("EZB_DHP80"); return e ? atoi(e) : 0; }();
+  return v;
+}
 // LayerNorm folded into the neighbouring GEMMs (gemm.cuh FoldIn / FoldOut); read when a handle is created
 inline int& opt_fold() {
   static int v = [] { const char* e = getenv("EZB_LN_FOLD"); return e ? atoi(e) : 0; }();   // environment override for A/B runs of whole programs

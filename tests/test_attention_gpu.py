@@ -17,7 +17,9 @@ def _ref(q, k, v, mask):
     return o.permute(0, 2, 1, 3).reshape(q.shape[0], q.shape[2], -1)
 
 
-@pytest.mark.parametrize("impl", [0, 1])  # 0 = fp32 CUDA-core kernel (parity mode), 1 = tcgen05 two-tile ping-pong kernel (attention_tc4.cuh)
+# 0 = fp32 CUDA-core kernel (parity mode); 1 = tcgen05 two-tile ping-pong kernel (attention_tc4.cuh); 5 = the same with two threads per query row
+# (attention_tc5.cuh); +100 = q / k rows of 80 elements for dh = 72 (160-byte pitch) instead of 128
+@pytest.mark.parametrize("impl", [0, 1, 5, 101, 105])
 @pytest.mark.parametrize("B,H,Lq,Lk,dh,masked", [(2, 4, 500, 500, 72, False), (2, 3, 256, 256, 64, False), (3, 2, 500, 100, 72, True),
                                                  (2, 2, 40, 12, 72, True), (1, 2, 130, 130, 64, False), (1, 16, 1500, 1500, 72, False),
                                                  (2, 2, 37, 100, 64, True), (8, 16, 500, 500, 72, False), (2, 5, 700, 700, 72, "grow")])
@@ -42,6 +44,8 @@ def test_attention(impl, B, H, Lq, Lk, dh, masked):
         ref = _ref(q, k, v, mask)
     else:
         dhp, dvp, lkp = (dh + 63) // 64 * 64, (dh + 15) // 16 * 16, (Lk + 7) // 8 * 8
+        if impl >= 100 and dh == 72:
+            dhp = 80
         qb = torch.zeros(B * H, Lq, dhp, device="cuda", dtype=torch.bfloat16)
         kb = torch.zeros(B * H, Lk, dhp, device="cuda", dtype=torch.bfloat16)
         vt = torch.zeros(B * H, dvp, lkp, device="cuda", dtype=torch.bfloat16)
