@@ -4,11 +4,12 @@ set -x
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -q -s -k "not multicast" > gpurun_out/c2_pytest.log 2>&1; echo "pytest exit $?" >> gpurun_out/c2_pytest.log
 tail -15 gpurun_out/c2_pytest.log
-for o in "" "--opt ln_fold=1"; do
+timeout 300 python profiles/attn_bench.py > gpurun_out/c2_attn_bench.txt 2>&1; cat gpurun_out/c2_attn_bench.txt
+for o in "" "--opt ln_fold=1" "--opt attn5=1" "--opt dhp80=1" "--opt ln_fold=1 --opt attn5=1 --opt dhp80=1"; do
   timeout 300 python profiles/profile_step.py --steps 1 --vae 0 $o 2>&1 | grep "ms per" >> gpurun_out/c2_ab.txt
 done
 cat gpurun_out/c2_ab.txt
-EZB_LN_FOLD=1 timeout 900 python bench.py --no-cpu-baseline > gpurun_out/c2_bench_fold.json 2> gpurun_out/c2_bench_fold.err; echo "bench exit $?"
+EZB_LN_FOLD=1 EZB_ATTN5=1 EZB_DHP80=1 timeout 900 python bench.py --no-cpu-baseline > gpurun_out/c2_bench_fold.json 2> gpurun_out/c2_bench_fold.err; echo "bench exit $?"
 cut -c1-400 gpurun_out/c2_bench_fold.json
 timeout 900 ncu --profile-from-start off --set full --clock-control none -k regex:gemm -c 9 -o gpurun_out/c2_full_gemm python profiles/profile_step.py --steps 1 --vae 0 --opt ln_fold=1 > gpurun_out/c2_ncu1.log 2>&1
 timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --cache-control none --csv --log-file gpurun_out/c2_launches_warm_fold.csv python profiles/profile_step.py --steps 1 --opt ln_fold=1 > gpurun_out/c2_ncu2.log 2>&1
