@@ -81,6 +81,7 @@ class _Handle:
             torch.cuda.current_stream().synchronize()
             _lib.check(L.ezb_dit_finalize_weights(self.h, st))
         self.loaded = True
+        self._ts, self._ctx_key = [], None   # tables derived from the previous weights are stale
 
     # ---- step-invariant precompute
     def set_context(self, context: torch.Tensor, context_mask: Optional[torch.Tensor]):
@@ -96,6 +97,8 @@ class _Handle:
 
     def set_timesteps(self, ts: Sequence[int]):
         ts = [int(t) for t in ts]
+        if ts == self._ts:   # the tables depend on the weights and the timestep values only: a repeated schedule (every job of a server) reuses them
+            return
         arr = (C.c_int64 * len(ts))(*ts)
         with torch.cuda.device(self.dev_index):
             _lib.check(_lib.lib().ezb_dit_set_timesteps(self.h, arr, len(ts), _lib.stream_ptr()))
