@@ -523,13 +523,15 @@ struct Dit {
     for (int i = 0; i < dh / 2 && i < 36; ++i) e.inv_freq[i] = h_inv_freq[i];
     e.out[0] = qo; e.out[1] = ko; e.out[2] = vto;
     e.ld_qk = DHP; e.dvp = DVP; e.Lpad = Lpad;
+    const bool direct = opt_heads_direct() != 0;
     if (qkv3_bn > 0 && N == 3 * D) {  // packed self-attention QKV: three heads per tile
-      if (dh == 72) return gemm2<224, EpiHeads<72, 3>>(*dev, st, A, D, W, D, M, H * 224, D, e);
-      return gemm2<192, EpiHeads<64, 3>>(*dev, st, A, D, W, D, M, H * 192, D, e);
+      if (dh == 72) return direct ? gemm2<224, EpiHeads<72, 3, true>>(*dev, st, A, D, W, D, M, H * 224, D, e)
+                                  : gemm2<224, EpiHeads<72, 3>>(*dev, st, A, D, W, D, M, H * 224, D, e);
+      return direct ? gemm2<192, EpiHeads<64, 3, true>>(*dev, st, A, D, W, D, M, H * 192, D, e) : gemm2<192, EpiHeads<64, 3>>(*dev, st, A, D, W, D, M, H * 192, D, e);
     }
     if (pair) {
-      if (dh == 72) return gemm2<144, EpiHeads<72>>(*dev, st, A, D, W, D, M, N, D, e);
-      return gemm2<128, EpiHeads<64>>(*dev, st, A, D, W, D, M, N, D, e);
+      if (dh == 72) return direct ? gemm2<144, EpiHeads<72, 2, true>>(*dev, st, A, D, W, D, M, N, D, e) : gemm2<144, EpiHeads<72>>(*dev, st, A, D, W, D, M, N, D, e);
+      return direct ? gemm2<128, EpiHeads<64, 2, true>>(*dev, st, A, D, W, D, M, N, D, e) : gemm2<128, EpiHeads<64>>(*dev, st, A, D, W, D, M, N, D, e);
     }
     if (dh == 72) return gemm<144, EpiHeads<72>>(*dev, st, A, D, W, D, M, N, D, e);
     return gemm<128, EpiHeads<64>>(*dev, st, A, D, W, D, M, N, D, e);

@@ -698,12 +698,15 @@ struct EpiHeadsParams {
 // HPT = 2: tile = two adjacent heads of the reference column order (N-tile 2*dh).  HPT = 3: the packed QKV layout -- the
 // 3H heads of [q | k | v] are regrouped three per tile (N-tile 224 for dh = 72: 3 x 72 + 8 zero columns; 192 for dh = 64), which
 // makes the tile wide enough for the tensor pipe (narrow tiles are operand-bandwidth bound) and keeps one head per warp.
-template <int DH, int HPT = 2>
+// DIRECT: every thread stores its own q / k row (dh bf16 = 128 or 144 contiguous bytes) with 16-byte stores instead of transposing it through a
+// per-warp 8 KB shared-memory tile.  The staging tiles of 12 epilogue warps take 96 KB, which leaves the 256 x 224 QKV tile only FOUR 30 KB
+// pipeline stages (the GEGLU kernel runs six); without them it gets seven.
+template <int DH, int HPT = 2, bool DIRECT = false>
 struct EpiHeads {
   using Params = EpiHeadsParams;
   static constexpr int BN = HPT == 3 ? (DH == 72 ? 224 : 3 * DH) : 2 * DH;
   static constexpr int EPI_WARPS = 4 * HPT;   // the HPT warps of a TMEM lane group take one head each
-  static constexpr int STAGE_FLOATS = EPI_STAGE_FLOATS;
+  static constexpr int STAGE_FLOATS = DIRECT ? 0 : EPI_STAGE_FLOATS;
   template <class Wait>
   static __device__ __forceinline__ void run(const Params& ep, float* st, uint32_t taddr_row, int row0, int nvalid, int n0, int N, int lane, int c_begin,
                                              int c_end, Wait wait) {
@@ -776,6 +779,16 @@ struct EpiHeads {
             v[i] = a * c.x - bq * c.y;
             v[i + DH / 2] = bq * c.x + a * c.y;
           }
+        }
+        if constexpr (DIRECT) {
+          if (row_ok) {
+            uint4* dst = reinterpret_cast<uint4*>(ep.out[kind] + (bh * ep.L + l) * (size_t)ep.ld_qk);
+#pragma unroll
+            for (int g = 0; g < DH / 8; ++g)
+              dst[g] = make_uint4(pack_bf16(v[8 * g], v[8 * g + 1]), pack_bf16(v[8 * g + 2], v[8 * g + 3]), pack_bf16(v[8 * g + 4], v[8 * g + 5]),
+                                  pack_bf16(v[8 * g + 6], v[8 * g + 7]));
+          }
+          return;
         }
         // bf16 pairs -> staging granules (4 bf16 each) -> coalesced row stores
 #pragma unroll

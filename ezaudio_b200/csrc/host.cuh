@@ -187,6 +187,10 @@ inline int& opt_skip() {
   static int v = 0;
   return v;
 }
+inline int& opt_heads_direct() {   // EpiHeads without shared-memory staging (deeper TMA pipeline), see gemm.cuh
+  static int v = [] { const char* e = getenv("EZB_HEADS_DIRECT"); return e ? atoi(e) : 0; }();
+  return v;
+}
 inline int& opt_dhp80() {
   static int v = [] { const char* e = getenv("EZB_DHP80"); return e ? atoi(e) : 0; }();
   return v;

@@ -130,3 +130,39 @@ def test_loop_graphs_and_short_clips_with_fold():
         e_ref, e_pair = float((res[1] - ref).abs().max()), float((res[1] - res[0]).abs().max())
         print(f"[parity] {steps}-step loop B{B} L{L} [bf16, LayerNorm folded]: vs oracle {e_ref:.3e}, vs unfolded {e_pair:.3e}")
         assert e_ref < 0.25 and e_pair < 0.25
+
+
+DEFAULTS = {"ln_fold": FOLD_DEFAULT, "attn5": 0, "dhp80": 0, "heads_direct": 0}
+
+
+@contextlib.contextmanager
+def options(**kw):
+    from ezaudio_b200 import _lib
+    L = _lib.lib()
+    for k, v in kw.items():
+        _lib.check(L.ezb_set_option(k.encode(), int(v)))
+    try:
+        yield
+    finally:
+        for k in kw:
+            _lib.check(L.ezb_set_option(k.encode(), DEFAULTS[k]))
+
+
+@pytest.mark.parametrize("opts", [dict(heads_direct=1), dict(dhp80=1), dict(attn5=1), dict(attn5=1, dhp80=1, heads_direct=1, ln_fold=1)],
+                         ids=["heads_direct", "dhp80", "attn5", "all"])
+@pytest.mark.parametrize("name", ["dit_tiny72", "dit_tiny64", "dit_XL", "dit_tiny72_inpaint"])
+def test_fast_path_options_keep_parity(name, opts):
+    """Every fast-path variant behind a runtime switch (q/k epilogue without smem staging, 80-element q/k rows, attention v5, folded LayerNorm)
+    holds the fast mode's tolerance against the reference goldens, alone and all together."""
+    from ezaudio_b200.dit import MaskDiT
+    cfg, sd, inp, g = helpers.dit_case_inputs(name)
+    B, _, L = inp["x"].shape
+    with options(**opts):
+        m = MaskDiT(precision="bf16", max_batch=B, max_len=L, max_ctx_len=inp["ctx"].shape[1], max_timesteps=8, **cfg).load_state_dict(sd)
+        gt = None if inp["gt"] is None else inp["gt"].cuda()
+        gm = None if inp["gt_mask"] is None else inp["gt_mask"].cuda()
+        out, _ = m(inp["x"].cuda(), inp["t"], inp["ctx"].cuda(), context_mask=inp["mask"].cuda(), gt=gt, mae_mask_infer=gm)
+        torch.cuda.synchronize()
+    err = (out.cpu() - torch.from_numpy(g["out"])).abs()
+    print(f"[parity] {name} [bf16, {opts}]: max-abs {float(err.max()):.3e} mean-abs {float(err.mean()):.3e}")
+    assert float(err.max()) < 6e-2 and float(err.mean()) < 1.2e-2
