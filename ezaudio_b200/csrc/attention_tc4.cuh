@@ -34,6 +34,7 @@ struct Attn4Params {
   int H, Lq, Lk, dvp;
   int n_qt, n_items;
   float scale_log2;         // (1/sqrt(dh)) * log2(e)
+  int dbg;                  // profiling only (option "attn_dbg", results are garbage): 1 no exp2, 2 no S load, 4 no P store, 8 no P V MMAs, 16 no S MMAs
 };
 
 // 2^x on the FMA pipe (Cody-Waite split + degree-3 minimax polynomial on [-0.5, 0.5], max relative error 7.8e-5 -- far below the bf16
@@ -151,10 +152,12 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
         mbar_wait(&k_full[st], (kc / A4_STAGES) & 1);
         tc_fence_after();
         const uint64_t qd = umma_desc_sw128(smem_u32(sQ + g * SM::Q_BYTES)), kd = umma_desc_sw128(smem_u32(sK + st * SM::K_BYTES));
+        if (!(p.dbg & 16)) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma_bf16(tmem0 + g * 128, qd + 2 * k, kd + 2 * k, idesc_s, k != 0);
         if (HAS_TAIL)
           umma_bf16(tmem0 + g * 128, umma_desc_sw32(smem_u32(sQ + g * SM::Q_BYTES + 16384)), umma_desc_sw32(smem_u32(sK + st * SM::K_BYTES + 16384)), idesc_s, 1);
+        }
         umma_commit(&k_empty[st]);
         umma_commit(&s_full[g]);
         if (j == n_kv - 1) umma_commit(&q_empty[g]);
@@ -166,7 +169,7 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
         const int st = vc % A4_STAGES;
         mbar_wait(&v_full[st], (vc / A4_STAGES) & 1);
         tc_fence_after();
-        for (int hh = 0; hh < 2; ++hh) {
+        for (int hh = 0; hh < 2 && !(p.dbg & 8); ++hh) {
           const uint64_t vd = umma_desc_sw128(smem_u32(sV + st * VB + hh * (VB / 2)));
 #pragma unroll
           for (int k = 0; k < 4; ++k)
@@ -228,9 +231,14 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
       mbar_wait(&s_full[g], s & 1);
       tc_fence_after();
       uint32_t sr[128];
+      if (p.dbg & 2) {
+#pragma unroll
+        for (int q = 0; q < 128; ++q) sr[q] = 0;
+      } else {
 #pragma unroll
       for (int q = 0; q < 4; ++q) tmem_ld_32x32(tS + q * 32, sr + q * 32);
       tmem_ld_wait();
+      }
       const int kbase = j * 128;
       const bool full = (p.key_mask == nullptr) && (kbase + 128 <= p.Lk);
       if (!full) {  // one validity bit per key column, identical for every row: 4 words built with warp ballots
@@ -270,6 +278,14 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
       const float mb = (m_ref == -INFINITY) ? 0.f : m_ref * p.scale_log2;  // fully masked so far: exp2(-inf) = 0
       float sum4[4] = {0.f, 0.f, 0.f, 0.f};
       uint32_t pk[64];
+      if (p.dbg & 1) {
+#pragma unroll
+        for (int c = 0; c < 128; c += 2) {
+          const float p0 = fmaf(__uint_as_float(sr[c]), p.scale_log2, -mb), p1 = fmaf(__uint_as_float(sr[c + 1]), p.scale_log2, -mb);
+          sum4[(c >> 1) & 3] += p0 + p1;
+          pk[c >> 1] = pack_bf16(p0, p1);
+        }
+      } else {
 #pragma unroll
       for (int c = 0; c < 128; c += 2) {
         const float p0 = ex2_approx(fmaf(__uint_as_float(sr[c]), p.scale_log2, -mb));
@@ -278,9 +294,12 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
         sum4[(c >> 1) & 3] += p0 + p1;
         pk[c >> 1] = pack_bf16(p0, p1);
       }
+      }
       l_run += (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
+      if (!(p.dbg & 4)) {
       tmem_st_32x32(tS, pk);
       tmem_st_32x32(tS + 32, pk + 32);
+      }
       if (s > 0 && j == 0) {  // retire the previous item while this unit's S / P hand-off is in flight: its last P V wrote the O that this
         mbar_wait(&o_full[g], (s - 1) & 1);   // unit's P V (accumulate = 0, issued after our arrive) will overwrite
         tc_fence_after();
@@ -338,6 +357,7 @@ inline int attention_tc4(Device& dev, cudaStream_t st, const __nv_bfloat16* q, c
   p.n_qt = (Lq + 127) / 128;
   p.n_items = p.n_qt * B * H;
   p.scale_log2 = scale * 1.4426950408889634f;
+  p.dbg = opt_attn_dbg();
   const int grid = p.n_items < dev.num_sms ? p.n_items : dev.num_sms;
   auto go = [&](auto kern, int smem) -> int {
     EZB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

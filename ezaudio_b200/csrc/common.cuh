@@ -249,10 +249,13 @@ __device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* m
       "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster), "r"(c0), "r"(c1)
       : "memory");
 }
-template <int COLS>
+template <int COLS, bool RELINQUISH = true>
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t* slot_in_smem) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_in_smem)), "n"(COLS) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  if (RELINQUISH) asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_inval(uint64_t* bar) {
+  asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 template <int COLS>
 __device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr) {

@@ -90,6 +90,7 @@ struct Dit {
   size_t st_ld = 0;
   float *gc_G = nullptr, *gc_C = nullptr, *gF = nullptr, *uF = nullptr, *vF = nullptr;
   float2* st_x0 = nullptr;
+  GridBarrier* grid_bar = nullptr;   // mlp_fused_kernel's self-resetting grid barrier
   std::vector<bf16*> cat;   // MaskDiT: per in-block [Mx, 2D] = [x of the paired out-block * snw[:D] | this block's output * snw[D:]]; ControlNet: [Mx, D] plain cast
   int geglu_bn = 128;     // N-tile of the GEGLU GEMM: packing group = geglu_bn / 2
   int qkv3_bn = 0;        // >0: self-attention QKV weight packed three heads per N-tile of this width (EpiHeads<DH,3>)
@@ -320,6 +321,7 @@ struct Dit {
         EZB_TRY(alloc(&blk[i].vtc16, (size_t)d.max_batch * H * DVP * Lcp));
       }
     }
+    EZB_TRY(alloc(&grid_bar, (size_t)1));
     // ---- folded LayerNorm: tables + operand / statistics buffers
     fold_cfg = opt_fold() != 0 && d.precision == 0 && pair && swap_ab && fused_heads && D <= 2304 / 2;
     if (fold_cfg) {
@@ -443,8 +445,12 @@ struct Dit {
     p.x = x; p.x2 = x2; p.x3 = x3; p.D1 = D1; p.D2 = D2; p.w = w; p.b = b; p.shift = shift; p.scale = scale; p.mod_bstride = mod_bstride;
     p.rows_per_batch = rows_per_batch; p.out = out; p.kmul = kmul; p.M = M;
     if (kmul == 1 && x2 == nullptr && w != nullptr && (D1 == 1152 || D1 == 1024)) {
-      if (D1 == 1152) return launch_k(ln_mod_cast_reg_kernel<9>, dim3((M + 3) / 4), dim3(128), 0, st, 1, p);
-      return launch_k(ln_mod_cast_reg_kernel<8>, dim3((M + 3) / 4), dim3(128), 0, st, 1, p);
+      if (opt_ln_variant() == 1) {
+        if (D1 == 1152) return launch_k(ln_mod_cast_reg_kernel<9, 8>, dim3((M + 3) / 4), dim3(128), 0, st, 1, p);
+        return launch_k(ln_mod_cast_reg_kernel<8, 8>, dim3((M + 3) / 4), dim3(128), 0, st, 1, p);
+      }
+      if (D1 == 1152) return launch_k(ln_mod_cast_reg_kernel<9, 1>, dim3((M + 3) / 4), dim3(128), 0, st, 1, p);
+      return launch_k(ln_mod_cast_reg_kernel<8, 1>, dim3((M + 3) / 4), dim3(128), 0, st, 1, p);
     }
     return launch_k(ln_mod_cast_kernel, dim3((M + 7) / 8), dim3(256), 0, st, 1, p);
   }
@@ -457,9 +463,13 @@ struct Dit {
     if ((opt_skip() & 8) && e.out_f32 != nullptr && e.out_bf16 == nullptr) return EZB_OK;
     // fp32-output layers (residual / gated-residual / plain): swap-AB 128 x 256 tiles -- one full wave for N = 1152 at M = 4000
     const bool folded = e.fin.u != nullptr || e.fout.st != nullptr;   // fold epilogues exist in the swap-AB kernel only
-    if (pair && swap_ab && kmul == 1 && e.out_bf16 == nullptr && e.out_f32 != nullptr && e.out_scale == 0.f && e.bias_mod == 0 && (M >= 512 || folded))
+    const bool short_clips = e.gate != nullptr && e.rows_per_batch < 32;  // per-token gate lookup lives in the generic (non swap-AB) epilogue
+    if (pair && swap_ab && kmul == 1 && e.out_bf16 == nullptr && e.out_f32 != nullptr && e.out_scale == 0.f && e.bias_mod == 0 && !short_clips &&
+        (M >= 512 || folded)) {
+      if (folded) return gemm_swapped<EpiLinearTF<256>>(*dev, st, A, K, W, K, M, N, K, e);
       return opt_swap_mc() ? gemm_swapped_mc<EpiLinearT<256>, 3>(*dev, st, A, K, W, K, M, N, K, e)
                            : gemm_swapped<EpiLinearT<256>>(*dev, st, A, K, W, K, M, N, K, e);
+    }
     if (folded) return fail(EZB_ERR_STATE, "folded LayerNorm epilogue requested on a GEMM that is not a swap-AB launch");
     if (pair) return gemm2<128, EpiLinear<128>>(*dev, st, A, kmul * K, W, kmul * K, M, N, kmul * K, e);
     return gemm<128, EpiLinear<128>>(*dev, st, A, kmul * K, W, kmul * K, M, N, kmul * K, e);
@@ -523,16 +533,19 @@ struct Dit {
     for (int i = 0; i < dh / 2 && i < 36; ++i) e.inv_freq[i] = h_inv_freq[i];
     e.out[0] = qo; e.out[1] = ko; e.out[2] = vto;
     e.ld_qk = DHP; e.dvp = DVP; e.Lpad = Lpad;
-    const bool direct = opt_heads_direct() != 0;
+    const bool direct = opt_heads_direct() != 0, fo = fin != nullptr;
+#define EZB_HEADS(BN_, DH_, HPT_, N_)                                                                                                          \
+  (fo ? (direct ? gemm2<BN_, EpiHeads<DH_, HPT_, true, true>>(*dev, st, A, D, W, D, M, N_, D, e) : gemm2<BN_, EpiHeads<DH_, HPT_, false, true>>(*dev, st, A, D, W, D, M, N_, D, e)) \
+      : (direct ? gemm2<BN_, EpiHeads<DH_, HPT_, true, false>>(*dev, st, A, D, W, D, M, N_, D, e) : gemm2<BN_, EpiHeads<DH_, HPT_, false, false>>(*dev, st, A, D, W, D, M, N_, D, e)))
     if (qkv3_bn > 0 && N == 3 * D) {  // packed self-attention QKV: three heads per tile
-      if (dh == 72) return direct ? gemm2<224, EpiHeads<72, 3, true>>(*dev, st, A, D, W, D, M, H * 224, D, e)
-                                  : gemm2<224, EpiHeads<72, 3>>(*dev, st, A, D, W, D, M, H * 224, D, e);
-      return direct ? gemm2<192, EpiHeads<64, 3, true>>(*dev, st, A, D, W, D, M, H * 192, D, e) : gemm2<192, EpiHeads<64, 3>>(*dev, st, A, D, W, D, M, H * 192, D, e);
+      if (dh == 72) return EZB_HEADS(224, 72, 3, H * 224);
+      return EZB_HEADS(192, 64, 3, H * 192);
     }
     if (pair) {
-      if (dh == 72) return direct ? gemm2<144, EpiHeads<72, 2, true>>(*dev, st, A, D, W, D, M, N, D, e) : gemm2<144, EpiHeads<72>>(*dev, st, A, D, W, D, M, N, D, e);
-      return direct ? gemm2<128, EpiHeads<64, 2, true>>(*dev, st, A, D, W, D, M, N, D, e) : gemm2<128, EpiHeads<64>>(*dev, st, A, D, W, D, M, N, D, e);
+      if (dh == 72) return EZB_HEADS(144, 72, 2, N);
+      return EZB_HEADS(128, 64, 2, N);
     }
+#undef EZB_HEADS
     if (dh == 72) return gemm<144, EpiHeads<72>>(*dev, st, A, D, W, D, M, N, D, e);
     return gemm<128, EpiHeads<64>>(*dev, st, A, D, W, D, M, N, D, e);
   }
@@ -742,12 +755,19 @@ struct Dit {
       memset(&g, 0, sizeof g);
       g.bias = w.b_mlp1; g.out_bf16 = mid; g.ld16 = kmul * inner; g.split_stride = kmul == 3 ? inner : 0;
       if (fc.on) g.fin = fold_in(w.st_b, nullptr, D, w.u3 + (size_t)fc.t * 2 * inner, w.v3 + (size_t)fc.t * 2 * inner);
-      if (opt_skip() & 16) {}
-      else if (geglu_bn == 256) EZB_TRY((gemm2<256, EpiGeglu<256>>(*dev, st, act, kmul * D, w.mlp1, kmul * D, M, 2 * inner, kmul * D, g)));
-      else EZB_TRY((gemm<128, EpiGeglu<128>>(*dev, st, act, kmul * D, w.mlp1, kmul * D, M, 2 * inner, kmul * D, g)));
       EpiLinearParams e = epi();
       e.bias = w.b_mlp2; e.resid = x_out; e.ldr = D; e.gate = m + 5 * D; e.gate_bstride = mbs; e.rows_per_batch = L; e.out_f32 = x_out; e.ld32 = D;
       if (fc.on) e.fout = block_output_fold(i, fc.t);
+      if (opt_mlp_fused() && geglu_bn == 256 && kmul == 1 && swap_ab && !(opt_skip() & 24) && L >= 32) {
+        // the whole MLP as one persistent launch (north_star: "MLP GEMM + act + GEMM as one persistent kernel")
+        if (fc.on) EZB_TRY((mlp_fused<EpiGeglu<256, true>, EpiLinearTF<256>>(*dev, st, act, w.mlp1, M, 2 * inner, D, g, mid, w.mlp2, D, inner, e, grid_bar)));
+        else EZB_TRY((mlp_fused<EpiGeglu<256>, EpiLinearT<256>>(*dev, st, act, w.mlp1, M, 2 * inner, D, g, mid, w.mlp2, D, inner, e, grid_bar)));
+        return EZB_OK;
+      }
+      if (opt_skip() & 16) {}
+      else if (geglu_bn == 256 && fc.on) EZB_TRY((gemm2<256, EpiGeglu<256, true>>(*dev, st, act, kmul * D, w.mlp1, kmul * D, M, 2 * inner, kmul * D, g)));
+      else if (geglu_bn == 256) EZB_TRY((gemm2<256, EpiGeglu<256>>(*dev, st, act, kmul * D, w.mlp1, kmul * D, M, 2 * inner, kmul * D, g)));
+      else EZB_TRY((gemm<128, EpiGeglu<128>>(*dev, st, act, kmul * D, w.mlp1, kmul * D, M, 2 * inner, kmul * D, g)));
       EZB_TRY(lin(st, mid, inner, w.mlp2, M, D, e));
     }
     return EZB_OK;
@@ -763,9 +783,9 @@ struct Dit {
     return lin(st, a_patch, Kp, w_patch, Be * L, D, e);
   }
   // fold mode for this call: tables valid for the schedule and one timestep for the whole batch
-  FoldCtx fold_ctx(int mbs, const float* modr) {
+  FoldCtx fold_ctx(int mbs, const float* modr, int L) {
     FoldCtx fc;
-    if (fold_cfg && fold_n > 0 && mbs == 0) {
+    if (fold_cfg && fold_n > 0 && mbs == 0 && L >= 32) {
       const int t = (int)((modr - mod) / ((size_t)nblk * 6 * D));
       if (t >= 0 && t < fold_n) { fc.on = true; fc.t = t; }
     }
@@ -787,7 +807,7 @@ struct Dit {
     const float *modr, *modf;
     int mbs, mbsf;
     EZB_TRY(select_mod(st, tidx, tall, Be, &modr, &modf, &mbs, &mbsf));
-    FoldCtx fc = fold_ctx(mbs, modr);
+    FoldCtx fc = fold_ctx(mbs, modr, L);
     EZB_TRY(embed(st, x, gt, gt_mask, nullptr, Be, L, fc));
     const float* xc = x0;
     fc.st_x = st_x0;
@@ -849,7 +869,7 @@ inline int Dit::controlnet_forward(const float* x, const float* gt, const uint8_
   EZB_TRY(conv(cs_t0, cs_c0_w, cs_c0_b, cs_t1, c0 + 1, c0, T, c0 + 1, T, 3, 1, 1, 1, 0));    // conv3 + SiLU (mask channel == 0)
   EZB_TRY(conv(cs_t1, cs_c1_w, cs_c1_b, cs_t2, c0 + 1, c0 + 1, T, c1, L, 3, 2, 1, 1, 0));    // conv3 stride 2 + SiLU
   EZB_TRY(conv(cs_t2, cs_out_w, cs_out_b, cond_emb, c1, c1, L, D, L, 1, 1, 0, 0, 1));        // conv_out -> (B,L,D)
-  FoldCtx fc = fold_ctx(mbs, modr);
+  FoldCtx fc = fold_ctx(mbs, modr, L);
   EZB_TRY(embed(st, x, gt, gt_mask, cond_emb, Be, L, fc));                                   // x = patch_embed(x) + condition
   const float* xc = x0;
   const int M = Be * L;

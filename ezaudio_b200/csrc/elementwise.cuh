@@ -100,8 +100,10 @@ __global__ void __launch_bounds__(256) ln_mod_cast_kernel(const LnParams p) {
 
 // Register-resident variant for the hot shapes (single source, D = 128 * NCH): the row is read once, both moments come
 // from registers (two-pass formula, same numerics as above), 8-byte bf16 stores.  One warp per row, 4 rows per 128-thread block.
-template <int NCH>
-__global__ void __launch_bounds__(128, 8) ln_mod_cast_reg_kernel(const LnParams p) {  // <= 64 registers: 8 CTAs per SM, so M = 4000 rows are ONE wave (79 registers gave 6 CTAs per SM = 888 of the 1000 CTAs, i.e. a second, nearly empty wave)
+// MINB = minimum CTAs per SM: 1 -> 79 registers, 6 CTAs of 4 rows per SM = 888 of the 1000 CTAs of an M = 4000 launch resident (a second, nearly
+// empty wave); 8 -> <= 64 registers, the whole launch is one wave.  Selected at run time (option "ln_variant") so both can be timed in situ.
+template <int NCH, int MINB>
+__global__ void __launch_bounds__(128, MINB) ln_mod_cast_reg_kernel(const LnParams p) {
   pdl_launch();
   pdl_wait();
   const int row = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;

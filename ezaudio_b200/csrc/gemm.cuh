@@ -318,7 +318,7 @@ __device__ __forceinline__ float geglu_fast(float h, float g) {
   return h * (0.5f * g) * (1.0f + erf_s);
 }
 
-template <int BN>
+template <int BN, bool FOLD = false>
 struct EpiGeglu {
   using Params = EpiGegluParams;
   static constexpr int HALF = BN / 2;
@@ -327,7 +327,7 @@ struct EpiGeglu {
   template <class Wait>
   static __device__ __forceinline__ void run(const Params& ep, float* st, uint32_t taddr_row, int row0, int nvalid, int n0, int N, int lane, int c_begin,
                                              int c_end, Wait wait) {
-    const bool fold = ep.fin.u != nullptr;
+    constexpr bool fold = FOLD;
     float rstd = 1.f, nmr = 0.f;
     if (fold && lane < nvalid) fold_row_stats(ep.fin, row0 + lane, rstd, nmr);   // before the accumulator wait
     wait();
@@ -421,6 +421,58 @@ struct EpiLinearT {
     const int f = row0 + lane;                 // output feature of this thread
     const bool f_ok = lane < nvalid;
     const float bias = (ep.bias != nullptr && f_ok) ? ep.bias[f] : 0.f;
+    bool waited = false;
+#pragma unroll 1
+    for (int c = c_begin; c < c_end; c += 32) {
+      const int t0 = n0 + c;                   // first token of this chunk
+      if (t0 >= N) break;                      // warp-uniform
+      const int nt = (N - t0) < 32 ? (N - t0) : 32;
+      float x[32];
+      if (ep.resid != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] = (f_ok && j < nt) ? ep.resid[(size_t)(t0 + j) * ep.ldr + f] : 0.f;
+      }
+      float g0 = 1.f, g1 = 1.f;
+      int btok = 0x7fffffff;                   // first token that belongs to the second batch item of this chunk
+      if (ep.gate != nullptr && f_ok) {
+        const int b0i = t0 / ep.rows_per_batch;
+        btok = (b0i + 1) * ep.rows_per_batch;
+        g0 = 1.0f - ep.gate[(size_t)b0i * ep.gate_bstride + f];
+        if (btok < t0 + nt) g1 = 1.0f - ep.gate[(size_t)(b0i + 1) * ep.gate_bstride + f];
+      }
+      if (!waited) { wait(); waited = true; }
+      uint32_t r[32];
+      __syncwarp();
+      tmem_ld_32x32(taddr_row + c, r);
+      tmem_ld_wait();
+      if (f_ok) {
+        float* o = ep.out_f32 + (size_t)t0 * ep.ld32 + f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (j >= nt) break;
+          float v = __uint_as_float(r[j]) + bias;
+          if (ep.resid != nullptr) v = fmaf((t0 + j >= btok) ? g1 : g0, v, x[j]);
+          o[(size_t)j * ep.ld32] = v;
+        }
+      }
+    }
+    if (!waited) wait();
+  }
+};
+
+// Fold-capable variant (LayerNorm folded in / out, see FoldIn / FoldOut).  Kept apart from EpiLinearT on purpose: the extra outputs and the
+// warp transposes cost this one-wave kernel ~19 us per launch (measured, profiles/r2), more than the LayerNorm pass they replace.
+template <int BN>
+struct EpiLinearTF {
+  using Params = EpiLinearParams;   // bias/gate indexed by feature, resid/out_f32 [token, feature]; bf16/act/split unsupported
+  static constexpr int EPI_WARPS = 8;
+  static constexpr int STAGE_FLOATS = 0;
+  template <class Wait>
+  static __device__ __forceinline__ void run(const Params& ep, float* st, uint32_t taddr_row, int row0, int nvalid, int n0, int N, int lane, int c_begin,
+                                             int c_end, Wait wait) {
+    const int f = row0 + lane;                 // output feature of this thread
+    const bool f_ok = lane < nvalid;
+    const float bias = (ep.bias != nullptr && f_ok) ? ep.bias[f] : 0.f;
     const bool fold_in = ep.fin.u != nullptr, fold_out = ep.fout.st != nullptr && nvalid > 0;
     float uf = 0.f, vf = 0.f, ga = 1.f, gb = 1.f;
     if (fold_in && f_ok) { uf = ep.fin.u[f]; vf = ep.fin.v[f]; }
@@ -464,7 +516,6 @@ struct EpiLinearT {
         }
         float v = acc + bias;
         float gj = (t0 + j >= btok) ? g1 : g0;
-        if (ep.gate != nullptr && ep.rows_per_batch < 32 && f_ok && j < nt) gj = 1.0f - ep.gate[(size_t)((t0 + j) / ep.rows_per_batch) * ep.gate_bstride + f];
         if (ep.resid != nullptr) v = fmaf(gj, v, x[j]);
         val[j] = (f_ok && j < nt) ? v : 0.f;
       }
@@ -528,16 +579,13 @@ struct GemmCfg {
 // sub-boxes j = r, r + MC, ... with .multicast::cluster, every CTA still expects the full A + B bytes on its own `full` barrier, and a
 // stage is free again only when all MC consumers have released it (`empty` counts MC multicast commits).
 template <int BN, class Epi, int MC = 1>
-__global__ void __launch_bounds__((GemmCfg<BN, Epi, false>::THREADS), 1)
-gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmShape g,
-                    const typename Epi::Params ep) {
+__device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmShape& g, const typename Epi::Params& ep, uint8_t* smem_raw) {
   static_assert(BN % 16 == 0 && BN >= 64 && BN <= 256, "BN");
   static_assert(MC >= 1 && MC <= 8 && (MC == 1 || BN % 32 == 0), "MC");
   constexpr uint16_t MC_MASK = static_cast<uint16_t>((1u << MC) - 1u);
   using SM = GemmCfg<BN, Epi, false>;
   constexpr int STAGES = SM::STAGES;
   constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-  extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment by pointer arithmetic on the __shared__ array (a round trip through uintptr_t loses the address space and
   // turns every staging access into a generic LD.E / ST.E)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -670,6 +718,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (MC > 1) cluster_sync_all();  // nobody leaves while a peer may still multicast into this CTA or arrive on its barriers
   if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
 }
+template <int BN, class Epi, int MC = 1>
+__global__ void __launch_bounds__((GemmCfg<BN, Epi, false>::THREADS), 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmShape g,
+                    const typename Epi::Params ep) {
+  extern __shared__ uint8_t smem_dyn[];
+  gemm_body<BN, Epi, MC>(tmA, tmB, g, ep, smem_dyn);
+}
 
 }  // namespace ezb
 
@@ -701,7 +756,7 @@ struct EpiHeadsParams {
 // DIRECT: every thread stores its own q / k row (dh bf16 = 128 or 144 contiguous bytes) with 16-byte stores instead of transposing it through a
 // per-warp 8 KB shared-memory tile.  The staging tiles of 12 epilogue warps take 96 KB, which leaves the 256 x 224 QKV tile only FOUR 30 KB
 // pipeline stages (the GEGLU kernel runs six); without them it gets seven.
-template <int DH, int HPT = 2, bool DIRECT = false>
+template <int DH, int HPT = 2, bool DIRECT = false, bool FOLD = false>
 struct EpiHeads {
   using Params = EpiHeadsParams;
   static constexpr int BN = HPT == 3 ? (DH == 72 ? 224 : 3 * DH) : 2 * DH;
@@ -712,7 +767,7 @@ struct EpiHeads {
                                              int c_end, Wait wait) {
     const int row = row0 + lane;
     const bool row_ok = lane < nvalid;
-    const bool fold = ep.fin.u != nullptr;
+    constexpr bool fold = FOLD;
     float f_rstd = 1.f, f_nmr = 0.f;
     if (fold && row_ok) fold_row_stats(ep.fin, row, f_rstd, f_nmr);   // issued before the accumulator wait
     wait();
@@ -825,14 +880,14 @@ namespace ezb {
 // 128 rows of A and rows [r*BN/2, (r+1)*BN/2) of the W tile; the leader's single MMA thread issues M=256 instructions that
 // read both CTAs' shared memory, so each SM pulls half the operand bytes per flop through L2 (the 128x128 single-CTA tile
 // is L2->smem bound at ~64 flop/B).  Accumulator rows 128r..128r+127 live in CTA r's TMEM; both CTAs run the epilogue.
-template <int BN, class Epi, int KSUB>
-__global__ void __launch_bounds__((GemmCfg<BN, Epi, true, KSUB>::THREADS), 1)
-gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmShape g, const typename Epi::Params ep) {
+// FIRST_PHASE: the body is followed by another GEMM phase in the same kernel (mlp_fused_kernel): keep the TMEM allocation permit and
+// invalidate the mbarriers so that the next phase may lay out its own in the same shared memory.
+template <int BN, class Epi, int KSUB, bool FIRST_PHASE = false>
+__device__ __forceinline__ void gemm2_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmShape& g, const typename Epi::Params& ep, uint8_t* smem_raw) {
   static_assert(BN % 16 == 0 && BN >= 64 && BN <= 256, "BN");
   using SM = GemmCfg<BN, Epi, true, KSUB>;
   constexpr int STAGES = SM::STAGES;
   constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-  extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment by pointer arithmetic on the __shared__ array (a round trip through uintptr_t loses the address space and
   // turns every staging access into a generic LD.E / ST.E)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -864,7 +919,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc_pair<TMEM_COLS>(tmem_slot);
+  if (warp == 1) tmem_alloc_pair<TMEM_COLS, !FIRST_PHASE>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();
@@ -965,6 +1020,57 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   __syncthreads();
   cluster_sync_all();
   if (warp == 1) tmem_dealloc_pair<TMEM_COLS>(tmem_base);
+  if (FIRST_PHASE) {
+    if (warp == 0 && lane == 0) {
+      for (int i = 0; i < STAGES; ++i) { mbar_inval(&full[i]); mbar_inval(&empty[i]); }
+      for (int i = 0; i < 2; ++i) { mbar_inval(&tfull[i]); mbar_inval(&tempty[i]); }
+    }
+    __syncthreads();
+  }
+}
+template <int BN, class Epi, int KSUB>
+__global__ void __launch_bounds__((GemmCfg<BN, Epi, true, KSUB>::THREADS), 1)
+gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmShape g, const typename Epi::Params ep) {
+  extern __shared__ uint8_t smem_dyn[];
+  gemm2_body<BN, Epi, KSUB>(tmA, tmB, g, ep, smem_dyn);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// The MLP of a DiT block (modules.py:263-277,366) as ONE persistent launch: phase 1 = the GEGLU projection (CTA-pair tiles, EpiGeglu), a
+// grid-wide barrier, phase 2 = the output projection with its gated-residual epilogue (swap-AB tiles, EpiLinearT, incl. the LayerNorm fold
+// outputs for the next block).  The grid is one CTA per SM (all co-resident), launched as clusters of two for phase 1.  Phase 2 reads the
+// bf16 intermediate that phase 1 wrote with ordinary stores through TMA, hence the generic->async proxy fence after the barrier.
+struct GridBarrier { unsigned int count; unsigned int gen; };
+__device__ __forceinline__ void grid_barrier(GridBarrier* b) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();   // this CTA's global writes (all threads, ordered by the barrier above) before the arrive
+    unsigned int gen;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(gen) : "l"(&b->gen) : "memory");
+    if (atomicAdd(&b->count, 1u) == gridDim.x - 1) {
+      b->count = 0;
+      __threadfence();
+      asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(&b->gen), "r"(gen + 1) : "memory");
+    } else {
+      unsigned int cur;
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(cur) : "l"(&b->gen) : "memory");
+      } while (cur == gen);
+    }
+  }
+  __syncthreads();
+  asm volatile("fence.proxy.async;" ::: "memory");
+}
+template <int BN1, class Epi1, class Epi2>
+__global__ void __launch_bounds__((GemmCfg<BN1, Epi1, true, 1>::THREADS), 1)
+mlp_fused_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1, const GemmShape g1, const typename Epi1::Params ep1,
+                 const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2, const GemmShape g2, const typename Epi2::Params ep2,
+                 GridBarrier* bar) {
+  static_assert(GemmCfg<BN1, Epi1, true, 1>::THREADS == GemmCfg<256, Epi2, false>::THREADS, "both phases use the same warp roles");
+  extern __shared__ uint8_t smem_dyn[];
+  gemm2_body<BN1, Epi1, 1, true>(tmA1, tmB1, g1, ep1, smem_dyn);
+  grid_barrier(bar);
+  gemm_body<256, Epi2, 1>(tmA2, tmB2, g2, ep2, smem_dyn);
 }
 
 }  // namespace ezb

@@ -191,6 +191,14 @@ inline int& opt_heads_direct() {   // EpiHeads without shared-memory staging (de
   static int v = [] { const char* e = getenv("EZB_HEADS_DIRECT"); return e ? atoi(e) : 0; }();
   return v;
 }
+inline int& opt_attn_dbg() {
+  static int v = 0;
+  return v;
+}
+inline int& opt_ln_variant() {
+  static int v = [] { const char* e = getenv("EZB_LN_VARIANT"); return e ? atoi(e) : 0; }();
+  return v;
+}
 inline int& opt_dhp80() {
   static int v = [] { const char* e = getenv("EZB_DHP80"); return e ? atoi(e) : 0; }();
   return v;
@@ -389,6 +397,41 @@ int gemm2(Device& dev, cudaStream_t st, const __nv_bfloat16* A, int lda, const _
   EZB_TRY(launch_k(kern, dim3(2 * pairs), dim3(GEMM_THREADS), smem, st, 2, *tA, *tB, g, ep));
   if (gp.on) EZB_CUDA(cudaEventRecord(e1, st));
   return EZB_OK;
+}
+
+inline int& opt_mlp_fused() {
+  static int v = [] { const char* e = getenv("EZB_MLP_FUSED"); return e ? atoi(e) : 0; }();
+  return v;
+}
+// One persistent launch for the MLP of a DiT block (gemm.cuh mlp_fused_kernel): GEGLU projection A1[M,K1] W1[N1,K1]^T (packed, BN1 = 256 pair
+// tiles) -> bf16 `mid` -> grid barrier -> output projection mid[M,K2] W2[N2,K2]^T as swap-AB tiles with the EpiLinearT epilogue.
+template <class Epi1, class Epi2>
+int mlp_fused(Device& dev, cudaStream_t st, const __nv_bfloat16* A1, const __nv_bfloat16* W1, int M, int N1, int K1, const typename Epi1::Params& ep1,
+              const __nv_bfloat16* mid, const __nv_bfloat16* W2, int N2, int K2, const typename Epi2::Params& ep2, GridBarrier* bar) {
+  constexpr int BN1 = 256, BN2 = 256;
+  if ((K1 % 8) || (K2 % 8) || (N1 % 8)) return fail(EZB_ERR_SHAPE, "mlp_fused: K / N must be multiples of 8");
+  GemmShape g1, g2;
+  memset(&g1, 0, sizeof g1);
+  memset(&g2, 0, sizeof g2);
+  g1.M = M; g1.N = N1;
+  g1.num_n_tiles = (N1 + BN1 - 1) / BN1; g1.num_m_tiles = (M + 2 * GEMM_BM - 1) / (2 * GEMM_BM); g1.num_k_blocks = (K1 + GEMM_BK - 1) / GEMM_BK;
+  g2.M = N2; g2.N = M;   // swap-AB: features on the accumulator rows
+  g2.num_m_tiles = (N2 + GEMM_BM - 1) / GEMM_BM; g2.num_n_tiles = (M + BN2 - 1) / BN2; g2.num_k_blocks = (K2 + GEMM_BK - 1) / GEMM_BK;
+  const CUtensorMap *tA1, *tB1, *tA2, *tB2;
+  EZB_TRY(dev.tmaps.get2d(A1, (uint64_t)K1, (uint64_t)M, (uint64_t)K1, GEMM_BM, &tA1));
+  EZB_TRY(dev.tmaps.get2d(W1, (uint64_t)K1, (uint64_t)N1, (uint64_t)K1, BN1 / 2, &tB1));
+  EZB_TRY(dev.tmaps.get2d(W2, (uint64_t)K2, (uint64_t)N2, (uint64_t)K2, GEMM_BM, &tA2));
+  EZB_TRY(dev.tmaps.get2d(mid, (uint64_t)K2, (uint64_t)M, (uint64_t)K2, BN2, &tB2));
+  auto kern = mlp_fused_kernel<BN1, Epi1, Epi2>;
+  constexpr int s1 = GemmCfg<BN1, Epi1, true, 1>::BYTES, s2 = GemmCfg<BN2, Epi2, false>::BYTES, smem = s1 > s2 ? s1 : s2;
+  constexpr int THREADS = GemmCfg<BN1, Epi1, true, 1>::THREADS;
+  static bool attr_set[16] = {};
+  if (!attr_set[dev.id & 15]) {
+    EZB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set[dev.id & 15] = true;
+  }
+  const int grid = dev.num_sms & ~1;   // one CTA per SM, whole pairs: every CTA is resident, so the grid barrier cannot dead-lock
+  return launch_k(kern, dim3(grid), dim3(THREADS), smem, st, 2, *tA1, *tB1, g1, ep1, *tA2, *tB2, g2, ep2, bar);
 }
 
 // A: [M, K] bf16 row-major (lda), W: [N, K] bf16 row-major (ldw).  K, lda, ldw multiples of 8.

@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(256) k_tmem(float* out, int iters, long long* 
                        : "r"(base + q * 32) : "memory");
         if (MODE == 0) {
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          acc += __uint_as_float(r[it & 127]);
+          acc += __uint_as_float(r[0] ^ r[31] ^ r[64] ^ r[127]);   // static indices: a dynamic index would push r[] to local memory
         }
       }
       if (MODE == 1) {
