@@ -10,6 +10,7 @@
 #include "attention_tc4.cuh"
 #include "attention_tc5.cuh"
 #include "host.cuh"
+#include "gemm_ln.cuh"
 
 namespace ezb {
 
@@ -438,28 +439,38 @@ struct Dit {
   }
 
   // ---------------------------------------------------------------- launch helpers
-  int ln(cudaStream_t st, const float* x, int D1, const float* x2, const float* x3, int D2, const float* w, const float* b, const float* shift,
-         const float* scale, int mod_bstride, int rows_per_batch, bf16* out, int M) {
-    if (opt_skip() & 1) return EZB_OK;
+  LnParams ln_params(const float* x, int D1, const float* x2, const float* x3, int D2, const float* w, const float* b, const float* shift, const float* scale,
+                     int mod_bstride, int rows_per_batch, bf16* out, int M) {
     LnParams p;
     p.x = x; p.x2 = x2; p.x3 = x3; p.D1 = D1; p.D2 = D2; p.w = w; p.b = b; p.shift = shift; p.scale = scale; p.mod_bstride = mod_bstride;
     p.rows_per_batch = rows_per_batch; p.out = out; p.kmul = kmul; p.M = M;
-    if (kmul == 1 && x2 == nullptr && w != nullptr && (D1 == 1152 || D1 == 1024)) {
+    return p;
+  }
+  int ln(cudaStream_t st, const LnParams& p) {
+    if (opt_skip() & 1) return EZB_OK;
+    const int M = p.M;
+    if (kmul == 1 && p.x2 == nullptr && p.w != nullptr && (p.D1 == 1152 || p.D1 == 1024)) {
       if (opt_ln_variant() == 1) {
-        if (D1 == 1152) return launch_k(ln_mod_cast_reg_kernel<9, 8>, dim3((M + 3) / 4), dim3(128), 0, st, 1, p);
+        if (p.D1 == 1152) return launch_k(ln_mod_cast_reg_kernel<9, 8>, dim3((M + 3) / 4), dim3(128), 0, st, 1, p);
         return launch_k(ln_mod_cast_reg_kernel<8, 8>, dim3((M + 3) / 4), dim3(128), 0, st, 1, p);
       }
-      if (D1 == 1152) return launch_k(ln_mod_cast_reg_kernel<9, 1>, dim3((M + 3) / 4), dim3(128), 0, st, 1, p);
+      if (p.D1 == 1152) return launch_k(ln_mod_cast_reg_kernel<9, 1>, dim3((M + 3) / 4), dim3(128), 0, st, 1, p);
       return launch_k(ln_mod_cast_reg_kernel<8, 1>, dim3((M + 3) / 4), dim3(128), 0, st, 1, p);
     }
     return launch_k(ln_mod_cast_kernel, dim3((M + 7) / 8), dim3(256), 0, st, 1, p);
+  }
+  int ln(cudaStream_t st, const float* x, int D1, const float* x2, const float* x3, int D2, const float* w, const float* b, const float* shift,
+         const float* scale, int mod_bstride, int rows_per_batch, bf16* out, int M) {
+    return ln(st, ln_params(x, D1, x2, x3, D2, w, b, shift, scale, mod_bstride, rows_per_batch, out, M));
   }
   EpiLinearParams epi() {
     EpiLinearParams e;
     memset(&e, 0, sizeof e);
     return e;
   }
-  int lin(cudaStream_t st, const bf16* A, int K, const bf16* W, int M, int N, const EpiLinearParams& e) {
+  // `tail`: the LayerNorm that reads this GEMM's fp32 output; when the GEMM is a one-wave swap-AB launch it runs as the tail phase of the same
+  // kernel (gemm_ln.cuh) and *tail_done is set, otherwise the caller launches it separately.
+  int lin(cudaStream_t st, const bf16* A, int K, const bf16* W, int M, int N, const EpiLinearParams& e, const LnParams* tail = nullptr, bool* tail_done = nullptr) {
     if ((opt_skip() & 8) && e.out_f32 != nullptr && e.out_bf16 == nullptr) return EZB_OK;
     // fp32-output layers (residual / gated-residual / plain): swap-AB 128 x 256 tiles -- one full wave for N = 1152 at M = 4000
     const bool folded = e.fin.u != nullptr || e.fout.st != nullptr;   // fold epilogues exist in the swap-AB kernel only
@@ -467,6 +478,8 @@ struct Dit {
     if (pair && swap_ab && kmul == 1 && e.out_bf16 == nullptr && e.out_f32 != nullptr && e.out_scale == 0.f && e.bias_mod == 0 && !short_clips &&
         (M >= 512 || folded)) {
       if (folded) return gemm_swapped<EpiLinearTF<256>>(*dev, st, A, K, W, K, M, N, K, e);
+      if (tail != nullptr && tail_done != nullptr && opt_ln_tail() && !(opt_skip() & 9))
+        return gemm_swapped_ln<EpiLinearT<256>>(*dev, st, A, K, W, K, M, N, K, e, *tail, grid_bar, tail_done);
       return opt_swap_mc() ? gemm_swapped_mc<EpiLinearT<256>, 3>(*dev, st, A, K, W, K, M, N, K, e)
                            : gemm_swapped<EpiLinearT<256>>(*dev, st, A, K, W, K, M, N, K, e);
     }
@@ -680,13 +693,16 @@ struct Dit {
     }
     return fold_out(w.st_out, act, D, gF + (size_t)t * D);   // last block: FinalBlock norm
   }
+  // LayerNorm tails (gemm_ln.cuh): `entry_ln_done` = the LayerNorm this block starts with (norm1, or skip_norm for an out-block) was already
+  // executed by the kernel that produced x_in; `next_ln` / `next_done` = the LayerNorm that reads this block's output, for its MLP-out GEMM.
   int block(cudaStream_t st, int i, const float* x_in, float* x_out, const float* skip, const float* cskip, const float* modr, int mbs, int Be, int L,
-            FoldCtx fc = FoldCtx()) {
+            FoldCtx fc = FoldCtx(), bool entry_ln_done = false, const LnParams* next_ln = nullptr, bool* next_done = nullptr) {
     BlockW& w = blk[i];
     const int M = Be * L;
     const float* m = modr + (size_t)i * 6 * D;  // shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp (blocks.py:132-133)
     const float2* st1 = fc.st_x;                // statistics of the tensor norm1 sees
     bool fold1 = fc.on;                         // norm1 folded?
+    bool ln2_done = false, ln3_done = false;
     if (skip) {  // out-blocks: x = skip_linear(LN_2D(cat[x, skip (+ controlnet skip)]))  (blocks.py:124-128, udit.py:345-348)
       const int si = half - 1 - (i - half - 1);
       EpiLinearParams e = epi();
@@ -698,14 +714,16 @@ struct Dit {
         EZB_TRY(lin(st, cat[si], 2 * D, w.skip, M, D, e));
       } else {  // ControlNet skips are added to the skip half before the norm: LayerNorm kernels for skip_norm and norm1 of this block
         // (`act` is this GEMM's own operand here, so its epilogue cannot also write the norm1 operand into it)
-        EZB_TRY(ln(st, x_in, D, skip, cskip, D, w.snw, w.snb, nullptr, nullptr, 0, L, act, M));
-        EZB_TRY(lin(st, act, 2 * D, w.skip, M, D, e));
+        if (!entry_ln_done) EZB_TRY(ln(st, x_in, D, skip, cskip, D, w.snw, w.snb, nullptr, nullptr, 0, L, act, M));
+        const LnParams p1 = ln_params(x_out, D, nullptr, nullptr, 0, w.n1w, w.n1b, m + 0 * D, m + 1 * D, mbs, L, act, M);
+        entry_ln_done = false;   // from here on: "norm1 done?"
+        EZB_TRY(lin(st, act, 2 * D, w.skip, M, D, e, &p1, &entry_ln_done));   // the tail runs behind a grid barrier: nobody reads `act` any more
         fold1 = false;
       }
       x_in = x_out;
     }
     // --- self-attention (blocks.py:137-141)
-    if (!fold1) EZB_TRY(ln(st, x_in, D, nullptr, nullptr, 0, w.n1w, w.n1b, m + 0 * D, m + 1 * D, mbs, L, act, M));
+    if (!fold1 && !entry_ln_done) EZB_TRY(ln(st, x_in, D, nullptr, nullptr, 0, w.n1w, w.n1b, m + 0 * D, m + 1 * D, mbs, L, act, M));
     if (fused_heads) {
       const int kinds[3] = {0, 1, 2};
       const int Lp = (L + 7) / 8 * 8;
@@ -725,10 +743,11 @@ struct Dit {
       EpiLinearParams e = epi();
       e.bias = w.b_proj; e.resid = x_in; e.ldr = D; e.gate = m + 2 * D; e.gate_bstride = mbs; e.rows_per_batch = L; e.out_f32 = x_out; e.ld32 = D;
       if (fc.on) e.fout = fold_out(w.st_a, act, D, w.n2w);   // norm2 has no modulation: g = its weight
-      EZB_TRY(lin(st, attn_out, D, w.proj, M, D, e));
+      const LnParams p2 = ln_params(x_out, D, nullptr, nullptr, 0, w.n2w, w.n2b, nullptr, nullptr, 0, L, act, M);
+      EZB_TRY(lin(st, attn_out, D, w.proj, M, D, e, fc.on ? nullptr : &p2, &ln2_done));
     }
     // --- cross-attention (blocks.py:147-151): no modulation, no gate
-    if (!fc.on) EZB_TRY(ln(st, x_out, D, nullptr, nullptr, 0, w.n2w, w.n2b, nullptr, nullptr, 0, L, act, M));
+    if (!fc.on && !ln2_done) EZB_TRY(ln(st, x_out, D, nullptr, nullptr, 0, w.n2w, w.n2b, nullptr, nullptr, 0, L, act, M));
     if (fused_heads) {
       const int kinds[1] = {0};
       FoldIn f2 = fold_in(w.st_a, nullptr, D, w.u2, w.v2);
@@ -746,10 +765,11 @@ struct Dit {
       EpiLinearParams e = epi();
       e.bias = w.b_cproj; e.resid = x_out; e.ldr = D; e.out_f32 = x_out; e.ld32 = D;
       if (fc.on) e.fout = fold_out(w.st_b, act, D, w.g3 + (size_t)fc.t * D);
-      EZB_TRY(lin(st, attn_out, D, w.cproj, M, D, e));
+      const LnParams p3 = ln_params(x_out, D, nullptr, nullptr, 0, w.n3w, w.n3b, m + 3 * D, m + 4 * D, mbs, L, act, M);
+      EZB_TRY(lin(st, attn_out, D, w.cproj, M, D, e, fc.on ? nullptr : &p3, &ln3_done));
     }
     // --- GEGLU MLP (blocks.py:155-156; modules.py:263-277,366)
-    if (!fc.on) EZB_TRY(ln(st, x_out, D, nullptr, nullptr, 0, w.n3w, w.n3b, m + 3 * D, m + 4 * D, mbs, L, act, M));
+    if (!fc.on && !ln3_done) EZB_TRY(ln(st, x_out, D, nullptr, nullptr, 0, w.n3w, w.n3b, m + 3 * D, m + 4 * D, mbs, L, act, M));
     {
       EpiGegluParams g;
       memset(&g, 0, sizeof g);
@@ -768,19 +788,20 @@ struct Dit {
       else if (geglu_bn == 256 && fc.on) EZB_TRY((gemm2<256, EpiGeglu<256, true>>(*dev, st, act, kmul * D, w.mlp1, kmul * D, M, 2 * inner, kmul * D, g)));
       else if (geglu_bn == 256) EZB_TRY((gemm2<256, EpiGeglu<256>>(*dev, st, act, kmul * D, w.mlp1, kmul * D, M, 2 * inner, kmul * D, g)));
       else EZB_TRY((gemm<128, EpiGeglu<128>>(*dev, st, act, kmul * D, w.mlp1, kmul * D, M, 2 * inner, kmul * D, g)));
-      EZB_TRY(lin(st, mid, inner, w.mlp2, M, D, e));
+      EZB_TRY(lin(st, mid, inner, w.mlp2, M, D, e, fc.on ? nullptr : next_ln, next_done));
     }
     return EZB_OK;
   }
 
-  int embed(cudaStream_t st, const float* x, const float* gt, const uint8_t* gt_mask, const float* resid, int Be, int L, const FoldCtx& fc = FoldCtx()) {
+  int embed(cudaStream_t st, const float* x, const float* gt, const uint8_t* gt_mask, const float* resid, int Be, int L, const FoldCtx& fc = FoldCtx(),
+            const LnParams* next_ln = nullptr, bool* next_done = nullptr) {
     dim3 grid((L + 31) / 32, (2 * C) / 32, Be), blockd(32, 8);
     if ((2 * C) % 32) return fail(EZB_ERR_UNSUPPORTED, "latent_chans must be a multiple of 16");
     EZB_TRY(launch_k(patch_pack_kernel, grid, blockd, 0, st, 1, x, gt, gt_mask, (const float*)mask_embed, a_patch, Be, C, L, Kp, kmul));
     EpiLinearParams e = epi();
     e.bias = b_patch; e.out_f32 = x0; e.ld32 = D; e.resid = resid; e.ldr = D;
     if (fc.on) e.fout = fold_out(st_x0, act, D, blk[0].g1 + (size_t)fc.t * D);
-    return lin(st, a_patch, Kp, w_patch, Be * L, D, e);
+    return lin(st, a_patch, Kp, w_patch, Be * L, D, e, fc.on ? nullptr : next_ln, next_done);
   }
   // fold mode for this call: tables valid for the schedule and one timestep for the whole batch
   FoldCtx fold_ctx(int mbs, const float* modr, int L) {
@@ -808,26 +829,49 @@ struct Dit {
     int mbs, mbsf;
     EZB_TRY(select_mod(st, tidx, tall, Be, &modr, &modf, &mbs, &mbsf));
     FoldCtx fc = fold_ctx(mbs, modr, L);
-    EZB_TRY(embed(st, x, gt, gt_mask, nullptr, Be, L, fc));
+    const int M = Be * L;
+    // the LayerNorm that opens block i, as parameters for the tail phase of the GEMM that produces its input x (gemm_ln.cuh)
+    auto entry_ln = [&](int i, const float* xin) -> LnParams {
+      if (i > half) {   // out-block: skip_norm over [x | skip (+ controlnet skip)]
+        const int si = half - 1 - (i - half - 1);
+        return ln_params(xin, D, skips[si], cskips ? cskips[si] : nullptr, D, blk[i].snw, blk[i].snb, nullptr, nullptr, 0, L, act, M);
+      }
+      const float* mi = modr + (size_t)i * 6 * D;
+      return ln_params(xin, D, nullptr, nullptr, 0, blk[i].n1w, blk[i].n1b, mi + 0 * D, mi + 1 * D, mbs, L, act, M);
+    };
+    bool done = false;
+    LnParams nl = entry_ln(0, x0);
+    EZB_TRY(embed(st, x, gt, gt_mask, nullptr, Be, L, fc, &nl, &done));
     const float* xc = x0;
     fc.st_x = st_x0;
     for (int i = 0; i < half; ++i) {
-      EZB_TRY(block(st, i, xc, skips[i], nullptr, nullptr, modr, mbs, Be, L, fc));
+      const bool entry = done;
+      done = false;
+      nl = entry_ln(i + 1, skips[i]);
+      EZB_TRY(block(st, i, xc, skips[i], nullptr, nullptr, modr, mbs, Be, L, fc, entry, &nl, &done));
       xc = skips[i];
       fc.st_x = blk[i].st_out;
     }
-    EZB_TRY(block(st, half, xc, xa, nullptr, nullptr, modr, mbs, Be, L, fc));
+    {
+      const bool entry = done;
+      done = false;
+      nl = entry_ln(half + 1, xa);
+      EZB_TRY(block(st, half, xc, xa, nullptr, nullptr, modr, mbs, Be, L, fc, entry, &nl, &done));
+    }
     xc = xa;
     fc.st_x = blk[half].st_out;
     for (int j = 0; j < half; ++j) {
       const int si = half - 1 - j;  // skips.pop()
-      EZB_TRY(block(st, half + 1 + j, xc, xb, skips[si], cskips ? cskips[si] : nullptr, modr, mbs, Be, L, fc));
+      const bool entry = done;
+      done = false;
+      if (j + 1 < half) nl = entry_ln(half + 2 + j, xb);
+      else nl = ln_params(xb, D, nullptr, nullptr, 0, fn_w, fn_b, modf, modf + D, mbsf, L, act, M);   // FinalBlock norm
+      EZB_TRY(block(st, half + 1 + j, xc, xb, skips[si], cskips ? cskips[si] : nullptr, modr, mbs, Be, L, fc, entry, &nl, &done));
       xc = xb;
       fc.st_x = blk[half + 1 + j].st_out;
     }
     // FinalBlock (blocks.py:199-211): shift, scale = time_ada_final.chunk(2)
-    const int M = Be * L;
-    if (!fc.on) EZB_TRY(ln(st, xc, D, nullptr, nullptr, 0, fn_w, fn_b, modf, modf + D, mbsf, L, act, M));
+    if (!fc.on && !done) EZB_TRY(ln(st, xc, D, nullptr, nullptr, 0, fn_w, fn_b, modf, modf + D, mbsf, L, act, M));
     EpiLinearParams e = epi();
     e.bias = b_final; e.out_f32 = ybuf; e.ld32 = C;
     if (fc.on) e.fin = fold_in(fc.st_x, nullptr, D, uF + (size_t)fc.t * C, vF + (size_t)fc.t * C);
@@ -870,12 +914,21 @@ inline int Dit::controlnet_forward(const float* x, const float* gt, const uint8_
   EZB_TRY(conv(cs_t1, cs_c1_w, cs_c1_b, cs_t2, c0 + 1, c0 + 1, T, c1, L, 3, 2, 1, 1, 0));    // conv3 stride 2 + SiLU
   EZB_TRY(conv(cs_t2, cs_out_w, cs_out_b, cond_emb, c1, c1, L, D, L, 1, 1, 0, 0, 1));        // conv_out -> (B,L,D)
   FoldCtx fc = fold_ctx(mbs, modr, L);
-  EZB_TRY(embed(st, x, gt, gt_mask, cond_emb, Be, L, fc));                                   // x = patch_embed(x) + condition
-  const float* xc = x0;
   const int M = Be * L;
+  auto entry_ln = [&](int i, const float* xin) -> LnParams {
+    const float* mi = modr + (size_t)i * 6 * D;
+    return ln_params(xin, D, nullptr, nullptr, 0, blk[i].n1w, blk[i].n1b, mi + 0 * D, mi + 1 * D, mbs, L, act, M);
+  };
+  bool done = false;
+  LnParams nl = entry_ln(0, x0);
+  EZB_TRY(embed(st, x, gt, gt_mask, cond_emb, Be, L, fc, &nl, &done));                       // x = patch_embed(x) + condition
+  const float* xc = x0;
   fc.st_x = st_x0;
   for (int i = 0; i < half; ++i) {
-    EZB_TRY(block(st, i, xc, skips[i], nullptr, nullptr, modr, mbs, Be, L, fc));
+    const bool entry = done;
+    done = false;
+    if (i + 1 < half) nl = entry_ln(i + 1, skips[i]);
+    EZB_TRY(block(st, i, xc, skips[i], nullptr, nullptr, modr, mbs, Be, L, fc, entry, i + 1 < half ? &nl : nullptr, &done));
     xc = skips[i];
     fc.st_x = blk[i].st_out;
   }

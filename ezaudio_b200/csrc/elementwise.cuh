@@ -37,34 +37,34 @@ struct LnParams {
   int M;
 };
 
-__global__ void __launch_bounds__(256) ln_mod_cast_kernel(const LnParams p) {
-  pdl_launch();
-  pdl_wait();
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= p.M) return;
+// x / x2 / x3 are read with ld.global.cg (L2 only): when the LayerNorm runs as the tail phase of the GEMM that produced x (gemm_ln.cuh), rows
+// written by other SMs moments ago must not be served from a stale L1 line; for the stand-alone kernels it makes no difference (streaming).
+__device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+
+__device__ __forceinline__ void ln_row_generic(const LnParams& p, int row, int lane) {
   const int D = p.D1 + p.D2;
-  const float* x = p.x + (size_t)warp * p.D1;
-  const float* x2 = p.x2 ? p.x2 + (size_t)warp * p.D2 : nullptr;
-  const float* x3 = p.x3 ? p.x3 + (size_t)warp * p.D2 : nullptr;
+  const float* x = p.x + (size_t)row * p.D1;
+  const float* x2 = p.x2 ? p.x2 + (size_t)row * p.D2 : nullptr;
+  const float* x3 = p.x3 ? p.x3 + (size_t)row * p.D2 : nullptr;
   float s = 0.f;
   for (int c = lane * 4; c < p.D1; c += 128) {
-    const float4 v = *reinterpret_cast<const float4*>(x + c);
+    const float4 v = ldcg4(x + c);
     s += v.x + v.y + v.z + v.w;
   }
   for (int c = lane * 4; c < p.D2; c += 128) {
-    float4 v = *reinterpret_cast<const float4*>(x2 + c);
-    if (x3) { const float4 u = *reinterpret_cast<const float4*>(x3 + c); v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w; }
+    float4 v = ldcg4(x2 + c);
+    if (x3) { const float4 u = ldcg4(x3 + c); v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w; }
     s += v.x + v.y + v.z + v.w;
   }
   const float mean = warp_sum(s) / D;
   float q = 0.f;
   for (int c = lane * 4; c < p.D1; c += 128) {
-    const float4 v = *reinterpret_cast<const float4*>(x + c);
+    const float4 v = ldcg4(x + c);
     q += (v.x - mean) * (v.x - mean) + (v.y - mean) * (v.y - mean) + (v.z - mean) * (v.z - mean) + (v.w - mean) * (v.w - mean);
   }
   for (int c = lane * 4; c < p.D2; c += 128) {
-    float4 v = *reinterpret_cast<const float4*>(x2 + c);
-    if (x3) { const float4 u = *reinterpret_cast<const float4*>(x3 + c); v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w; }
+    float4 v = ldcg4(x2 + c);
+    if (x3) { const float4 u = ldcg4(x3 + c); v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w; }
     q += (v.x - mean) * (v.x - mean) + (v.y - mean) * (v.y - mean) + (v.z - mean) * (v.z - mean) + (v.w - mean) * (v.w - mean);
   }
   float rstd = rsqrtf(warp_sum(q) / D + 1e-5f);
@@ -73,18 +73,18 @@ __global__ void __launch_bounds__(256) ln_mod_cast_kernel(const LnParams p) {
   if (!norm) { mu = 0.f; rstd = 1.f; }
   const float *sh = nullptr, *sc = nullptr;
   if (p.shift) {
-    const size_t off = (size_t)(warp / p.rows_per_batch) * p.mod_bstride;
+    const size_t off = (size_t)(row / p.rows_per_batch) * p.mod_bstride;
     sh = p.shift + off;
     sc = p.scale + off;
   }
-  __nv_bfloat16* o = p.out + (size_t)warp * p.kmul * D;
+  __nv_bfloat16* o = p.out + (size_t)row * p.kmul * D;
   for (int c = lane * 4; c < D; c += 128) {
     float4 v;
     if (c < p.D1) {
-      v = *reinterpret_cast<const float4*>(x + c);
+      v = ldcg4(x + c);
     } else {
-      v = *reinterpret_cast<const float4*>(x2 + (c - p.D1));
-      if (x3) { const float4 u = *reinterpret_cast<const float4*>(x3 + (c - p.D1)); v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w; }
+      v = ldcg4(x2 + (c - p.D1));
+      if (x3) { const float4 u = ldcg4(x3 + (c - p.D1)); v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w; }
     }
     float4 w = make_float4(1.f, 1.f, 1.f, 1.f), b = make_float4(0.f, 0.f, 0.f, 0.f);
     if (norm) { w = *reinterpret_cast<const float4*>(p.w + c); b = *reinterpret_cast<const float4*>(p.b + c); }
@@ -97,22 +97,23 @@ __global__ void __launch_bounds__(256) ln_mod_cast_kernel(const LnParams p) {
     for (int e = 0; e < 4; ++e) store_act(o, c + e, D, p.kmul, y[e]);
   }
 }
-
-// Register-resident variant for the hot shapes (single source, D = 128 * NCH): the row is read once, both moments come
-// from registers (two-pass formula, same numerics as above), 8-byte bf16 stores.  One warp per row, 4 rows per 128-thread block.
-// MINB = minimum CTAs per SM: 1 -> 79 registers, 6 CTAs of 4 rows per SM = 888 of the 1000 CTAs of an M = 4000 launch resident (a second, nearly
-// empty wave); 8 -> <= 64 registers, the whole launch is one wave.  Selected at run time (option "ln_variant") so both can be timed in situ.
-template <int NCH, int MINB>
-__global__ void __launch_bounds__(128, MINB) ln_mod_cast_reg_kernel(const LnParams p) {
+__global__ void __launch_bounds__(256) ln_mod_cast_kernel(const LnParams p) {
   pdl_launch();
   pdl_wait();
-  const int row = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (row >= p.M) return;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= p.M) return;
+  ln_row_generic(p, warp, lane);
+}
+
+// Register-resident variant for the hot shapes (single source, D = 128 * NCH): the row is read once, both moments come
+// from registers (two-pass formula, same numerics as above), 8-byte bf16 stores.
+template <int NCH>
+__device__ __forceinline__ void ln_row_reg(const LnParams& p, int row, int lane) {
   constexpr int D = NCH * 128;
-  const float4* x = reinterpret_cast<const float4*>(p.x + (size_t)row * D);
+  const float* x = p.x + (size_t)row * D;
   float4 v[NCH];
 #pragma unroll
-  for (int i = 0; i < NCH; ++i) v[i] = x[lane + 32 * i];
+  for (int i = 0; i < NCH; ++i) v[i] = ldcg4(x + 4 * (lane + 32 * i));
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < NCH; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
@@ -143,6 +144,30 @@ __global__ void __launch_bounds__(128, MINB) ln_mod_cast_reg_kernel(const LnPara
       y0 = y0 * (1.f + a.x) + d.x; y1 = y1 * (1.f + a.y) + d.y; y2 = y2 * (1.f + a.z) + d.z; y3 = y3 * (1.f + a.w) + d.w;
     }
     *reinterpret_cast<uint2*>(o + 4 * c4) = make_uint2(pack_bf16(y0, y1), pack_bf16(y2, y3));
+  }
+}
+// One warp per row, 4 rows per 128-thread block.  MINB = minimum CTAs per SM: 1 -> 79 registers, 6 CTAs per SM = 888 of the 1000 CTAs of an
+// M = 4000 launch resident (a second, nearly empty wave); 8 -> <= 64 registers, one wave.  Run-time choice (option "ln_variant").
+template <int NCH, int MINB>
+__global__ void __launch_bounds__(128, MINB) ln_mod_cast_reg_kernel(const LnParams p) {
+  pdl_launch();
+  pdl_wait();
+  const int row = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= p.M) return;
+  ln_row_reg<NCH>(p, row, lane);
+}
+// LayerNorm as the tail phase of another kernel (gemm_ln.cuh): every warp of the (persistent, fully resident) grid takes rows in a strided loop
+__device__ __forceinline__ bool ln_reg_eligible(const LnParams& p) { return p.kmul == 1 && p.x2 == nullptr && p.w != nullptr && (p.D1 == 1152 || p.D1 == 1024); }
+__device__ __forceinline__ void ln_tail(const LnParams& p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const bool reg = ln_reg_eligible(p);
+  for (int row = blockIdx.x * nw + warp; row < p.M; row += gridDim.x * nw) {
+    if (reg) {
+      if (p.D1 == 1152) ln_row_reg<9>(p, row, lane);
+      else ln_row_reg<8>(p, row, lane);
+    } else {
+      ln_row_generic(p, row, lane);
+    }
   }
 }
 

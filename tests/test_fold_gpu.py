@@ -132,7 +132,7 @@ def test_loop_graphs_and_short_clips_with_fold():
         assert e_ref < 0.25 and e_pair < 0.25
 
 
-DEFAULTS = {"ln_fold": FOLD_DEFAULT, "attn5": 0, "dhp80": 0, "heads_direct": 0}
+DEFAULTS = {"ln_fold": FOLD_DEFAULT, "attn5": 0, "dhp80": 0, "heads_direct": 0, "ln_tail": 0, "mlp_fused": 0, "ln_variant": 0}
 
 
 @contextlib.contextmanager
@@ -148,9 +148,10 @@ def options(**kw):
             _lib.check(L.ezb_set_option(k.encode(), DEFAULTS[k]))
 
 
-@pytest.mark.parametrize("opts", [dict(heads_direct=1), dict(dhp80=1), dict(attn5=1), dict(attn5=1, dhp80=1, heads_direct=1, ln_fold=1)],
-                         ids=["heads_direct", "dhp80", "attn5", "all"])
-@pytest.mark.parametrize("name", ["dit_tiny72", "dit_tiny64", "dit_XL", "dit_tiny72_inpaint"])
+@pytest.mark.parametrize("opts", [dict(heads_direct=1), dict(dhp80=1), dict(attn5=1), dict(attn5=1, dhp80=1, heads_direct=1, ln_fold=1), dict(ln_tail=1),
+                                  dict(ln_variant=1)],
+                         ids=["heads_direct", "dhp80", "attn5", "all", "ln_tail", "ln_variant1"])
+@pytest.mark.parametrize("name", ["dit_tiny72", "dit_tiny64", "dit_XL", "dit_tiny72_inpaint", "dit_XL_inpaint_30s"])
 def test_fast_path_options_keep_parity(name, opts):
     """Every fast-path variant behind a runtime switch (q/k epilogue without smem staging, 80-element q/k rows, attention v5, folded LayerNorm)
     holds the fast mode's tolerance against the reference goldens, alone and all together."""
@@ -166,3 +167,45 @@ def test_fast_path_options_keep_parity(name, opts):
     err = (out.cpu() - torch.from_numpy(g["out"])).abs()
     print(f"[parity] {name} [bf16, {opts}]: max-abs {float(err.max()):.3e} mean-abs {float(err.mean()):.3e}")
     assert float(err.max()) < 6e-2 and float(err.mean()) < 1.2e-2
+
+
+def test_ln_tail_bit_identical_and_controlnet():
+    """LayerNorm as the tail phase of the GEMM that produces its input (gemm_ln.cuh): the same arithmetic as the stand-alone kernels, so the
+    DiT output must be BIT-IDENTICAL with and without it -- on XL (M = 1000 tokens: every residual-stream GEMM is a one-wave swap-AB launch),
+    with ControlNet skips (the skip_norm tail adds the ControlNet skip) and through the graph-replayed sampling loop."""
+    from ezaudio_b200.dit import DiTControlNet, MaskDiT
+    from ezaudio_b200.inference import sample_latents
+    from ezaudio_b200.scheduler import DDIMScheduler
+    cfg, cn = synth.model_cfg("xl"), synth.CONTROLNET
+    g = helpers.load_golden("controlnet_XL")
+    seed = int(g["seed"])
+    sd = weights.synthetic_state_dict(weights.dit_param_shapes(cfg), seed)
+    sd_cn = weights.synthetic_state_dict(weights.controlnet_param_shapes(cfg, cn), seed + 1)
+    B, L, Lc = 2, int(g["L"]), int(g["Lc"])
+    x = synth.synth_latents(B, L).cuda()
+    ctx, mask = synth.synth_context(B, Lc, cfg["context_dim"])
+    ctx, mask = ctx.cuda(), mask.cuda()
+    cond = torch.rand(B, 1, 2 * L, generator=torch.Generator().manual_seed(9)).cuda()
+    t = torch.tensor(499)
+    kw = dict(precision="bf16", max_batch=2 * B, max_len=L, max_ctx_len=Lc, max_timesteps=8)
+    unet = MaskDiT(**kw, **cfg).load_state_dict(sd)
+    cnet = DiTControlNet(**kw, **cfg, **cn).load_state_dict(sd_cn, mask_embed=sd["mask_embed"])
+    uctx, umask = synth.synth_context(1, Lc, cfg["context_dim"], seed=8, uncond=True)
+    noise = synth.synth_latents(B, L, seed=5)
+    res = {}
+    for tail in (0, 1):
+        with options(ln_tail=tail):
+            x257, _ = unet(x, t, ctx, context_mask=mask, forward_model=False)
+            skips = cnet(x257, t, ctx, context_mask=mask, condition=cond, conditioning_scale=0.8)
+            out = unet.model(x257, t, ctx, context_mask=mask, controlnet_skips=list(skips))
+            plain, _ = unet(x, t, ctx, context_mask=mask)
+            lat = sample_latents(unet, DDIMScheduler(), ctx.cpu(), mask.cpu(), uctx, umask, audio_frames=L, guidance_scale=5.0, guidance_rescale=0.75,
+                                 ddim_steps=2, eta=0, init_noise=noise)
+            lat2 = sample_latents(unet, DDIMScheduler(), ctx.cpu(), mask.cpu(), uctx, umask, audio_frames=L, guidance_scale=5.0, guidance_rescale=0.75,
+                                  ddim_steps=2, eta=0, init_noise=noise)   # graph replay
+            torch.cuda.synchronize()
+            assert torch.equal(lat, lat2)
+            res[tail] = (out.clone(), plain.clone(), skips[-1].clone(), lat.clone())
+    for a, b in zip(res[0], res[1]):
+        assert torch.equal(a, b)
+    assert float((res[1][0].cpu() - torch.from_numpy(g["out"])).abs().max()) < 6e-2
