@@ -34,7 +34,10 @@ struct Attn4Params {
   int H, Lq, Lk, dvp;
   int n_qt, n_items;
   float scale_log2;         // (1/sqrt(dh)) * log2(e)
-  int dbg;                  // profiling only (option "attn_dbg", results are garbage): 1 no exp2, 2 no S load, 4 no P store, 8 no P V MMAs, 16 no S MMAs
+  int dbg;                  // profiling only (option "attn_dbg", DBG instantiation; results are garbage): 1 no exp2, 2 no S load, 4 no P store,
+                            // 8 no P V MMAs, 16 no S MMAs
+  unsigned long long* dbg_buf;  // CTA 0 cycle counters: [0] softmax g0 wait S, [1] softmax g0 item write-out, [2] softmax g0 loop total,
+                                // [3] MMA wait P, [4] MMA wait V, [5] MMA wait Q/K, [6] TMA wait empty slots, [7] MMA thread total
 };
 
 // 2^x on the FMA pipe (Cody-Waite split + degree-3 minimax polynomial on [-0.5, 0.5], max relative error 7.8e-5 -- far below the bf16
@@ -58,7 +61,7 @@ struct Attn4Smem {
   static __host__ __device__ constexpr int total(int dvp) { return 1024 + 2 * Q_BYTES + A4_STAGES * K_BYTES + A4_STAGES * v_bytes(dvp) + 512; }
 };
 
-template <int DH, int POLY>
+template <int DH, int POLY, int DBG = 0>
 __global__ void __launch_bounds__(A4_THREADS, 1)
 attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
              const __grid_constant__ CUtensorMap tmQt, const __grid_constant__ CUtensorMap tmKt, const Attn4Params p) {
@@ -79,6 +82,10 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
   const int n_kv = (p.Lk + 127) / 128;
   const int my_items = (p.n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int U0 = ((my_items + 1) >> 1) * n_kv, U1 = (my_items >> 1) * n_kv;   // units of softmax group 0 / 1
+  const int dbg = DBG ? p.dbg : 0;   // compile-time zero in the production instantiation: the skip branches and counters vanish
+  const bool cnt = DBG && p.dbg_buf != nullptr && blockIdx.x == 0;
+  long long c_a = 0, c_b = 0, c_c = 0, t_begin = 0;
+#define A4_TIMED(acc, stmt) do { if (cnt) { const long long _t = clock64(); stmt; acc += clock64() - _t; } else { stmt; } } while (0)
 
   if (warp == 8) {
     if (lane == 0) {
@@ -115,13 +122,13 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
           const int item = blockIdx.x + (2 * itl + g) * gridDim.x;
           const int bh = item / p.n_qt, q0 = (item - bh * p.n_qt) * 128;
           if (j == 0) {
-            mbar_wait(&q_empty[g], (itl & 1) ^ 1);
+            A4_TIMED(c_a, mbar_wait(&q_empty[g], (itl & 1) ^ 1));
             mbar_expect_tx(&q_full[g], SM::Q_BYTES);
             tma_load_3d(sQ + g * SM::Q_BYTES, &tmQ, &q_full[g], 0, q0, bh);
             if (HAS_TAIL) tma_load_3d(sQ + g * SM::Q_BYTES + 16384, &tmQt, &q_full[g], 64, q0, bh);
           }
           const int st = kc % A4_STAGES;
-          mbar_wait(&k_empty[st], ((kc / A4_STAGES) & 1) ^ 1);
+          A4_TIMED(c_a, mbar_wait(&k_empty[st], ((kc / A4_STAGES) & 1) ^ 1));
           mbar_expect_tx(&k_full[st], SM::K_BYTES);
           tma_load_3d(sK + st * SM::K_BYTES, &tmK, &k_full[st], 0, j * 128, bh);
           if (HAS_TAIL) tma_load_3d(sK + st * SM::K_BYTES + 16384, &tmKt, &k_full[st], 64, j * 128, bh);
@@ -133,26 +140,28 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
           const int item = blockIdx.x + (2 * itl + g) * gridDim.x;
           const int bh = item / p.n_qt;
           const int st = vc % A4_STAGES;
-          mbar_wait(&v_empty[st], ((vc / A4_STAGES) & 1) ^ 1);
+          A4_TIMED(c_a, mbar_wait(&v_empty[st], ((vc / A4_STAGES) & 1) ^ 1));
           mbar_expect_tx(&v_full[st], VB);
           for (int hh = 0; hh < 2; ++hh) tma_load_3d(sV + st * VB + hh * (VB / 2), &tmV, &v_full[st], j * 128 + hh * 64, 0, bh);
           ++vc;
         }
       }
+      if (cnt) p.dbg_buf[6] = (unsigned long long)c_a;
     }
   } else if (warp == 8) {
     // ------------------------------------------------ MMA issuer
     if (lane == 0) {
       const uint32_t idesc_s = umma_idesc_bf16(128, 128), idesc_o = umma_idesc_bf16(128, p.dvp);
       int kc = 0, vc = 0;
+      if (cnt) t_begin = clock64();
       auto issue_s = [&](int g, int s) {
         const int itl = s / n_kv, j = s - itl * n_kv;
-        if (j == 0) mbar_wait(&q_full[g], itl & 1);
+        if (j == 0) A4_TIMED(c_c, mbar_wait(&q_full[g], itl & 1));
         const int st = kc % A4_STAGES;
-        mbar_wait(&k_full[st], (kc / A4_STAGES) & 1);
+        A4_TIMED(c_c, mbar_wait(&k_full[st], (kc / A4_STAGES) & 1));
         tc_fence_after();
         const uint64_t qd = umma_desc_sw128(smem_u32(sQ + g * SM::Q_BYTES)), kd = umma_desc_sw128(smem_u32(sK + st * SM::K_BYTES));
-        if (!(p.dbg & 16)) {
+        if (!(dbg & 16)) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma_bf16(tmem0 + g * 128, qd + 2 * k, kd + 2 * k, idesc_s, k != 0);
         if (HAS_TAIL)
@@ -165,11 +174,11 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
       };
       auto issue_pv = [&](int g, int s) {
         const int j = s % n_kv;
-        mbar_wait(&p_full[g], s & 1);
+        A4_TIMED(c_a, mbar_wait(&p_full[g], s & 1));
         const int st = vc % A4_STAGES;
-        mbar_wait(&v_full[st], (vc / A4_STAGES) & 1);
+        A4_TIMED(c_b, mbar_wait(&v_full[st], (vc / A4_STAGES) & 1));
         tc_fence_after();
-        for (int hh = 0; hh < 2 && !(p.dbg & 8); ++hh) {
+        for (int hh = 0; hh < 2 && !(dbg & 8); ++hh) {
           const uint64_t vd = umma_desc_sw128(smem_u32(sV + st * VB + hh * (VB / 2)));
 #pragma unroll
           for (int k = 0; k < 4; ++k)
@@ -190,6 +199,8 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
           if (s + 1 < Ug) issue_s(g, s + 1);
         }
       }
+      if (cnt) { p.dbg_buf[3] = (unsigned long long)c_a; p.dbg_buf[4] = (unsigned long long)c_b; p.dbg_buf[5] = (unsigned long long)c_c;
+                 p.dbg_buf[7] = (unsigned long long)(clock64() - t_begin); }
     }
   } else {
     // ------------------------------------------------ softmax groups
@@ -224,14 +235,15 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
       }
     };
 
+    if (cnt) t_begin = clock64();
     for (int s = 0; s < Ug; ++s) {
       const int itl = s / n_kv, j = s - itl * n_kv;
       const int item = blockIdx.x + (2 * itl + g) * gridDim.x;
       const int bh = item / p.n_qt, b = bh / p.H;
-      mbar_wait(&s_full[g], s & 1);
+      A4_TIMED(c_a, mbar_wait(&s_full[g], s & 1));
       tc_fence_after();
       uint32_t sr[128];
-      if (p.dbg & 2) {
+      if (dbg & 2) {
 #pragma unroll
         for (int q = 0; q < 128; ++q) sr[q] = 0;
       } else {
@@ -278,7 +290,7 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
       const float mb = (m_ref == -INFINITY) ? 0.f : m_ref * p.scale_log2;  // fully masked so far: exp2(-inf) = 0
       float sum4[4] = {0.f, 0.f, 0.f, 0.f};
       uint32_t pk[64];
-      if (p.dbg & 1) {
+      if (dbg & 1) {
 #pragma unroll
         for (int c = 0; c < 128; c += 2) {
           const float p0 = fmaf(__uint_as_float(sr[c]), p.scale_log2, -mb), p1 = fmaf(__uint_as_float(sr[c + 1]), p.scale_log2, -mb);
@@ -296,14 +308,14 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
       }
       }
       l_run += (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
-      if (!(p.dbg & 4)) {
+      if (!(dbg & 4)) {
       tmem_st_32x32(tS, pk);
       tmem_st_32x32(tS + 32, pk + 32);
       }
       if (s > 0 && j == 0) {  // retire the previous item while this unit's S / P hand-off is in flight: its last P V wrote the O that this
-        mbar_wait(&o_full[g], (s - 1) & 1);   // unit's P V (accumulate = 0, issued after our arrive) will overwrite
+        A4_TIMED(c_b, { mbar_wait(&o_full[g], (s - 1) & 1);   // unit's P V (accumulate = 0, issued after our arrive) will overwrite
         tc_fence_after();
-        write_item(item - 2 * (int)gridDim.x, l_prev);
+        write_item(item - 2 * (int)gridDim.x, l_prev); });
       }
       // in-place rescale of the O rows whose reference max moved (warp-collective TMEM access: every lane takes part)
       if (j != 0 && __any_sync(0xffffffffu, need)) {
@@ -330,11 +342,13 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
       mbar_arrive(&p_full[g]);
     }
     if (Ug > 0) {  // last item of this group
-      mbar_wait(&o_full[g], (Ug - 1) & 1);
+      A4_TIMED(c_b, { mbar_wait(&o_full[g], (Ug - 1) & 1);
       tc_fence_after();
-      write_item(blockIdx.x + (2 * ((Ug - 1) / n_kv) + g) * (int)gridDim.x, l_run);
+      write_item(blockIdx.x + (2 * ((Ug - 1) / n_kv) + g) * (int)gridDim.x, l_run); });
     }
+    if (cnt && warp == 0 && lane == 0) { p.dbg_buf[0] = (unsigned long long)c_a; p.dbg_buf[1] = (unsigned long long)c_b; p.dbg_buf[2] = (unsigned long long)(clock64() - t_begin); }
   }
+#undef A4_TIMED
   tc_fence_before();
   __syncthreads();
   if (warp == 8) tmem_dealloc<512>(tmem0);
@@ -357,13 +371,15 @@ inline int attention_tc4(Device& dev, cudaStream_t st, const __nv_bfloat16* q, c
   p.n_qt = (Lq + 127) / 128;
   p.n_items = p.n_qt * B * H;
   p.scale_log2 = scale * 1.4426950408889634f;
-  p.dbg = opt_attn_dbg();
+  p.dbg = opt_attn_dbg() & 31;
+  p.dbg_buf = (opt_attn_dbg() & 32) ? gemm_dbg_buf() : nullptr;
   const int grid = p.n_items < dev.num_sms ? p.n_items : dev.num_sms;
   auto go = [&](auto kern, int smem) -> int {
     EZB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     return launch_k(kern, dim3(grid), dim3(A4_THREADS), smem, st, 1, *tq, *tk, *tv, *tqt, *tkt, p);
   };
   const bool poly = opt_attn_poly() != 0;
+  if (opt_attn_dbg() != 0 && dh == 72) return go(attn4_kernel<72, 0, 1>, Attn4Smem<72>::total(dvp));   // profiling instantiation
   if (dh == 64) {
     EZB_TRY(poly ? go(attn4_kernel<64, 1>, Attn4Smem<64>::total(dvp)) : go(attn4_kernel<64, 0>, Attn4Smem<64>::total(dvp)));
   } else {

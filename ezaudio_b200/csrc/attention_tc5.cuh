@@ -322,7 +322,7 @@ inline int attention_tc5(Device& dev, cudaStream_t st, const __nv_bfloat16* q, c
   p.n_qt = (Lq + 127) / 128;
   p.n_items = p.n_qt * B * H;
   p.scale_log2 = scale * 1.4426950408889634f;
-  p.dbg = 0;
+  p.dbg = 0; p.dbg_buf = nullptr;
   const int grid = p.n_items < dev.num_sms ? p.n_items : dev.num_sms;
   auto go = [&](auto kern, int smem) -> int {
     EZB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
