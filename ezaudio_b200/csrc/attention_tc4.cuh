@@ -93,7 +93,7 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
       if (HAS_TAIL) { tma_prefetch_desc(&tmQt); tma_prefetch_desc(&tmKt); }
       for (int i = 0; i < 2; ++i) {
         mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); mbar_init(&s_full[i], 1); mbar_init(&o_full[i], 1);
-        mbar_init(&p_full[i], A4_SOFTMAX_THREADS / 2);
+        mbar_init(&p_full[i], A4_SOFTMAX_THREADS / 2 / 32);   // one elected arrival per softmax warp (128 per-thread arrivals on one mbarrier serialise)
       }
       for (int i = 0; i < A4_STAGES; ++i) {
         mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
@@ -339,7 +339,8 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
       }
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(&p_full[g]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[g]);
     }
     if (Ug > 0) {  // last item of this group
       A4_TIMED(c_b, { mbar_wait(&o_full[g], (Ug - 1) & 1);
