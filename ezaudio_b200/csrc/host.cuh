@@ -191,6 +191,10 @@ inline int& opt_heads_direct() {   // EpiHeads without shared-memory staging (de
   static int v = [] { const char* e = getenv("EZB_HEADS_DIRECT"); return e ? atoi(e) : 0; }();
   return v;
 }
+inline int& opt_attn_mma2() {   // attention: one MMA-issuing warp per softmax group (attention_tc4.cuh)
+  static int v = [] { const char* e = getenv("EZB_ATTN_MMA2"); return e ? atoi(e) : 0; }();
+  return v;
+}
 inline int& opt_attn_dbg() {
   static int v = 0;
   return v;

@@ -40,7 +40,12 @@ def run(B, H, Lq, Lk, dh, masked, label, impl, reps=20):
     print(f"{label:14s} impl {impl:3d} B{B} H{H} Lq{Lq} Lk{Lk} dh{dh}: {ms * 1e3:7.1f} us  {fl / ms / 1e9:6.1f} TFLOP/s")
 
 
-for impl in (1, 5, 101, 105):
+MMA2 = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+L.ezb_set_option(b"attn_mma2", MMA2)
+print("attn_mma2 =", MMA2)
+for impl in (1, 5, 101):
+    if MMA2 and impl == 5:
+        continue
     run(8, 16, 500, 500, 72, False, "self XL", impl)
     run(8, 16, 500, 100, 72, True, "cross XL", impl)
     run(4, 16, 1500, 1500, 72, False, "self XL 30s", impl)

@@ -65,3 +65,16 @@ def _run(L, _lib, args, mask, out, B, H, Lq, Lk, dh, impl):
     _lib.check(L.ezb_test_attention(0, _lib.ptr(args[0]), _lib.ptr(args[1]), _lib.ptr(args[2]), _lib.ptr(mask), _lib.ptr(out), B, H, Lq, Lk, dh, impl,
                                     _lib.stream_ptr()))
     torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("B,H,Lq,Lk,dh,masked", [(2, 4, 500, 500, 72, False), (3, 2, 500, 100, 72, True), (2, 2, 40, 12, 72, True), (1, 16, 1500, 1500, 72, False),
+                                                 (2, 3, 256, 256, 64, False), (8, 16, 500, 500, 72, False), (2, 5, 700, 700, 72, "grow"), (5, 3, 300, 100, 64, True)])
+def test_attention_two_mma_warps(B, H, Lq, Lk, dh, masked):
+    """attn4 with one MMA-issuing warp per softmax group (option attn_mma2): odd item counts per CTA (groups of unequal length), masks, growth."""
+    from ezaudio_b200 import _lib
+    L = _lib.lib()
+    _lib.check(L.ezb_set_option(b"attn_mma2", 1))
+    try:
+        test_attention(1, B, H, Lq, Lk, dh, masked)
+    finally:
+        _lib.check(L.ezb_set_option(b"attn_mma2", 0))
