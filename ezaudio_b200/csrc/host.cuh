@@ -204,7 +204,7 @@ inline int& opt_ln_variant() {
   return v;
 }
 inline int& opt_dhp80() {
-  static int v = [] { const char* e = getenv("EZB_DHP80"); return e ? atoi(e) : 0; }();
+  static int v = [] { const char* e = getenv("EZB_DHP80"); return e ? atoi(e) : 1; }();   // default on: -0.5 % step time, -0.9 us per self-attention launch (profiles/r2)
   return v;
 }
 // LayerNorm folded into the neighbouring GEMMs (gemm.cuh FoldIn / FoldOut); read when a handle is created

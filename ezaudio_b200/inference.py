@@ -125,11 +125,14 @@ def _sample_latents_on_device(unet, noise_scheduler, text, text_mask, uncond_tex
         cond_c = torch.cat([cond, cond], 0).contiguous() if use_cfg else cond.contiguous()
         skips = [torch.empty(Be, L, unet.cfg["embed_dim"], device=device, dtype=torch.float32) for _ in range(controlnet.half)]
 
-    # ---- the loop.  Every step is the same launch sequence on static buffers, so each step index is captured once into a
-    # CUDA graph (per shape / schedule) and replayed: ~500 kernel launches per step collapse into one graph launch.
-    # Everything a captured launch sequence bakes in: shapes (incl. the context length, which fixes the cross-attention K/V layout and
+    # ---- the loop.  Every step is the same launch sequence on static buffers, so the WHOLE schedule (all steps: ~365 kernels each) is captured
+    # once into one CUDA graph per shape / schedule and replayed with a single launch; the per-step Gaussian draws of DDIM (eta > 0) stay in
+    # PyTorch -- same generators, same order, same per-step tensor shapes as the step-by-step loop -- and are simply made up front into one
+    # [steps, B, C, L] buffer (round 1 replayed one graph per step: 50 launches and 200 RNG kernels interleaved cost ~0.3 ms of gaps per step).
+    # Everything a captured launch sequence bakes in is in the key: shapes (incl. the context length, which fixes the cross-attention K/V layout and
     # tensor maps), the schedule, the guidance constants, which ControlNet handle (its serial, not id(): ids are recycled) and the
     # library's option epoch (ezb_set_option changes kernel selection).
+    nsteps = len(timesteps)
     key = (B, Be, L, int(ctx.shape[1]), tuple(timesteps), use_cfg, float(guidance_scale or 0.0), float(guidance_rescale or 0.0), float(eta or 0.0),
            gt is not None, controlnet._h.serial if controlnet is not None else 0, float(conditioning_scale), int(_lib.lib().ezb_option_epoch()))
     cache = unet.__dict__.setdefault("_loop_cache", {})
@@ -138,9 +141,9 @@ def _sample_latents_on_device(unet, noise_scheduler, text, text_mask, uncond_tex
         st = dict(lat=torch.empty(B, Cc, L, device=device, dtype=torch.float32),
                   x_in=torch.empty(Be, Cc, L, device=device, dtype=torch.float32) if use_cfg else None,
                   out=torch.empty(Be, Cc, L, device=device, dtype=torch.float32),
-                  noise=torch.empty(B, Cc, L, device=device, dtype=torch.float32) if (eta and eta > 0) else None,
+                  noise=torch.empty(nsteps, B, Cc, L, device=device, dtype=torch.float32) if (eta and eta > 0) else None,
                   gt=None if gt_c is None else torch.empty_like(gt_c), m8=None if m8 is None else torch.empty_like(m8),
-                  cond=None, skips=None, graphs=[None] * len(timesteps), launches=[0] * len(timesteps))
+                  cond=None, skips=None, graph=None, launches=0)
         if controlnet is not None:
             st["cond"] = torch.empty_like(cond_c)
             st["skips"] = skips
@@ -154,7 +157,14 @@ def _sample_latents_on_device(unet, noise_scheduler, text, text_mask, uncond_tex
         st["m8"].copy_(m8)
     if controlnet is not None:
         st["cond"].copy_(cond_c)
-    lat, x_in, out, noise_buf = st["lat"], st["x_in"], st["out"], st["noise"]
+    lat, x_in, out, noise_all = st["lat"], st["x_in"], st["out"], st["noise"]
+    if noise_all is not None:  # RNG stays in PyTorch, outside the graph: step i, prompt b draws (1, C, L) from prompt b's generator, in step order
+        for i in range(nsteps):
+            if step_noise is not None:
+                noise_all[i].copy_(step_noise[i])
+            else:
+                for b, g in enumerate(gens):
+                    noise_all[i, b:b + 1].normal_(generator=g)
 
     def one_step(i, t):
         if use_cfg:
@@ -168,32 +178,25 @@ def _sample_latents_on_device(unet, noise_scheduler, text, text_mask, uncond_tex
             sk = controlnet.forward_step(xi, i, st["cond"], conditioning_scale, gt=st["gt"], gt_mask_u8=st["m8"], outs=st["skips"])
         unet.forward_step(xi, i, gt=st["gt"], gt_mask_u8=st["m8"], controlnet_skips=sk, out=out)
         coef = noise_scheduler.step_coefficients(t, float(eta or 0.0))
-        _ddim_step(out, lat, noise_buf, B, Cc, L, guidance_scale if use_cfg else 0.0, guidance_rescale, coef)
+        _ddim_step(out, lat, None if noise_all is None else noise_all[i], B, Cc, L, guidance_scale if use_cfg else 0.0, guidance_rescale, coef)
 
     L_ = _lib.lib()
-    for i, t in enumerate(timesteps):
-        if noise_buf is not None:  # RNG stays in PyTorch, outside the graph
-            if step_noise is not None:
-                noise_buf.copy_(step_noise[i])
-            else:
-                for b, g in enumerate(gens):
-                    noise_buf[b:b + 1].normal_(generator=g)
-        if not use_graphs:
+    if use_graphs and st["graph"] is not None:
+        st["graph"].replay()
+        L_.ezb_launch_count_add(st["launches"])
+    else:
+        for i, t in enumerate(timesteps):   # eager pass: warms caches (tensor maps, function attributes) and IS this call's result
             one_step(i, t)
-            continue
-        if st["graphs"][i] is None:
-            one_step(i, t)  # eager first pass: warms caches (tensor maps, function attributes) and IS this step's result
+        if use_graphs:
             snap = lat.clone()
             g = torch.cuda.CUDAGraph()
             n0 = L_.ezb_launch_count()
             with torch.cuda.graph(g):
-                one_step(i, t)
-            st["launches"][i] = int(L_.ezb_launch_count() - n0)
-            st["graphs"][i] = g
+                for i, t in enumerate(timesteps):
+                    one_step(i, t)
+            st["launches"] = int(L_.ezb_launch_count() - n0)
+            st["graph"] = g
             lat.copy_(snap)  # capture does not execute; keep the eager result
-        else:
-            st["graphs"][i].replay()
-            L_.ezb_launch_count_add(st["launches"][i])
     return lat.clone()   # the inpainting paste happens after scale_shift_re, in inference() (src/inference.py:102-105)
 
 
