@@ -415,6 +415,12 @@ struct EpiLinearT {
   using Params = EpiLinearParams;   // bias/gate indexed by feature, resid/out_f32 [token, feature]; bf16/act/split unsupported
   static constexpr int EPI_WARPS = 8;
   static constexpr int STAGE_FLOATS = 0;
+  // residual values of one 32-token chunk (feature f of tokens t0 .. t0+31)
+  static __device__ __forceinline__ void load_resid(const Params& ep, float (&x)[32], int t0, int N, int f, bool f_ok) {
+    const int nt = (N - t0) < 32 ? (N - t0) : 32;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) x[j] = (f_ok && j < nt) ? ep.resid[(size_t)(t0 + j) * ep.ldr + f] : 0.f;
+  }
   template <class Wait>
   static __device__ __forceinline__ void run(const Params& ep, float* st, uint32_t taddr_row, int row0, int nvalid, int n0, int N, int lane, int c_begin,
                                              int c_end, Wait wait) {
@@ -422,16 +428,18 @@ struct EpiLinearT {
     const bool f_ok = lane < nvalid;
     const float bias = (ep.bias != nullptr && f_ok) ? ep.bias[f] : 0.f;
     bool waited = false;
+    // The kernel is one wave, so this epilogue is exposed: the residual of chunk c + 1 is fetched while chunk c is processed (and the first
+    // chunk's before the accumulator wait), instead of one L2 round trip per chunk on the critical path.
+    float x[32];
+    if (ep.resid != nullptr && n0 + c_begin < N) load_resid(ep, x, n0 + c_begin, N, f, f_ok);
 #pragma unroll 1
     for (int c = c_begin; c < c_end; c += 32) {
       const int t0 = n0 + c;                   // first token of this chunk
       if (t0 >= N) break;                      // warp-uniform
       const int nt = (N - t0) < 32 ? (N - t0) : 32;
-      float x[32];
-      if (ep.resid != nullptr) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) x[j] = (f_ok && j < nt) ? ep.resid[(size_t)(t0 + j) * ep.ldr + f] : 0.f;
-      }
+      float xn[32];
+      const bool more = ep.resid != nullptr && c + 32 < c_end && t0 + 32 < N;
+      if (more) load_resid(ep, xn, t0 + 32, N, f, f_ok);
       float g0 = 1.f, g1 = 1.f;
       int btok = 0x7fffffff;                   // first token that belongs to the second batch item of this chunk
       if (ep.gate != nullptr && f_ok) {
@@ -454,6 +462,10 @@ struct EpiLinearT {
           if (ep.resid != nullptr) v = fmaf((t0 + j >= btok) ? g1 : g0, v, x[j]);
           o[(size_t)j * ep.ld32] = v;
         }
+      }
+      if (more) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] = xn[j];
       }
     }
     if (!waited) wait();
