@@ -30,6 +30,7 @@ struct BlockW {
   // static for site 2 (norm2 -> cross-Q) and the skip path (skip_norm -> skip_linear)
   float *g1 = nullptr, *u1 = nullptr, *v1 = nullptr, *g3 = nullptr, *u3 = nullptr, *v3 = nullptr, *u2 = nullptr, *v2 = nullptr, *us = nullptr, *vs = nullptr;
   float2 *st_skip = nullptr, *st_a = nullptr, *st_b = nullptr, *st_out = nullptr;   // per-row partial sums written by the residual-stream GEMMs
+  float *lnG1 = nullptr, *lnC1 = nullptr, *lnG3 = nullptr, *lnC3 = nullptr;   // [T][D]: norm1 / norm3 affine x AdaLN modulation precombined per timestep (ln_gc_kernel)
   // per-clip cross-attention K / V^T caches
   float *kc32 = nullptr, *vc32 = nullptr;
   bf16 *kc16 = nullptr, *vtc16 = nullptr;
@@ -91,6 +92,8 @@ struct Dit {
   size_t st_ld = 0;
   float *gc_G = nullptr, *gc_C = nullptr, *gF = nullptr, *uF = nullptr, *vF = nullptr;
   float2* st_x0 = nullptr;
+  float *lnGF = nullptr, *lnCF = nullptr;   // FinalBlock norm, per timestep
+  int gc_T = 0, gc_n = 0;                   // capacity / timesteps currently tabulated
   GridBarrier* grid_bar = nullptr;   // mlp_fused_kernel's self-resetting grid barrier
   std::vector<bf16*> cat;   // MaskDiT: per in-block [Mx, 2D] = [x of the paired out-block * snw[:D] | this block's output * snw[D:]]; ControlNet: [Mx, D] plain cast
   int geglu_bn = 128;     // N-tile of the GEGLU GEMM: packing group = geglu_bn / 2
@@ -323,6 +326,14 @@ struct Dit {
       }
     }
     EZB_TRY(alloc(&grid_bar, (size_t)1));
+    if (d.precision == 0 && (D == 1152 || D == 1024)) {   // precombined LayerNorm affine tables (ln_gc_kernel)
+      gc_T = d.max_timesteps < 128 ? d.max_timesteps : 128;
+      for (int i = 0; i < nblk; ++i) {
+        EZB_TRY(alloc(&blk[i].lnG1, (size_t)gc_T * D)); EZB_TRY(alloc(&blk[i].lnC1, (size_t)gc_T * D));
+        EZB_TRY(alloc(&blk[i].lnG3, (size_t)gc_T * D)); EZB_TRY(alloc(&blk[i].lnC3, (size_t)gc_T * D));
+      }
+      if (!d.is_controlnet) { EZB_TRY(alloc(&lnGF, (size_t)gc_T * D)); EZB_TRY(alloc(&lnCF, (size_t)gc_T * D)); }
+    }
     // ---- folded LayerNorm: tables + operand / statistics buffers
     fold_cfg = opt_fold() != 0 && d.precision == 0 && pair && swap_ab && fused_heads && D <= 2304 / 2;
     if (fold_cfg) {
@@ -412,7 +423,28 @@ struct Dit {
     return EZB_OK;
   }
   // per-timestep tables of the modulated sites (called at the end of set_timesteps)
+  int build_gc_tables(int n, cudaStream_t st) {
+    gc_n = 0;
+    if (gc_T == 0 || n > gc_T) return EZB_OK;
+    const int ldm = nblk * 6 * D;
+    auto gc = [&](const float* w_, const float* b_, const float* shift, const float* scale, int ld, float* G, float* Cc) -> int {
+      ++launch_counter();
+      fold_gc_kernel<<<(n * D + 255) / 256, 256, 0, st>>>(w_, b_, shift, scale, ld, G, Cc, n, D);
+      EZB_CUDA(cudaGetLastError());
+      return EZB_OK;
+    };
+    for (int i = 0; i < nblk; ++i) {
+      BlockW& w = blk[i];
+      const float* m = mod + (size_t)i * 6 * D;
+      EZB_TRY(gc(w.n1w, w.n1b, m + 0 * D, m + 1 * D, ldm, w.lnG1, w.lnC1));
+      EZB_TRY(gc(w.n3w, w.n3b, m + 3 * D, m + 4 * D, ldm, w.lnG3, w.lnC3));
+    }
+    if (!d.is_controlnet) EZB_TRY(gc(fn_w, fn_b, mod_final, mod_final + D, 2 * D, lnGF, lnCF));
+    gc_n = n;
+    return EZB_OK;
+  }
   int build_fold_tables(int n, cudaStream_t st) {
+    EZB_TRY(build_gc_tables(n, st));
     fold_n = 0;
     if (!fold_cfg || n > fold_T) return EZB_OK;
     const int ldm = nblk * 6 * D;
@@ -444,12 +476,35 @@ struct Dit {
     LnParams p;
     p.x = x; p.x2 = x2; p.x3 = x3; p.D1 = D1; p.D2 = D2; p.w = w; p.b = b; p.shift = shift; p.scale = scale; p.mod_bstride = mod_bstride;
     p.rows_per_batch = rows_per_batch; p.out = out; p.kmul = kmul; p.M = M;
+    p.G = nullptr; p.C = nullptr;
+    // precombined affine (ln_gc_kernel): static norms directly, modulated ones from the per-timestep tables when the batch shares one timestep
+    if (x2 == nullptr && w != nullptr && gc_T > 0) {
+      if (shift == nullptr) { p.G = w; p.C = b; }
+      else if (mod_bstride == 0 && gc_n > 0) {
+        const size_t ldm = (size_t)nblk * 6 * D;
+        if (shift >= mod && shift < mod + (size_t)n_timesteps * ldm) {
+          const size_t off = (size_t)(shift - mod), t = off / ldm, r = off % ldm, bi = r / (6 * D), site = (r % (6 * D)) / D;   // site 0: norm1, 3: norm3
+          if ((int)t < gc_n && (site == 0 || site == 3)) {
+            p.G = (site == 0 ? blk[bi].lnG1 : blk[bi].lnG3) + t * D;
+            p.C = (site == 0 ? blk[bi].lnC1 : blk[bi].lnC3) + t * D;
+          }
+        } else if (mod_final && shift >= mod_final && shift < mod_final + (size_t)n_timesteps * 2 * D) {
+          const size_t t = (size_t)(shift - mod_final) / (2 * D);
+          if ((int)t < gc_n) { p.G = lnGF + t * D; p.C = lnCF + t * D; }
+        }
+      }
+    }
     return p;
   }
   int ln(cudaStream_t st, const LnParams& p) {
     if (opt_skip() & 1) return EZB_OK;
     const int M = p.M;
     if (kmul == 1 && p.x2 == nullptr && p.w != nullptr && (p.D1 == 1152 || p.D1 == 1024)) {
+      if (opt_ln_variant() == 2 && p.G != nullptr && (p.shift == nullptr || p.mod_bstride == 0)) {
+        const int grid = dev->num_sms * 4 < (M + 3) / 4 ? dev->num_sms * 4 : (M + 3) / 4;
+        if (p.D1 == 1152) return launch_k(ln_gc_kernel<9>, dim3(grid), dim3(128), 0, st, 1, p);
+        return launch_k(ln_gc_kernel<8>, dim3(grid), dim3(128), 0, st, 1, p);
+      }
       if (opt_ln_variant() == 1) {
         if (p.D1 == 1152) return launch_k(ln_mod_cast_reg_kernel<9, 8>, dim3((M + 3) / 4), dim3(128), 0, st, 1, p);
         return launch_k(ln_mod_cast_reg_kernel<8, 8>, dim3((M + 3) / 4), dim3(128), 0, st, 1, p);

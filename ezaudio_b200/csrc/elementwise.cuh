@@ -35,6 +35,8 @@ struct LnParams {
   __nv_bfloat16* out;  // [M, kmul * (D1 + D2)]
   int kmul;
   int M;
+  const float* G;      // optional precombined affine for ln_gc_kernel: y = (x - mu) * rstd * G + C with G = w (1 + scale), C = b (1 + scale) + shift
+  const float* C;      // (one row for the whole batch: uniform timestep)
 };
 
 // x / x2 / x3 are read with ld.global.cg (L2 only): when the LayerNorm runs as the tail phase of the GEMM that produced x (gemm_ln.cuh), rows
@@ -155,6 +157,47 @@ __global__ void __launch_bounds__(128, MINB) ln_mod_cast_reg_kernel(const LnPara
   const int row = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= p.M) return;
   ln_row_reg<NCH>(p, row, lane);
+}
+// Variant with the affine precombined per timestep (G, C: fold_gc_kernel) and held in REGISTERS across rows.  In the kernel above every warp
+// re-reads weight, bias, scale and shift (4 x 4.6 KB) for its one row: 27 warps per SM pull ~500 KB of parameters through L1 for 124 KB of
+// activations.  Here a warp loads G and C once (2 x 36 registers per lane) and walks its rows in a strided loop.
+template <int NCH>
+__global__ void __launch_bounds__(128, 4) ln_gc_kernel(const LnParams p) {
+  pdl_launch();
+  pdl_wait();
+  constexpr int D = NCH * 128;
+  const int lane = threadIdx.x & 31, gw = blockIdx.x * 4 + (threadIdx.x >> 5), nw = gridDim.x * 4;
+  if (gw >= p.M) return;
+  float4 g[NCH], c[NCH];
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) {
+    g[i] = __ldg(reinterpret_cast<const float4*>(p.G) + lane + 32 * i);
+    c[i] = __ldg(reinterpret_cast<const float4*>(p.C) + lane + 32 * i);
+  }
+  for (int row = gw; row < p.M; row += nw) {
+    const float* x = p.x + (size_t)row * D;
+    float4 v[NCH];
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) v[i] = ldcg4(x + 4 * (lane + 32 * i));
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    const float mean = warp_sum(s) * (1.0f / D);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
+      q += (a * a + b * b) + (cc * cc + d * d);
+    }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + 1e-5f);
+    __nv_bfloat16* o = p.out + (size_t)row * D;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      const float y0 = fmaf((v[i].x - mean) * rstd, g[i].x, c[i].x), y1 = fmaf((v[i].y - mean) * rstd, g[i].y, c[i].y);
+      const float y2 = fmaf((v[i].z - mean) * rstd, g[i].z, c[i].z), y3 = fmaf((v[i].w - mean) * rstd, g[i].w, c[i].w);
+      *reinterpret_cast<uint2*>(o + 4 * (lane + 32 * i)) = make_uint2(pack_bf16(y0, y1), pack_bf16(y2, y3));
+    }
+  }
 }
 // LayerNorm as the tail phase of another kernel (gemm_ln.cuh): every warp of the (persistent, fully resident) grid takes rows in a strided loop
 __device__ __forceinline__ bool ln_reg_eligible(const LnParams& p) { return p.kmul == 1 && p.x2 == nullptr && p.w != nullptr && (p.D1 == 1152 || p.D1 == 1024); }
