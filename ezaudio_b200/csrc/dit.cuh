@@ -610,6 +610,8 @@ struct Dit {
       if (dh == 72) return EZB_HEADS(224, 72, 3, H * 224);
       return EZB_HEADS(192, 64, 3, H * 192);
     }
+    if (pair && opt_cq_single() && !fo && N == D && dh == 72)   // cross-Q as 256 single-CTA tiles of 128 x 144 (1.73 waves of half-size tiles)
+      return gemm<144, EpiHeads<72>>(*dev, st, A, D, W, D, M, N, D, e);
     if (pair) {
       if (dh == 72) return EZB_HEADS(144, 72, 2, N);
       return EZB_HEADS(128, 64, 2, N);

@@ -191,6 +191,10 @@ inline int& opt_heads_direct() {   // EpiHeads without shared-memory staging (de
   static int v = [] { const char* e = getenv("EZB_HEADS_DIRECT"); return e ? atoi(e) : 0; }();
   return v;
 }
+inline int& opt_cq_single() {   // cross-attention Q projection on the single-CTA kernel (smaller tiles, better wave balance) instead of CTA pairs
+  static int v = [] { const char* e = getenv("EZB_CQ_SINGLE"); return e ? atoi(e) : 0; }();
+  return v;
+}
 inline int& opt_ksub2() {   // 128-deep pipeline stages for the wide pair GEMMs (GEGLU, packed QKV): half as many per-stage waits / commits for the single MMA thread
   static int v = [] { const char* e = getenv("EZB_KSUB2"); return e ? atoi(e) : 0; }();
   return v;
