@@ -606,7 +606,7 @@ struct Dit {
   (fo ? (direct ? gemm2<BN_, EpiHeads<DH_, HPT_, true, true>>(*dev, st, A, D, W, D, M, N_, D, e) : gemm2<BN_, EpiHeads<DH_, HPT_, false, true>>(*dev, st, A, D, W, D, M, N_, D, e)) \
       : (direct ? gemm2<BN_, EpiHeads<DH_, HPT_, true, false>>(*dev, st, A, D, W, D, M, N_, D, e) : gemm2<BN_, EpiHeads<DH_, HPT_, false, false>>(*dev, st, A, D, W, D, M, N_, D, e)))
     if (qkv3_bn > 0 && N == 3 * D) {  // packed self-attention QKV: three heads per tile
-      if (dh == 72 && opt_ksub2() && !fo) return gemm2<224, EpiHeads<72, 3, true, false>, 2>(*dev, st, A, D, W, D, M, H * 224, D, e);   // 128-deep stages (needs the staging-free epilogue)
+      if (dh == 72 && (opt_ksub2() & 2) && !fo) return gemm2<224, EpiHeads<72, 3, true, false>, 2>(*dev, st, A, D, W, D, M, H * 224, D, e);   // 128-deep stages (needs the staging-free epilogue)
       if (dh == 72) return EZB_HEADS(224, 72, 3, H * 224);
       return EZB_HEADS(192, 64, 3, H * 192);
     }
@@ -844,7 +844,7 @@ struct Dit {
       }
       if (opt_skip() & 16) {}
       else if (geglu_bn == 256 && fc.on) EZB_TRY((gemm2<256, EpiGeglu<256, true>>(*dev, st, act, kmul * D, w.mlp1, kmul * D, M, 2 * inner, kmul * D, g)));
-      else if (geglu_bn == 256 && opt_ksub2() && kmul == 1) EZB_TRY((gemm2<256, EpiGeglu<256>, 2>(*dev, st, act, D, w.mlp1, D, M, 2 * inner, D, g)));   // 128-deep stages
+      else if (geglu_bn == 256 && (opt_ksub2() & 1) && kmul == 1) EZB_TRY((gemm2<256, EpiGeglu<256>, 2>(*dev, st, act, D, w.mlp1, D, M, 2 * inner, D, g)));   // 128-deep stages
       else if (geglu_bn == 256) EZB_TRY((gemm2<256, EpiGeglu<256>>(*dev, st, act, kmul * D, w.mlp1, kmul * D, M, 2 * inner, kmul * D, g)));
       else if (fc.on) EZB_TRY((gemm<128, EpiGeglu<128, true>>(*dev, st, act, kmul * D, w.mlp1, kmul * D, M, 2 * inner, kmul * D, g)));
       else EZB_TRY((gemm<128, EpiGeglu<128>>(*dev, st, act, kmul * D, w.mlp1, kmul * D, M, 2 * inner, kmul * D, g)));

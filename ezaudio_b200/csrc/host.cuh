@@ -195,8 +195,9 @@ inline int& opt_cq_single() {   // cross-attention Q projection on the single-CT
   static int v = [] { const char* e = getenv("EZB_CQ_SINGLE"); return e ? atoi(e) : 0; }();
   return v;
 }
-inline int& opt_ksub2() {   // 128-deep pipeline stages for the wide pair GEMMs (GEGLU, packed QKV): half as many per-stage waits / commits for the single MMA thread
-  static int v = [] { const char* e = getenv("EZB_KSUB2"); return e ? atoi(e) : 0; }();
+inline int& opt_ksub2() {   // 128-deep pipeline stages (half as many per-stage waits / commits for the single MMA thread): bit 0 GEGLU GEMM (76 -> 68 us, default),
+                            // bit 1 packed QKV GEMM with the staging-free epilogue (no gain, off)
+  static int v = [] { const char* e = getenv("EZB_KSUB2"); return e ? atoi(e) : 1; }();
   return v;
 }
 inline int& opt_attn_mma2() {   // attention: one MMA-issuing warp per softmax group (attention_tc4.cuh)
