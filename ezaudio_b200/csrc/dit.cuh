@@ -512,6 +512,10 @@ struct Dit {
       if (p.D1 == 1152) return launch_k(ln_mod_cast_reg_kernel<9, 1>, dim3((M + 3) / 4), dim3(128), 0, st, 1, p);
       return launch_k(ln_mod_cast_reg_kernel<8, 1>, dim3((M + 3) / 4), dim3(128), 0, st, 1, p);
     }
+    if (kmul == 1 && opt_ln_variant() == 2 && p.x2 != nullptr && p.w != nullptr && p.shift == nullptr && p.D1 == p.D2 && (p.D1 == 1152 || p.D1 == 1024)) {
+      if (p.D1 == 1152) return launch_k(ln_cat_reg_kernel<9>, dim3((M + 3) / 4), dim3(128), 0, st, 1, p);
+      return launch_k(ln_cat_reg_kernel<8>, dim3((M + 3) / 4), dim3(128), 0, st, 1, p);
+    }
     return launch_k(ln_mod_cast_kernel, dim3((M + 7) / 8), dim3(256), 0, st, 1, p);
   }
   int ln(cudaStream_t st, const float* x, int D1, const float* x2, const float* x3, int D2, const float* w, const float* b, const float* shift,

@@ -199,6 +199,53 @@ __global__ void __launch_bounds__(128, 4) ln_gc_kernel(const LnParams p) {
     }
   }
 }
+// skip_norm of the out-blocks (blocks.py:124-126): LayerNorm over the concatenated row [x | x2 (+ x3)] with D1 = D2 = 128 NCH, held in registers (one
+// pass; the generic kernel above walks the row three times).  No modulation.  One warp per row, 4 rows per 128-thread block.
+template <int NCH>
+__global__ void __launch_bounds__(128) ln_cat_reg_kernel(const LnParams p) {
+  pdl_launch();
+  pdl_wait();
+  const int row = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= p.M) return;
+  constexpr int D1 = NCH * 128, D = 2 * D1;
+  const float* x = p.x + (size_t)row * D1;
+  const float* x2 = p.x2 + (size_t)row * D1;
+  float4 v[2 * NCH];
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) {
+    v[i] = ldcg4(x + 4 * (lane + 32 * i));
+    v[NCH + i] = ldcg4(x2 + 4 * (lane + 32 * i));
+  }
+  if (p.x3 != nullptr) {
+    const float* x3 = p.x3 + (size_t)row * D1;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      const float4 u = ldcg4(x3 + 4 * (lane + 32 * i));
+      v[NCH + i].x += u.x; v[NCH + i].y += u.y; v[NCH + i].z += u.z; v[NCH + i].w += u.w;
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 2 * NCH; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  const float mean = warp_sum(s) * (1.0f / D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 2 * NCH; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + 1e-5f);
+  const float4 *w4 = reinterpret_cast<const float4*>(p.w), *b4 = reinterpret_cast<const float4*>(p.b);
+  __nv_bfloat16* o = p.out + (size_t)row * D;
+#pragma unroll
+  for (int i = 0; i < 2 * NCH; ++i) {
+    const int c4 = (i < NCH ? 0 : D1 / 4) + lane + 32 * (i < NCH ? i : i - NCH);
+    const float4 w = __ldg(w4 + c4), b = __ldg(b4 + c4);
+    const float y0 = (v[i].x - mean) * rstd * w.x + b.x, y1 = (v[i].y - mean) * rstd * w.y + b.y;
+    const float y2 = (v[i].z - mean) * rstd * w.z + b.z, y3 = (v[i].w - mean) * rstd * w.w + b.w;
+    *reinterpret_cast<uint2*>(o + 4 * c4) = make_uint2(pack_bf16(y0, y1), pack_bf16(y2, y3));
+  }
+}
 // LayerNorm as the tail phase of another kernel (gemm_ln.cuh): every warp of the (persistent, fully resident) grid takes rows in a strided loop
 __device__ __forceinline__ bool ln_reg_eligible(const LnParams& p) { return p.kmul == 1 && p.x2 == nullptr && p.w != nullptr && (p.D1 == 1152 || p.D1 == 1024); }
 __device__ __forceinline__ void ln_tail(const LnParams& p) {

@@ -209,7 +209,7 @@ inline int& opt_attn_dbg() {
   return v;
 }
 inline int& opt_ln_variant() {
-  static int v = [] { const char* e = getenv("EZB_LN_VARIANT"); return e ? atoi(e) : 0; }();
+  static int v = [] { const char* e = getenv("EZB_LN_VARIANT"); return e ? atoi(e) : 2; }();   // 2: precombined affine in registers + register-resident skip_norm (8.9 -> 6.2 us per launch)
   return v;
 }
 inline int& opt_dhp80() {
