@@ -852,6 +852,9 @@ struct Dit {
       else if (geglu_bn == 256) EZB_TRY((gemm2<256, EpiGeglu<256>>(*dev, st, act, kmul * D, w.mlp1, kmul * D, M, 2 * inner, kmul * D, g)));
       else if (fc.on) EZB_TRY((gemm<128, EpiGeglu<128, true>>(*dev, st, act, kmul * D, w.mlp1, kmul * D, M, 2 * inner, kmul * D, g)));
       else EZB_TRY((gemm<128, EpiGeglu<128>>(*dev, st, act, kmul * D, w.mlp1, kmul * D, M, 2 * inner, kmul * D, g)));
+      if (opt_mlp2_pair() && pair && kmul == 1 && !fc.on)   // MLP-out on CTA-pair tiles (256 tokens x 128 features, thread = token row) instead of swap-AB
+        EZB_TRY((gemm2<128, EpiLinear<128>>(*dev, st, mid, inner, w.mlp2, inner, M, D, inner, e)));
+      else
       EZB_TRY(lin(st, mid, inner, w.mlp2, M, D, e, fc.on ? nullptr : next_ln, next_done));
     }
     return EZB_OK;

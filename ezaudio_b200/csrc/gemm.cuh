@@ -251,13 +251,15 @@ struct EpiLinear {
         }
       }
       if (!waited) { wait(); waited = true; }
-      uint32_t r[64];
       __syncwarp();
-      tmem_ld_32x32(taddr_row + c, r);
-      tmem_ld_32x32(taddr_row + c + 32, r + 32);
-      tmem_ld_wait();
 #pragma unroll
-      for (int g = 0; g < 32; ++g) stage_put(st, lane, g, __uint_as_float(r[2 * g]), __uint_as_float(r[2 * g + 1]));
+      for (int hc = 0; hc < 2; ++hc) {  // two 32-column halves: 32 accumulator registers live next to the 64 prefetched residual values (one 64-wide
+        uint32_t r[32];                 // load spilled 780 bytes per thread under the 168-register cap of this 320-thread CTA)
+        tmem_ld_32x32(taddr_row + c + 32 * hc, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < 16; ++g) stage_put(st, lane, 16 * hc + g, __uint_as_float(r[2 * g]), __uint_as_float(r[2 * g + 1]));
+      }
       __syncwarp();
       if (col_ok) {
         const int c16 = ep.phase_cols > 0 ? (col / ep.phase_cols) * ep.phase_ld16 + col % ep.phase_cols : col;
