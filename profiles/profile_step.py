@@ -64,6 +64,13 @@ for i in range(20):
 e1.record()
 torch.cuda.synchronize()
 eager_ms = e0.elapsed_time(e1) / 20
+# VAE decode of the B clips (10 s each), 5 back-to-back decodes
+e0.record()
+for _ in range(5):
+    ez.autoencoder(embedding=lat)
+e1.record()
+torch.cuda.synchronize()
+print(f"opts {a.opt}: VAE decode of {B} x 10 s: {e0.elapsed_time(e1) / 5:.3f} ms")
 # the same step replayed from a CUDA graph (what the sampling loop does): no host launch cost at all
 g = torch.cuda.CUDAGraph()
 with torch.cuda.graph(g):
