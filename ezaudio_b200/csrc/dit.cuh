@@ -609,6 +609,10 @@ struct Dit {
 #define EZB_HEADS(BN_, DH_, HPT_, N_)                                                                                                          \
   (fo ? (direct ? gemm2<BN_, EpiHeads<DH_, HPT_, true, true>>(*dev, st, A, D, W, D, M, N_, D, e) : gemm2<BN_, EpiHeads<DH_, HPT_, false, true>>(*dev, st, A, D, W, D, M, N_, D, e)) \
       : (direct ? gemm2<BN_, EpiHeads<DH_, HPT_, true, false>>(*dev, st, A, D, W, D, M, N_, D, e) : gemm2<BN_, EpiHeads<DH_, HPT_, false, false>>(*dev, st, A, D, W, D, M, N_, D, e)))
+    if (qkv3_bn > 0 && N == 3 * D && dh == 72 && opt_heads_dbg() && !fo) {   // profiling instantiation: parts of the epilogue removed
+      e.dbg = opt_heads_dbg();
+      return gemm2<224, EpiHeads<72, 3, false, false, true>>(*dev, st, A, D, W, D, M, H * 224, D, e);
+    }
     if (qkv3_bn > 0 && N == 3 * D) {  // packed self-attention QKV: three heads per tile
       if (dh == 72 && (opt_ksub2() & 2) && !fo) return gemm2<224, EpiHeads<72, 3, true, false>, 2>(*dev, st, A, D, W, D, M, H * 224, D, e);   // 128-deep stages (needs the staging-free epilogue)
       if (dh == 72) return EZB_HEADS(224, 72, 3, H * 224);

@@ -270,6 +270,7 @@ EZB_API int ezb_set_option(const char* name, int value) {
   if (name && !strcmp(name, "swap_ab")) { opt_swap_ab() = value; return EZB_OK; }
   if (name && !strcmp(name, "qkv3")) { opt_qkv3() = value; return EZB_OK; }
   if (name && !strcmp(name, "ln_tail")) { opt_ln_tail() = value; return EZB_OK; }
+  if (name && !strcmp(name, "heads_dbg")) { opt_heads_dbg() = value; return EZB_OK; }
   if (name && !strcmp(name, "mlp2_pair")) { opt_mlp2_pair() = value; return EZB_OK; }
   if (name && !strcmp(name, "cq_single")) { opt_cq_single() = value; return EZB_OK; }
   if (name && !strcmp(name, "ksub2")) { opt_ksub2() = value; return EZB_OK; }

@@ -761,6 +761,7 @@ struct EpiHeadsParams {
   int rope_kinds;              // bit k set: apply RoPE to kind k
   __nv_bfloat16* out[3];       // per kind: q rows, k rows, v^T
   int ld_qk, dvp, Lpad;
+  int dbg;                     // profiling instantiation only (option heads_dbg; results garbage): 1 no RoPE, 2 no per-head LayerNorm, 4 no V^T stores, 8 no q / k stores
   FoldIn fin;                  // LayerNorm (+ AdaLN modulate) of the block input folded into this projection
 };
 
@@ -770,7 +771,7 @@ struct EpiHeadsParams {
 // DIRECT: every thread stores its own q / k row (dh bf16 = 128 or 144 contiguous bytes) with 16-byte stores instead of transposing it through a
 // per-warp 8 KB shared-memory tile.  The staging tiles of 12 epilogue warps take 96 KB, which leaves the 256 x 224 QKV tile only FOUR 30 KB
 // pipeline stages (the GEGLU kernel runs six); without them it gets seven.
-template <int DH, int HPT = 2, bool DIRECT = false, bool FOLD = false>
+template <int DH, int HPT = 2, bool DIRECT = false, bool FOLD = false, bool DBG = false>
 struct EpiHeads {
   using Params = EpiHeadsParams;
   static constexpr int BN = HPT == 3 ? (DH == 72 ? 224 : 3 * DH) : 2 * DH;
@@ -829,14 +830,15 @@ struct EpiHeads {
         const float var = fmaxf(((s2[0] + s2[1]) + (s2[2] + s2[3])) * (1.0f / DH) - mean * mean, 0.f);
         const float rstd = rsqrtf(var + 1e-5f);
         const float nmr = -mean * rstd;
-        if (kind == 0) {
+        if (DBG && (ep.dbg & 2)) {
+        } else if (kind == 0) {
 #pragma unroll
           for (int i = 0; i < DH; ++i) v[i] = fmaf(fmaf(v[i], rstd, nmr), ep.nw[0][i], ep.nb[0][i]);
         } else {
 #pragma unroll
           for (int i = 0; i < DH; ++i) v[i] = fmaf(fmaf(v[i], rstd, nmr), ep.nw[1][i], ep.nb[1][i]);
         }
-        if (ep.rope != nullptr && ((ep.rope_kinds >> kind) & 1)) {
+        if (ep.rope != nullptr && ((ep.rope_kinds >> kind) & 1) && !(DBG && (ep.dbg & 1))) {
           const float2* cs = ep.rope + (size_t)l * (DH / 2);
           const float lf = (float)l;
 #pragma unroll
@@ -864,7 +866,7 @@ struct EpiHeads {
         for (int g = 0; g < DH / 4; ++g)
           stage_put(st, lane, g, __uint_as_float(pack_bf16(v[4 * g], v[4 * g + 1])), __uint_as_float(pack_bf16(v[4 * g + 2], v[4 * g + 3])));
         __syncwarp();
-        if (lane < DH / 4) {
+        if (lane < DH / 4 && !(DBG && (ep.dbg & 8))) {
           const int rb0 = row0 / ep.L, rl0 = row0 - rb0 * ep.L;
           __nv_bfloat16* base = ep.out[kind] + 4 * lane;
           const size_t head_rows = (size_t)ep.L * ep.ld_qk;
@@ -876,7 +878,7 @@ struct EpiHeads {
             *reinterpret_cast<float2*>(base + ((size_t)rb * ep.H + head) * head_rows + (size_t)rl * ep.ld_qk) = stage_get(st, rr, lane);
           }
         }
-      } else if (row_ok) {
+      } else if (row_ok && !(DBG && (ep.dbg & 4))) {
         __nv_bfloat16* dst = ep.out[2] + bh * ep.dvp * ep.Lpad + l;
 #pragma unroll
         for (int i = 0; i < DH; ++i) { *dst = __float2bfloat16_rn(v[i]); dst += ep.Lpad; }

@@ -191,6 +191,10 @@ inline int& opt_heads_direct() {   // EpiHeads without shared-memory staging (de
   static int v = [] { const char* e = getenv("EZB_HEADS_DIRECT"); return e ? atoi(e) : 0; }();
   return v;
 }
+inline int& opt_heads_dbg() {
+  static int v = 0;
+  return v;
+}
 inline int& opt_mlp2_pair() {   // MLP output projection (K = 4608) on the CTA-pair kernel instead of the one-wave swap-AB kernel
   static int v = [] { const char* e = getenv("EZB_MLP2_PAIR"); return e ? atoi(e) : 0; }();
   return v;
