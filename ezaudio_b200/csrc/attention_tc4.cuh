@@ -66,7 +66,11 @@ struct Attn4Smem {
 // ~90 cycles even when already complete, five tcgen05.commit, fences) plus ~830 blocked behind the tensor pipe while issuing -- for 16 blocks per
 // CTA: 32 K of the kernel's 48 K cycles are serialised on that one thread.  With two issuers each group's chain is independent; K / V^T rings become
 // two 2-deep rings (stage = 2 g + (s & 1)) filled in the same order.
-template <int DH, int POLY, int DBG = 0, int MMA2 = 0>
+// RES = 1 ("K/V resident"): one CTA per (b, h); its K and V^T key blocks (at most A4_STAGES = 4, i.e. Lk <= 512) are loaded ONCE and stay in
+// the ring slots while the CTA walks all query tiles of that head.  The MMA thread then has no k_full / v_full waits (after the first pass) and
+// no k_empty / v_empty commits per score block -- it was the longest pole (32 K of 48 K cycles, ~1150 cycles of bookkeeping per block) --
+// every CTA has the same number of blocks (no 4-items-vs-3 tail) and K / V^T are read from L2 once instead of once per query tile.
+template <int DH, int POLY, int DBG = 0, int MMA2 = 0, int RES = 0>
 __global__ void __launch_bounds__(A4_THREADS + 32 * MMA2, 1)
 attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
              const __grid_constant__ CUtensorMap tmQt, const __grid_constant__ CUtensorMap tmKt, const Attn4Params p) {
@@ -85,7 +89,8 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_kv = (p.Lk + 127) / 128;
-  const int my_items = (p.n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int my_items = RES ? p.n_qt : (p.n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+#define A4_ITEM(itl_, g_) (RES ? (int)blockIdx.x * p.n_qt + 2 * (itl_) + (g_) : (int)blockIdx.x + (2 * (itl_) + (g_)) * (int)gridDim.x)
   const int U0 = ((my_items + 1) >> 1) * n_kv, U1 = (my_items >> 1) * n_kv;   // units of softmax group 0 / 1
   const int dbg = DBG ? p.dbg : 0;   // compile-time zero in the production instantiation: the skip branches and counters vanish
   const bool cnt = DBG && p.dbg_buf != nullptr && blockIdx.x == 0;
@@ -125,13 +130,21 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
           if (s >= (g ? U1 : U0)) continue;
           if (MMA2) kc = (g * 2 + (s & 1)) + A4_STAGES * (s >> 1);   // per-group 2-deep ring: same stage / phase arithmetic as below
           const int itl = s / n_kv, j = s - itl * n_kv;
-          const int item = blockIdx.x + (2 * itl + g) * gridDim.x;
+          const int item = A4_ITEM(itl, g);
           const int bh = item / p.n_qt, q0 = (item - bh * p.n_qt) * 128;
           if (j == 0) {
             A4_TIMED(c_a, mbar_wait(&q_empty[g], (itl & 1) ^ 1));
             mbar_expect_tx(&q_full[g], SM::Q_BYTES);
             tma_load_3d(sQ + g * SM::Q_BYTES, &tmQ, &q_full[g], 0, q0, bh);
             if (HAS_TAIL) tma_load_3d(sQ + g * SM::Q_BYTES + 16384, &tmQt, &q_full[g], 64, q0, bh);
+          }
+          if (RES) {   // K block j lives in slot j for the whole CTA: loaded by the first item that needs it (group 0's first query tile)
+            if (itl == 0 && g == 0) {
+              mbar_expect_tx(&k_full[j], SM::K_BYTES);
+              tma_load_3d(sK + j * SM::K_BYTES, &tmK, &k_full[j], 0, j * 128, bh);
+              if (HAS_TAIL) tma_load_3d(sK + j * SM::K_BYTES + 16384, &tmKt, &k_full[j], 64, j * 128, bh);
+            }
+            continue;
           }
           const int st = kc % A4_STAGES;
           A4_TIMED(c_a, mbar_wait(&k_empty[st], ((kc / A4_STAGES) & 1) ^ 1));
@@ -144,8 +157,15 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
           if (s >= (g ? U1 : U0)) continue;
           if (MMA2) vc = (g * 2 + (s & 1)) + A4_STAGES * (s >> 1);
           const int itl = s / n_kv, j = s - itl * n_kv;
-          const int item = blockIdx.x + (2 * itl + g) * gridDim.x;
+          const int item = A4_ITEM(itl, g);
           const int bh = item / p.n_qt;
+          if (RES) {
+            if (itl == 0 && g == 0) {
+              mbar_expect_tx(&v_full[j], VB);
+              for (int hh = 0; hh < 2; ++hh) tma_load_3d(sV + j * VB + hh * (VB / 2), &tmV, &v_full[j], j * 128 + hh * 64, 0, bh);
+            }
+            continue;
+          }
           const int st = vc % A4_STAGES;
           A4_TIMED(c_a, mbar_wait(&v_empty[st], ((vc / A4_STAGES) & 1) ^ 1));
           mbar_expect_tx(&v_full[st], VB);
@@ -160,12 +180,16 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
     if (lane == 0) {
       const uint32_t idesc_s = umma_idesc_bf16(128, 128), idesc_o = umma_idesc_bf16(128, p.dvp);
       int kc = 0, vc = 0;
+      unsigned kseen = 0, vseen = 0;   // RES: resident key blocks whose arrival this thread has already observed
       if (cnt) t_begin = clock64();
       auto issue_s = [&](int g, int s) {
         if (MMA2) kc = (g * 2 + (s & 1)) + A4_STAGES * (s >> 1);
         const int itl = s / n_kv, j = s - itl * n_kv;
         if (j == 0) A4_TIMED(c_c, mbar_wait(&q_full[g], itl & 1));
-        const int st = kc % A4_STAGES;
+        const int st = RES ? j : kc % A4_STAGES;
+        if (RES) {
+          if (!((kseen >> j) & 1)) { mbar_wait(&k_full[j], 0); kseen |= 1 << j; }
+        } else
         A4_TIMED(c_c, mbar_wait(&k_full[st], (kc / A4_STAGES) & 1));
         tc_fence_after();
         const uint64_t qd = umma_desc_sw128(smem_u32(sQ + g * SM::Q_BYTES)), kd = umma_desc_sw128(smem_u32(sK + st * SM::K_BYTES));
@@ -175,7 +199,7 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
         if (HAS_TAIL)
           umma_bf16(tmem0 + g * 128, umma_desc_sw32(smem_u32(sQ + g * SM::Q_BYTES + 16384)), umma_desc_sw32(smem_u32(sK + st * SM::K_BYTES + 16384)), idesc_s, 1);
         }
-        umma_commit(&k_empty[st]);
+        if (!RES) umma_commit(&k_empty[st]);
         umma_commit(&s_full[g]);
         if (j == n_kv - 1) umma_commit(&q_empty[g]);
         ++kc;
@@ -184,7 +208,10 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
         if (MMA2) vc = (g * 2 + (s & 1)) + A4_STAGES * (s >> 1);
         const int j = s % n_kv;
         A4_TIMED(c_a, mbar_wait(&p_full[g], s & 1));
-        const int st = vc % A4_STAGES;
+        const int st = RES ? j : vc % A4_STAGES;
+        if (RES) {
+          if (!((vseen >> j) & 1)) { mbar_wait(&v_full[j], 0); vseen |= 1 << j; }
+        } else
         A4_TIMED(c_b, mbar_wait(&v_full[st], (vc / A4_STAGES) & 1));
         tc_fence_after();
         for (int hh = 0; hh < 2 && !(dbg & 8); ++hh) {
@@ -193,7 +220,7 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
           for (int k = 0; k < 4; ++k)
             umma_bf16_ts(tmem0 + 256 + g * 128, tmem0 + g * 128 + hh * 32 + k * 8, vd + 2 * k, idesc_o, (j != 0) || ((hh | k) != 0));
         }
-        umma_commit(&v_empty[st]);
+        if (!RES) umma_commit(&v_empty[st]);
         umma_commit(&o_full[g]);
         ++vc;
       };
@@ -256,7 +283,7 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
     if (cnt) t_begin = clock64();
     for (int s = 0; s < Ug; ++s) {
       const int itl = s / n_kv, j = s - itl * n_kv;
-      const int item = blockIdx.x + (2 * itl + g) * gridDim.x;
+      const int item = A4_ITEM(itl, g);
       const int bh = item / p.n_qt, b = bh / p.H;
       A4_TIMED(c_a, mbar_wait(&s_full[g], s & 1));
       tc_fence_after();
@@ -333,7 +360,7 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
       if (s > 0 && j == 0) {  // retire the previous item while this unit's S / P hand-off is in flight: its last P V wrote the O that this
         A4_TIMED(c_b, { mbar_wait(&o_full[g], (s - 1) & 1);   // unit's P V (accumulate = 0, issued after our arrive) will overwrite
         tc_fence_after();
-        write_item(item - 2 * (int)gridDim.x, l_prev); });
+        write_item(A4_ITEM(itl - 1, g), l_prev); });
       }
       // in-place rescale of the O rows whose reference max moved (warp-collective TMEM access: every lane takes part)
       if (j != 0 && __any_sync(0xffffffffu, need)) {
@@ -363,11 +390,12 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
     if (Ug > 0) {  // last item of this group
       A4_TIMED(c_b, { mbar_wait(&o_full[g], (Ug - 1) & 1);
       tc_fence_after();
-      write_item(blockIdx.x + (2 * ((Ug - 1) / n_kv) + g) * (int)gridDim.x, l_run); });
+      write_item(A4_ITEM((Ug - 1) / n_kv, g), l_run); });
     }
     if (cnt && warp == 0 && lane == 0) { p.dbg_buf[0] = (unsigned long long)c_a; p.dbg_buf[1] = (unsigned long long)c_b; p.dbg_buf[2] = (unsigned long long)(clock64() - t_begin); }
   }
 #undef A4_TIMED
+#undef A4_ITEM
   tc_fence_before();
   __syncthreads();
   if (warp == 8) tmem_dealloc<512>(tmem0);
@@ -401,6 +429,14 @@ inline int attention_tc4(Device& dev, cudaStream_t st, const __nv_bfloat16* q, c
   if (opt_attn_dbg() != 0 && dh == 72) {   // profiling instantiations
     if (opt_attn_mma2()) return go(attn4_kernel<72, 0, 1, 1>, Attn4Smem<72>::total(dvp), A4_THREADS + 32);
     return go(attn4_kernel<72, 0, 1>, Attn4Smem<72>::total(dvp));
+  }
+  if (opt_attn_res() && (Lk + 127) / 128 <= A4_STAGES && !opt_attn_dbg()) {   // K / V^T resident: one CTA per (b, h), all its query tiles
+    auto go_res = [&](auto kern, int smem) -> int {
+      EZB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      return launch_k(kern, dim3(B * H), dim3(A4_THREADS), smem, st, 1, *tq, *tk, *tv, *tqt, *tkt, p);
+    };
+    if (dh == 64) return go_res(attn4_kernel<64, 0, 0, 0, 1>, Attn4Smem<64>::total(dvp));
+    return go_res(attn4_kernel<72, 0, 0, 0, 1>, Attn4Smem<72>::total(dvp));
   }
   if (opt_attn_mma2()) {
     if (dh == 64) return go(attn4_kernel<64, 0, 0, 1>, Attn4Smem<64>::total(dvp), A4_THREADS + 32);

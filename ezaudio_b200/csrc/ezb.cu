@@ -274,6 +274,7 @@ EZB_API int ezb_set_option(const char* name, int value) {
   if (name && !strcmp(name, "mlp2_pair")) { opt_mlp2_pair() = value; return EZB_OK; }
   if (name && !strcmp(name, "cq_single")) { opt_cq_single() = value; return EZB_OK; }
   if (name && !strcmp(name, "ksub2")) { opt_ksub2() = value; return EZB_OK; }
+  if (name && !strcmp(name, "attn_res")) { opt_attn_res() = value; return EZB_OK; }
   if (name && !strcmp(name, "attn_mma2")) { opt_attn_mma2() = value; return EZB_OK; }
   if (name && !strcmp(name, "attn_dbg")) { opt_attn_dbg() = value; return EZB_OK; }
   if (name && !strcmp(name, "ln_variant")) { opt_ln_variant() = value; return EZB_OK; }

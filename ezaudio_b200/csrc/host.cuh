@@ -208,6 +208,10 @@ inline int& opt_ksub2() {   // 128-deep pipeline stages (half as many per-stage 
   static int v = [] { const char* e = getenv("EZB_KSUB2"); return e ? atoi(e) : 1; }();
   return v;
 }
+inline int& opt_attn_res() {   // attention with K / V^T resident per (b, h) (attention_tc4.cuh, RES = 1)
+  static int v = [] { const char* e = getenv("EZB_ATTN_RES"); return e ? atoi(e) : 0; }();
+  return v;
+}
 inline int& opt_attn_mma2() {   // attention: one MMA-issuing warp per softmax group (attention_tc4.cuh)
   static int v = [] { const char* e = getenv("EZB_ATTN_MMA2"); return e ? atoi(e) : 0; }();
   return v;

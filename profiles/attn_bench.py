@@ -41,8 +41,10 @@ def run(B, H, Lq, Lk, dh, masked, label, impl, reps=20):
 
 
 MMA2 = int(sys.argv[1]) if len(sys.argv) > 1 else 0
-L.ezb_set_option(b"attn_mma2", MMA2)
-print("attn_mma2 =", MMA2)
+L.ezb_set_option(b"attn_mma2", MMA2 & 1)
+L.ezb_set_option(b"attn_res", (MMA2 >> 1) & 1)
+L.ezb_set_option(b"attn_poly", (MMA2 >> 2) & 1)
+print("attn_mma2 =", MMA2 & 1, "attn_res =", (MMA2 >> 1) & 1, "attn_poly =", (MMA2 >> 2) & 1)
 for impl in (1, 5, 101):
     if MMA2 and impl == 5:
         continue

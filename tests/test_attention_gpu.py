@@ -78,3 +78,19 @@ def test_attention_two_mma_warps(B, H, Lq, Lk, dh, masked):
         test_attention(1, B, H, Lq, Lk, dh, masked)
     finally:
         _lib.check(L.ezb_set_option(b"attn_mma2", 0))
+
+
+@pytest.mark.parametrize("B,H,Lq,Lk,dh,masked", [(2, 4, 500, 500, 72, False), (3, 2, 500, 100, 72, True), (2, 2, 40, 12, 72, True), (1, 16, 1500, 1500, 72, False),
+                                                 (2, 3, 256, 256, 64, False), (8, 16, 500, 500, 72, False), (2, 5, 400, 512, 72, "grow"), (5, 3, 300, 100, 64, True),
+                                                 (16, 16, 500, 500, 72, False), (2, 2, 130, 385, 72, True)])
+def test_attention_kv_resident(B, H, Lq, Lk, dh, masked):
+    """attn4 with the K / V^T key blocks of a head resident in shared memory (option attn_res; falls back above 512 keys): odd and even numbers
+    of query tiles per head, one to four key blocks, more heads than SMs (two waves of CTAs), masks, growth."""
+    from ezaudio_b200 import _lib
+    L = _lib.lib()
+    _lib.check(L.ezb_set_option(b"attn_res", 1))
+    try:
+        test_attention(1, B, H, Lq, Lk, dh, masked)
+        test_attention(101, B, H, Lq, Lk, dh, masked)
+    finally:
+        _lib.check(L.ezb_set_option(b"attn_res", 0))
