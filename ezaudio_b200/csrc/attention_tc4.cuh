@@ -121,70 +121,88 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
   pdl_wait();
 
   if (warp == 9 + MMA2) {
-    // ------------------------------------------------ TMA producer (static ping-pong order)
-    if (lane == 0) {
+    // ------------------------------------------------ TMA producer (static ping-pong order).  Warp-uniform loop, copies issued under
+    // elect.sync (inside an `if (lane == 0)` region ptxas serialises every UTMALDG / UTCHMMA / UTCBAR through an ELECT ... BRA.U.ANY loop).
+    {
       int kc = 0, vc = 0;
       const int maxU = U0 > U1 ? U0 : U1;
+      int itl = 0, j = 0;   // s = itl * n_kv + j
       for (int s = 0; s < maxU; ++s) {
         for (int g = 0; g < 2; ++g) {
           if (s >= (g ? U1 : U0)) continue;
           if (MMA2) kc = (g * 2 + (s & 1)) + A4_STAGES * (s >> 1);   // per-group 2-deep ring: same stage / phase arithmetic as below
-          const int itl = s / n_kv, j = s - itl * n_kv;
           const int item = A4_ITEM(itl, g);
           const int bh = item / p.n_qt, q0 = (item - bh * p.n_qt) * 128;
           if (j == 0) {
             A4_TIMED(c_a, mbar_wait(&q_empty[g], (itl & 1) ^ 1));
-            mbar_expect_tx(&q_full[g], SM::Q_BYTES);
-            tma_load_3d(sQ + g * SM::Q_BYTES, &tmQ, &q_full[g], 0, q0, bh);
-            if (HAS_TAIL) tma_load_3d(sQ + g * SM::Q_BYTES + 16384, &tmQt, &q_full[g], 64, q0, bh);
+            if (elect_one()) {
+              mbar_expect_tx(&q_full[g], SM::Q_BYTES);
+              tma_load_3d(sQ + g * SM::Q_BYTES, &tmQ, &q_full[g], 0, q0, bh);
+              if (HAS_TAIL) tma_load_3d(sQ + g * SM::Q_BYTES + 16384, &tmQt, &q_full[g], 64, q0, bh);
+            }
+            __syncwarp();
           }
           if (RES) {   // K block j lives in slot j for the whole CTA: loaded by the first item that needs it (group 0's first query tile)
             if (itl == 0 && g == 0) {
-              mbar_expect_tx(&k_full[j], SM::K_BYTES);
-              tma_load_3d(sK + j * SM::K_BYTES, &tmK, &k_full[j], 0, j * 128, bh);
-              if (HAS_TAIL) tma_load_3d(sK + j * SM::K_BYTES + 16384, &tmKt, &k_full[j], 64, j * 128, bh);
+              if (elect_one()) {
+                mbar_expect_tx(&k_full[j], SM::K_BYTES);
+                tma_load_3d(sK + j * SM::K_BYTES, &tmK, &k_full[j], 0, j * 128, bh);
+                if (HAS_TAIL) tma_load_3d(sK + j * SM::K_BYTES + 16384, &tmKt, &k_full[j], 64, j * 128, bh);
+              }
+              __syncwarp();
             }
             continue;
           }
           const int st = kc % A4_STAGES;
           A4_TIMED(c_a, mbar_wait(&k_empty[st], ((kc / A4_STAGES) & 1) ^ 1));
-          mbar_expect_tx(&k_full[st], SM::K_BYTES);
-          tma_load_3d(sK + st * SM::K_BYTES, &tmK, &k_full[st], 0, j * 128, bh);
-          if (HAS_TAIL) tma_load_3d(sK + st * SM::K_BYTES + 16384, &tmKt, &k_full[st], 64, j * 128, bh);
+          if (elect_one()) {
+            mbar_expect_tx(&k_full[st], SM::K_BYTES);
+            tma_load_3d(sK + st * SM::K_BYTES, &tmK, &k_full[st], 0, j * 128, bh);
+            if (HAS_TAIL) tma_load_3d(sK + st * SM::K_BYTES + 16384, &tmKt, &k_full[st], 64, j * 128, bh);
+          }
+          __syncwarp();
           ++kc;
         }
         for (int g = 0; g < 2; ++g) {
           if (s >= (g ? U1 : U0)) continue;
           if (MMA2) vc = (g * 2 + (s & 1)) + A4_STAGES * (s >> 1);
-          const int itl = s / n_kv, j = s - itl * n_kv;
           const int item = A4_ITEM(itl, g);
           const int bh = item / p.n_qt;
           if (RES) {
             if (itl == 0 && g == 0) {
-              mbar_expect_tx(&v_full[j], VB);
-              for (int hh = 0; hh < 2; ++hh) tma_load_3d(sV + j * VB + hh * (VB / 2), &tmV, &v_full[j], j * 128 + hh * 64, 0, bh);
+              if (elect_one()) {
+                mbar_expect_tx(&v_full[j], VB);
+                for (int hh = 0; hh < 2; ++hh) tma_load_3d(sV + j * VB + hh * (VB / 2), &tmV, &v_full[j], j * 128 + hh * 64, 0, bh);
+              }
+              __syncwarp();
             }
             continue;
           }
           const int st = vc % A4_STAGES;
           A4_TIMED(c_a, mbar_wait(&v_empty[st], ((vc / A4_STAGES) & 1) ^ 1));
-          mbar_expect_tx(&v_full[st], VB);
-          for (int hh = 0; hh < 2; ++hh) tma_load_3d(sV + st * VB + hh * (VB / 2), &tmV, &v_full[st], j * 128 + hh * 64, 0, bh);
+          if (elect_one()) {
+            mbar_expect_tx(&v_full[st], VB);
+            for (int hh = 0; hh < 2; ++hh) tma_load_3d(sV + st * VB + hh * (VB / 2), &tmV, &v_full[st], j * 128 + hh * 64, 0, bh);
+          }
+          __syncwarp();
           ++vc;
         }
+        if (++j == n_kv) { j = 0; ++itl; }
       }
-      if (cnt) p.dbg_buf[6] = (unsigned long long)c_a;
+      if (cnt && lane == 0) p.dbg_buf[6] = (unsigned long long)c_a;
     }
   } else if (warp == 8 || (MMA2 && warp == 9)) {
-    // ------------------------------------------------ MMA issuer(s)
-    if (lane == 0) {
+    // ------------------------------------------------ MMA issuer(s): warp-uniform control flow, one elected lane issues
+    {
       const uint32_t idesc_s = umma_idesc_bf16(128, 128), idesc_o = umma_idesc_bf16(128, p.dvp);
       int kc = 0, vc = 0;
-      unsigned kseen = 0, vseen = 0;   // RES: resident key blocks whose arrival this thread has already observed
+      unsigned kseen = 0, vseen = 0;   // RES: resident key blocks whose arrival this warp has already observed
+      int sj[2] = {0, 0}, sit[2] = {0, 0};   // next score block to issue per group: key block j, local item index
+      int pj[2] = {0, 0};                    // next P V per group: key block j
       if (cnt) t_begin = clock64();
       auto issue_s = [&](int g, int s) {
         if (MMA2) kc = (g * 2 + (s & 1)) + A4_STAGES * (s >> 1);
-        const int itl = s / n_kv, j = s - itl * n_kv;
+        const int itl = sit[g], j = sj[g];
         if (j == 0) A4_TIMED(c_c, mbar_wait(&q_full[g], itl & 1));
         const int st = RES ? j : kc % A4_STAGES;
         if (RES) {
@@ -192,21 +210,25 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
         } else
         A4_TIMED(c_c, mbar_wait(&k_full[st], (kc / A4_STAGES) & 1));
         tc_fence_after();
-        const uint64_t qd = umma_desc_sw128(smem_u32(sQ + g * SM::Q_BYTES)), kd = umma_desc_sw128(smem_u32(sK + st * SM::K_BYTES));
-        if (!(dbg & 16)) {
+        if (elect_one()) {
+          const uint64_t qd = umma_desc_sw128(smem_u32(sQ + g * SM::Q_BYTES)), kd = umma_desc_sw128(smem_u32(sK + st * SM::K_BYTES));
+          if (!(dbg & 16)) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tmem0 + g * 128, qd + 2 * k, kd + 2 * k, idesc_s, k != 0);
-        if (HAS_TAIL)
-          umma_bf16(tmem0 + g * 128, umma_desc_sw32(smem_u32(sQ + g * SM::Q_BYTES + 16384)), umma_desc_sw32(smem_u32(sK + st * SM::K_BYTES + 16384)), idesc_s, 1);
+          for (int k = 0; k < 4; ++k) umma_bf16(tmem0 + g * 128, qd + 2 * k, kd + 2 * k, idesc_s, k != 0);
+          if (HAS_TAIL)
+            umma_bf16(tmem0 + g * 128, umma_desc_sw32(smem_u32(sQ + g * SM::Q_BYTES + 16384)), umma_desc_sw32(smem_u32(sK + st * SM::K_BYTES + 16384)), idesc_s, 1);
+          }
+          if (!RES) umma_commit(&k_empty[st]);
+          umma_commit(&s_full[g]);
+          if (j == n_kv - 1) umma_commit(&q_empty[g]);
         }
-        if (!RES) umma_commit(&k_empty[st]);
-        umma_commit(&s_full[g]);
-        if (j == n_kv - 1) umma_commit(&q_empty[g]);
+        __syncwarp();
         ++kc;
+        if (++sj[g] == n_kv) { sj[g] = 0; ++sit[g]; }
       };
       auto issue_pv = [&](int g, int s) {
         if (MMA2) vc = (g * 2 + (s & 1)) + A4_STAGES * (s >> 1);
-        const int j = s % n_kv;
+        const int j = pj[g];
         A4_TIMED(c_a, mbar_wait(&p_full[g], s & 1));
         const int st = RES ? j : vc % A4_STAGES;
         if (RES) {
@@ -214,15 +236,19 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
         } else
         A4_TIMED(c_b, mbar_wait(&v_full[st], (vc / A4_STAGES) & 1));
         tc_fence_after();
-        for (int hh = 0; hh < 2 && !(dbg & 8); ++hh) {
-          const uint64_t vd = umma_desc_sw128(smem_u32(sV + st * VB + hh * (VB / 2)));
+        if (elect_one()) {
+          for (int hh = 0; hh < 2 && !(dbg & 8); ++hh) {
+            const uint64_t vd = umma_desc_sw128(smem_u32(sV + st * VB + hh * (VB / 2)));
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16_ts(tmem0 + 256 + g * 128, tmem0 + g * 128 + hh * 32 + k * 8, vd + 2 * k, idesc_o, (j != 0) || ((hh | k) != 0));
+            for (int k = 0; k < 4; ++k)
+              umma_bf16_ts(tmem0 + 256 + g * 128, tmem0 + g * 128 + hh * 32 + k * 8, vd + 2 * k, idesc_o, (j != 0) || ((hh | k) != 0));
+          }
+          if (!RES) umma_commit(&v_empty[st]);
+          umma_commit(&o_full[g]);
         }
-        if (!RES) umma_commit(&v_empty[st]);
-        umma_commit(&o_full[g]);
+        __syncwarp();
         ++vc;
+        if (++pj[g] == n_kv) pj[g] = 0;
       };
       if (MMA2) {   // this warp's own group only
         const int g = warp - 8, Ug = g ? U1 : U0;
@@ -236,6 +262,7 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
       if (U0 > 0) issue_s(0, 0);
       if (U1 > 0) issue_s(1, 0);
       for (int s = 0; s < maxU; ++s) {
+#pragma unroll
         for (int g = 0; g < 2; ++g) {
           const int Ug = g ? U1 : U0;
           if (s >= Ug) continue;
@@ -244,7 +271,7 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
         }
       }
       }
-      if (cnt && warp == 8) { p.dbg_buf[3] = (unsigned long long)c_a; p.dbg_buf[4] = (unsigned long long)c_b; p.dbg_buf[5] = (unsigned long long)c_c;
+      if (cnt && warp == 8 && lane == 0) { p.dbg_buf[3] = (unsigned long long)c_a; p.dbg_buf[4] = (unsigned long long)c_b; p.dbg_buf[5] = (unsigned long long)c_c;
                  p.dbg_buf[7] = (unsigned long long)(clock64() - t_begin); }
     }
   } else {
@@ -281,8 +308,8 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
     };
 
     if (cnt) t_begin = clock64();
+    int itl = 0, j = 0;   // s = itl * n_kv + j
     for (int s = 0; s < Ug; ++s) {
-      const int itl = s / n_kv, j = s - itl * n_kv;
       const int item = A4_ITEM(itl, g);
       const int bh = item / p.n_qt, b = bh / p.H;
       A4_TIMED(c_a, mbar_wait(&s_full[g], s & 1));
@@ -386,6 +413,7 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[g]);
+      if (++j == n_kv) { j = 0; ++itl; }
     }
     if (Ug > 0) {  // last item of this group
       A4_TIMED(c_b, { mbar_wait(&o_full[g], (Ug - 1) & 1);

@@ -639,14 +639,18 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
   pdl_wait();  // everything above overlapped the previous kernel's tail; global memory is touched only below
 
   if (warp == 0) {
-    // ------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // ------------------------------------------------ TMA producer.  The loop is warp-uniform and the copies are issued under elect.sync:
+    // inside an `if (lane == 0)` region ptxas wraps every UTMALDG / UTCHMMA / UTCBAR (uniform-datapath instructions) in an
+    // ELECT ... BRA.U.ANY serialisation loop with R2UR broadcasts (~40-60 cycles per instruction); under elect.sync it knows a
+    // single lane is active and issues them back to back.
+    {
       uint32_t stage = 0, phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int mt = tile % g.num_m_tiles, nt = tile / g.num_m_tiles;
         const int n0 = nt * BN;
         for (int kb = 0; kb < g.num_k_blocks; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
+          if (elect_one()) {
           mbar_expect_tx(&full[stage], SM::A_BYTES + SM::B_BYTES);
           if (g.taps == 0) {
             tma_load_2d(sA + stage * SM::A_BYTES, &tmA, &full[stage], kb * GEMM_BK, mt * GEMM_BM);
@@ -667,12 +671,14 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
             for (int j = (int)cluster_ctarank(); j < BN / 32; j += MC)
               tma_load_2d_mc(sB + stage * SM::B_BYTES + j * 4096, &tmB, &full[stage], kb * GEMM_BK, n0 + j * 32, MC_MASK);
           }
+          }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------ MMA issuer
+    // ------------------------------------------------ MMA issuer (warp-uniform loop, one elected lane issues: see the producer's note)
     constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN);
     uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -682,7 +688,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
       for (int kb = 0; kb < g.num_k_blocks; ++kb) {
         mbar_wait(&full[stage], phase);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const uint64_t ad = umma_desc_sw128(smem_u32(sA + stage * SM::A_BYTES));
           const uint64_t bd = umma_desc_sw128(smem_u32(sB + stage * SM::B_BYTES));
 #pragma unroll
@@ -947,7 +953,7 @@ __device__ __forceinline__ void gemm2_body(const CUtensorMap& tmA, const CUtenso
 
   if (warp == 0) {
     // ------------------------------------------------ TMA producer (both CTAs; bytes are credited to the leader's barrier)
-    if (lane == 0) {
+    {
       uint32_t stage = 0, phase = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
         const int mt = tile % g.num_m_tiles, nt = tile / g.num_m_tiles;
@@ -958,11 +964,14 @@ __device__ __forceinline__ void gemm2_body(const CUtensorMap& tmA, const CUtenso
           EZB_DBG(w0 += clock64() - tq;)
           const uint32_t bar = mapa_u32(smem_u32(&full[stage]), 0);
           const int nsub = (g.num_k_blocks - kb) < KSUB ? (g.num_k_blocks - kb) : KSUB;
-          if (leader) mbar_expect_tx(&full[stage], 2 * nsub * (SM::A_SUB + SM::B_SUB));
-          for (int sub = 0; sub < nsub; ++sub) {
-            tma_load_2d_pair(sA + stage * SM::A_BYTES + sub * SM::A_SUB, &tmA, bar, (kb + sub) * GEMM_BK, m0);
-            tma_load_2d_pair(sB + stage * SM::B_BYTES + sub * SM::B_SUB, &tmB, bar, (kb + sub) * GEMM_BK, n0);
+          if (elect_one()) {
+            if (leader) mbar_expect_tx(&full[stage], 2 * nsub * (SM::A_SUB + SM::B_SUB));
+            for (int sub = 0; sub < nsub; ++sub) {
+              tma_load_2d_pair(sA + stage * SM::A_BYTES + sub * SM::A_SUB, &tmA, bar, (kb + sub) * GEMM_BK, m0);
+              tma_load_2d_pair(sB + stage * SM::B_BYTES + sub * SM::B_SUB, &tmB, bar, (kb + sub) * GEMM_BK, n0);
+            }
           }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -983,7 +992,7 @@ __device__ __forceinline__ void gemm2_body(const CUtensorMap& tmA, const CUtenso
           mbar_wait(&full[stage], phase);
           EZB_DBG(w0 += clock64() - tq;)
           tc_fence_after();
-          if (lane == 0) {
+          if (elect_one()) {
             const int nsub = (g.num_k_blocks - kb) < KSUB ? (g.num_k_blocks - kb) : KSUB;
             for (int sub = 0; sub < nsub; ++sub) {
               const uint64_t ad = umma_desc_sw128(smem_u32(sA + stage * SM::A_BYTES + sub * SM::A_SUB));
