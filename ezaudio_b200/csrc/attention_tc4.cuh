@@ -34,6 +34,7 @@ struct Attn4Params {
   int H, Lq, Lk, dvp;
   int n_qt, n_items;
   float scale_log2;         // (1/sqrt(dh)) * log2(e)
+  int pp;                   // 1: the two softmax groups take turns in their exponent phases (MUFU token, see the kernel comment)
   int dbg;                  // profiling only (option "attn_dbg", DBG instantiation; results are garbage): 1 no exp2, 2 no S load, 4 no P store,
                             // 8 no P V MMAs, 16 no S MMAs
   unsigned long long* dbg_buf;  // CTA 0 cycle counters: [0] softmax g0 wait S, [1] softmax g0 item write-out, [2] softmax g0 loop total,
@@ -85,7 +86,8 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
   uint64_t* bars = reinterpret_cast<uint64_t*>(sV + A4_STAGES * VB);
   uint64_t *q_full = bars, *q_empty = bars + 2, *s_full = bars + 4, *p_full = bars + 6, *o_full = bars + 8;
   uint64_t *k_full = bars + 10, *k_empty = k_full + A4_STAGES, *v_full = k_empty + A4_STAGES, *v_empty = v_full + A4_STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(v_empty + A4_STAGES);
+  uint64_t* tok = v_empty + A4_STAGES;   // [2] MUFU token: tok[g] completes a phase when the OTHER group has finished an exponent phase
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tok + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_kv = (p.Lk + 127) / 128;
@@ -104,6 +106,7 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
       for (int i = 0; i < 2; ++i) {
         mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); mbar_init(&s_full[i], 1); mbar_init(&o_full[i], 1);
         mbar_init(&p_full[i], A4_SOFTMAX_THREADS / 2 / 32);   // one elected arrival per softmax warp (128 per-thread arrivals on one mbarrier serialise)
+        mbar_init(&tok[i], A4_SOFTMAX_THREADS / 2 / 32);
       }
       for (int i = 0; i < A4_STAGES; ++i) {
         mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
@@ -362,6 +365,11 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
       const float mb = (m_ref == -INFINITY) ? 0.f : m_ref * p.scale_log2;  // fully masked so far: exp2(-inf) = 0
       float sum4[4] = {0.f, 0.f, 0.f, 0.f};
       uint32_t pk[64];
+      // MUFU token (p.pp): exponent phases strictly alternate  G0#0 G1#0 G0#1 G1#1 ...  Left alone the two groups drift INTO phase (the MMA warp serves
+      // them back to back): both then share the 16 ex2 / clock of the SM during their exponent phases and both wait for the tensor pipe afterwards
+      // -- ncu: XU 38 % busy, 31 % of the softmax warps' samples on the S wait.  With the token one group's exponentials run at the full MUFU rate
+      // while the other group's P V / next S MMAs, tcgen05.ld and row max are in flight.
+      if (p.pp && !(g == 0 && s == 0)) mbar_wait(&tok[g], (g == 0 ? s - 1 : s) & 1);
       if (dbg & 1) {
 #pragma unroll
         for (int c = 0; c < 128; c += 2) {
@@ -380,6 +388,10 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
       }
       }
       l_run += (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
+      if (p.pp) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tok[g ^ 1]);
+      }
       if (!(dbg & 4)) {
       tmem_st_32x32(tS, pk);
       tmem_st_32x32(tS + 32, pk + 32);
@@ -420,6 +432,13 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
       tc_fence_after();
       write_item(A4_ITEM((Ug - 1) / n_kv, g), l_run); });
     }
+    if (p.pp && g == 1) {   // group 0 has n_kv more blocks than group 1 when the CTA's item count is odd: keep handing the token back
+      for (int n = U1; n < U0 - 1; ++n) {
+        mbar_wait(&tok[1], n & 1);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tok[0]);
+      }
+    }
     if (cnt && warp == 0 && lane == 0) { p.dbg_buf[0] = (unsigned long long)c_a; p.dbg_buf[1] = (unsigned long long)c_b; p.dbg_buf[2] = (unsigned long long)(clock64() - t_begin); }
   }
 #undef A4_TIMED
@@ -446,6 +465,7 @@ inline int attention_tc4(Device& dev, cudaStream_t st, const __nv_bfloat16* q, c
   p.n_qt = (Lq + 127) / 128;
   p.n_items = p.n_qt * B * H;
   p.scale_log2 = scale * 1.4426950408889634f;
+  p.pp = opt_attn_pp() != 0;
   p.dbg = opt_attn_dbg() & 31;
   p.dbg_buf = (opt_attn_dbg() & 32) ? gemm_dbg_buf() : nullptr;
   const int grid = p.n_items < dev.num_sms ? p.n_items : dev.num_sms;

@@ -1,0 +1,442 @@
+// tcgen05 flash attention, generation 6: the same pipeline as attention_tc4.cuh (two query tiles in flight per persistent CTA, thread = query
+// row, P kept in tensor memory, K / V^T rings filled by TMA) with the softmax rebuilt around what the ncu source-level capture of attn4 showed
+// (profiles/r2/attention_r2b.md): its softmax warps execute ~750 instructions per 128 x 128 score block at 0.2-0.3 IPC -- 128 scalar FFMA, 130 FADD
+// and ~70 register moves around the 128-register score array and the 64-register P array that coexist until the two tcgen05.st at the end -- and both
+// groups run their exponent phases at the same time, so the MUFU (16 ex2 / clock / SM) is shared while it is needed and idle while both wait for the
+// tensor pipe.  Changes:
+//   * the exponent pass walks the score registers in four 32-column chunks; each chunk's 16 packed bf16x2 words go to tensor memory at once
+//     (tcgen05.st .x16): no 64-register P array, no register shuffling;
+//   * packed arithmetic: fma.rn.f32x2 for x * scale - max and add.rn.f32x2 for the row sum (half the issue slots of the scalar forms);
+//   * MUFU token: the exponent phases of the two groups strictly alternate (G0 #0, G1 #0, G0 #1, ...), so one group's exponentials run at the
+//     full MUFU rate while the other group's P V / next-S MMAs, tcgen05.ld and row max are in flight;
+//   * P is handed to the MMA warp in two halves (64 keys each): the first four P V MMAs run under the second half of the exponentials;
+//   * the previous item's write-out and the (rare) in-place O rescale happen BEFORE the exponent phase (they must precede the first P V of the block).
+// Replaces F.scaled_dot_product_attention in src/models/utils/attention.py:107-110 (self: mask None; cross: bool key mask, attention.py:30-37).
+// Layouts as produced by the QKV GEMM epilogue: Q, K [B*H, L, DHP] bf16; V^T [B*H, DVP, Lpad] bf16.  Output [B, Lq, H*dh] bf16 token-major.
+#pragma once
+#include "attention_tc4.cuh"
+
+namespace ezb {
+
+__device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
+  unsigned long long v;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(lo), "f"(hi));
+  return v;
+}
+__device__ __forceinline__ void unpack_f32x2(unsigned long long v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ unsigned long long fma_f32x2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ unsigned long long add_f32x2(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]),
+      "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+
+// PP: MUFU token between the softmax groups.  HALF: P handed over in two halves.
+template <int DH, int PP, int HALF>
+__global__ void __launch_bounds__(A4_THREADS, 1)
+attn6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+             const __grid_constant__ CUtensorMap tmQt, const __grid_constant__ CUtensorMap tmKt, const Attn4Params p) {
+  using SM = Attn4Smem<DH>;
+  constexpr bool HAS_TAIL = DH > 64;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int VB = SM::v_bytes(p.dvp);
+  uint8_t* sQ = smem;                              // [2 groups][Q_BYTES]
+  uint8_t* sK = sQ + 2 * SM::Q_BYTES;              // [STAGES][K_BYTES]
+  uint8_t* sV = sK + A4_STAGES * SM::K_BYTES;      // [STAGES][VB]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + A4_STAGES * VB);
+  uint64_t *q_full = bars, *q_empty = bars + 2, *s_full = bars + 4, *p_full = bars + 6, *o_full = bars + 8;
+  uint64_t *k_full = bars + 10, *k_empty = k_full + A4_STAGES, *v_full = k_empty + A4_STAGES, *v_empty = v_full + A4_STAGES;
+  uint64_t* tok = v_empty + A4_STAGES;   // [2] tok[g] completes a phase when the OTHER group has finished an exponent phase
+  uint64_t* p_half = tok + 2;            // [2] first 64 keys of P are in tensor memory
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_half + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_kv = (p.Lk + 127) / 128;
+  const int my_items = (p.n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+#define A6_ITEM(itl_, g_) ((int)blockIdx.x + (2 * (itl_) + (g_)) * (int)gridDim.x)
+  const int U0 = ((my_items + 1) >> 1) * n_kv, U1 = (my_items >> 1) * n_kv;   // score blocks of softmax group 0 / 1
+
+  if (warp == 8) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+      if (HAS_TAIL) { tma_prefetch_desc(&tmQt); tma_prefetch_desc(&tmKt); }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); mbar_init(&s_full[i], 1); mbar_init(&o_full[i], 1);
+        mbar_init(&p_full[i], 4); mbar_init(&p_half[i], 4); mbar_init(&tok[i], 4);   // one elected arrival per softmax warp
+      }
+      for (int i = 0; i < A4_STAGES; ++i) {
+        mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
+      }
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc<512>(tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem0 = *tmem_slot;  // S/P of group g @ g*128, O of group g @ 256 + g*128
+  pdl_launch();
+  pdl_wait();
+
+  if (warp == 9) {
+    // ------------------------------------------------ TMA producer (static ping-pong order; warp-uniform, copies issued under elect.sync)
+    int kc = 0, vc = 0;
+    const int maxU = U0 > U1 ? U0 : U1;
+    int itl = 0, j = 0;   // s = itl * n_kv + j
+    for (int s = 0; s < maxU; ++s) {
+      for (int g = 0; g < 2; ++g) {
+        if (s >= (g ? U1 : U0)) continue;
+        const int item = A6_ITEM(itl, g);
+        const int bh = item / p.n_qt, q0 = (item - bh * p.n_qt) * 128;
+        if (j == 0) {
+          mbar_wait(&q_empty[g], (itl & 1) ^ 1);
+          if (elect_one()) {
+            mbar_expect_tx(&q_full[g], SM::Q_BYTES);
+            tma_load_3d(sQ + g * SM::Q_BYTES, &tmQ, &q_full[g], 0, q0, bh);
+            if (HAS_TAIL) tma_load_3d(sQ + g * SM::Q_BYTES + 16384, &tmQt, &q_full[g], 64, q0, bh);
+          }
+          __syncwarp();
+        }
+        const int st = kc % A4_STAGES;
+        mbar_wait(&k_empty[st], ((kc / A4_STAGES) & 1) ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(&k_full[st], SM::K_BYTES);
+          tma_load_3d(sK + st * SM::K_BYTES, &tmK, &k_full[st], 0, j * 128, bh);
+          if (HAS_TAIL) tma_load_3d(sK + st * SM::K_BYTES + 16384, &tmKt, &k_full[st], 64, j * 128, bh);
+        }
+        __syncwarp();
+        ++kc;
+      }
+      for (int g = 0; g < 2; ++g) {
+        if (s >= (g ? U1 : U0)) continue;
+        const int item = A6_ITEM(itl, g);
+        const int bh = item / p.n_qt;
+        const int st = vc % A4_STAGES;
+        mbar_wait(&v_empty[st], ((vc / A4_STAGES) & 1) ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(&v_full[st], VB);
+          for (int hh = 0; hh < 2; ++hh) tma_load_3d(sV + st * VB + hh * (VB / 2), &tmV, &v_full[st], j * 128 + hh * 64, 0, bh);
+        }
+        __syncwarp();
+        ++vc;
+      }
+      if (++j == n_kv) { j = 0; ++itl; }
+    }
+  } else if (warp == 8) {
+    // ------------------------------------------------ MMA issuer: warp-uniform control flow, one elected lane issues.
+    // Order  S_0(0) S_1(0) | PV_0(0) S_0(1) | PV_1(0) S_1(1) | ...   (S_{u+1} of a group aliases P_u: it is issued after PV_u; in-order tensor pipe)
+    const uint32_t idesc_s = umma_idesc_bf16(128, 128), idesc_o = umma_idesc_bf16(128, p.dvp);
+    int kc = 0, vc = 0;
+    int sj[2] = {0, 0}, sit[2] = {0, 0};   // next score block per group: key block, local item index
+    int pj[2] = {0, 0};                    // next P V per group: key block
+    auto issue_s = [&](int g) {
+      const int itl = sit[g], j = sj[g];
+      if (j == 0) mbar_wait(&q_full[g], itl & 1);
+      const int st = kc % A4_STAGES;
+      mbar_wait(&k_full[st], (kc / A4_STAGES) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t qd = umma_desc_sw128(smem_u32(sQ + g * SM::Q_BYTES)), kd = umma_desc_sw128(smem_u32(sK + st * SM::K_BYTES));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem0 + g * 128, qd + 2 * k, kd + 2 * k, idesc_s, k != 0);
+        if (HAS_TAIL)
+          umma_bf16(tmem0 + g * 128, umma_desc_sw32(smem_u32(sQ + g * SM::Q_BYTES + 16384)), umma_desc_sw32(smem_u32(sK + st * SM::K_BYTES + 16384)), idesc_s, 1);
+        umma_commit(&k_empty[st]);
+        umma_commit(&s_full[g]);
+        if (j == n_kv - 1) umma_commit(&q_empty[g]);
+      }
+      __syncwarp();
+      ++kc;
+      if (++sj[g] == n_kv) { sj[g] = 0; ++sit[g]; }
+    };
+    auto issue_pv = [&](int g, int s) {
+      const int j = pj[g];
+      const int st = vc % A4_STAGES;
+      if (HALF) {
+        mbar_wait(&p_half[g], s & 1);
+        mbar_wait(&v_full[st], (vc / A4_STAGES) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t vd = umma_desc_sw128(smem_u32(sV + st * VB));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16_ts(tmem0 + 256 + g * 128, tmem0 + g * 128 + k * 8, vd + 2 * k, idesc_o, (j != 0) || (k != 0));
+        }
+        __syncwarp();
+      }
+      mbar_wait(&p_full[g], s & 1);
+      if (!HALF) mbar_wait(&v_full[st], (vc / A4_STAGES) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        for (int hh = HALF ? 1 : 0; hh < 2; ++hh) {
+          const uint64_t vd = umma_desc_sw128(smem_u32(sV + st * VB + hh * (VB / 2)));
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16_ts(tmem0 + 256 + g * 128, tmem0 + g * 128 + hh * 32 + k * 8, vd + 2 * k, idesc_o, (j != 0) || ((hh | k) != 0));
+        }
+        umma_commit(&v_empty[st]);
+        umma_commit(&o_full[g]);
+      }
+      __syncwarp();
+      ++vc;
+      if (++pj[g] == n_kv) pj[g] = 0;
+    };
+    const int maxU = U0 > U1 ? U0 : U1;
+    if (U0 > 0) issue_s(0);
+    if (U1 > 0) issue_s(1);
+    for (int s = 0; s < maxU; ++s) {
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        const int Ug = g ? U1 : U0;
+        if (s >= Ug) continue;
+        issue_pv(g, s);
+        if (s + 1 < Ug) issue_s(g);
+      }
+    }
+  } else {
+    // ------------------------------------------------ softmax groups
+    const int g = warp >> 2, lg = warp & 3;
+    const int r = lg * 32 + lane;
+    const uint32_t t_row = static_cast<uint32_t>(lg * 32) << 16;
+    const uint32_t tS = tmem0 + g * 128 + t_row, tO = tmem0 + 256 + g * 128 + t_row;
+    const int Ug = g ? U1 : U0;
+    float m_ref = -INFINITY, l_run = 0.f;
+
+    auto write_item = [&](int item, float l_fin) {  // O / l of a finished item -> global (its last P V has completed)
+      uint32_t orr[64];
+      uint32_t o8[8];
+      tmem_ld_32x64(tO, orr);
+      if (DH > 64) tmem_ld_32x8(tO + 64, o8);
+      tmem_ld_wait();
+      tc_fence_before();
+      const float inv = 1.f / l_fin;
+      const int bh = item / p.n_qt, b = bh / p.H, h = bh - b * p.H;
+      const int qrow = (item - bh * p.n_qt) * 128 + r;
+      if (qrow < p.Lq) {
+        uint4* orow = reinterpret_cast<uint4*>(p.out + ((size_t)b * p.Lq + qrow) * (size_t)(p.H * DH) + h * DH);
+#pragma unroll
+        for (int v = 0; v < 8; ++v)
+          orow[v] = make_uint4(pack_bf16(__uint_as_float(orr[8 * v]) * inv, __uint_as_float(orr[8 * v + 1]) * inv),
+                               pack_bf16(__uint_as_float(orr[8 * v + 2]) * inv, __uint_as_float(orr[8 * v + 3]) * inv),
+                               pack_bf16(__uint_as_float(orr[8 * v + 4]) * inv, __uint_as_float(orr[8 * v + 5]) * inv),
+                               pack_bf16(__uint_as_float(orr[8 * v + 6]) * inv, __uint_as_float(orr[8 * v + 7]) * inv));
+        if (DH > 64)
+          orow[8] = make_uint4(pack_bf16(__uint_as_float(o8[0]) * inv, __uint_as_float(o8[1]) * inv), pack_bf16(__uint_as_float(o8[2]) * inv, __uint_as_float(o8[3]) * inv),
+                               pack_bf16(__uint_as_float(o8[4]) * inv, __uint_as_float(o8[5]) * inv), pack_bf16(__uint_as_float(o8[6]) * inv, __uint_as_float(o8[7]) * inv));
+      }
+    };
+
+    int itl = 0, j = 0;   // s = itl * n_kv + j
+    for (int s = 0; s < Ug; ++s) {
+      const int item = A6_ITEM(itl, g);
+      const int bh = item / p.n_qt, b = bh / p.H;
+      mbar_wait(&s_full[g], s & 1);
+      tc_fence_after();
+      // pass 1: row max over the 128 key columns (the score registers die here: the exponent pass below re-reads S from tensor memory chunk by
+      // chunk, so that nothing but a 32-column window is live across the write-out / rescale branches and the token wait)
+      const int kbase = j * 128;
+      const bool full = (p.key_mask == nullptr) && (kbase + 128 <= p.Lk);
+      uint32_t kw[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};   // one validity bit per key column, identical for every row
+      float mx;
+      {
+        uint32_t sr[128];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) tmem_ld_32x32(tS + q * 32, sr + q * 32);
+        tmem_ld_wait();
+        if (!full) {
+          const uint8_t* km = p.key_mask ? p.key_mask + (size_t)b * p.Lk : nullptr;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int kk = kbase + q * 32 + lane;
+            bool ok = kk < p.Lk;
+            if (ok && km != nullptr) ok = km[kk] != 0;
+            kw[q] = __ballot_sync(0xffffffffu, ok);
+#pragma unroll
+            for (int c = 0; c < 32; ++c) sr[q * 32 + c] = ((kw[q] >> c) & 1u) ? sr[q * 32 + c] : 0xff800000u;  // -inf
+          }
+        }
+        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int c = 0; c < 128; c += 4) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) mx4[e] = fmaxf(mx4[e], __uint_as_float(sr[c + e]));
+        }
+        mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+      }
+      // reference max: fresh for the first key block of an item, afterwards only moved when the row max outgrew it by 2^8
+      float fac = 1.f;
+      bool need = false;
+      const float l_prev = l_run;  // the previous item's sum (retired below when j == 0)
+      if (j == 0) {
+        m_ref = mx;
+        l_run = 0.f;
+      } else {
+        need = (mx - m_ref) * p.scale_log2 > 8.f;  // also true when m_ref = -inf and mx is finite
+        if (need) {
+          fac = (m_ref == -INFINITY) ? 0.f : ex2_approx((m_ref - mx) * p.scale_log2);
+          m_ref = mx;
+          l_run *= fac;
+        }
+      }
+      // Everything that touches O precedes the first P V of this block (arrive on p_half / p_full below): the previous item's write-out (its last
+      // P V completed before this block's S, same in-order pipe) and the in-place rescale of rows whose reference max moved.
+      if (s > 0 && j == 0) {
+        mbar_wait(&o_full[g], (s - 1) & 1);
+        tc_fence_after();
+        write_item(A6_ITEM(itl - 1, g), l_prev);
+      }
+      if (j != 0 && __any_sync(0xffffffffu, need)) {   // warp-collective TMEM access: every lane takes part
+        mbar_wait(&o_full[g], (s - 1) & 1);  // P_{s-1} V_{s-1} has landed
+        tc_fence_after();
+        uint32_t orr[64];
+        tmem_ld_32x64(tO, orr);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 64; ++i) orr[i] = __float_as_uint(__uint_as_float(orr[i]) * fac);
+        tmem_st_32x32(tO, orr);
+        tmem_st_32x32(tO + 32, orr + 32);
+        if (DH > 64) {
+          uint32_t o8[8];
+          tmem_ld_32x8(tO + 64, o8);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o8[i] = __float_as_uint(__uint_as_float(o8[i]) * fac);
+          tmem_st_32x8(tO + 64, o8);
+        }
+        tmem_st_wait();
+      }
+      const float mb = (m_ref == -INFINITY) ? 0.f : m_ref * p.scale_log2;  // fully masked so far: exp2(-inf) = 0
+      if (PP && !(g == 0 && s == 0)) mbar_wait(&tok[g], (g == 0 ? s - 1 : s) & 1);   // MUFU token
+      const unsigned long long sc2 = pack_f32x2(p.scale_log2, p.scale_log2), nmb2 = pack_f32x2(-mb, -mb);
+      unsigned long long sum2a = 0ull, sum2b = 0ull;   // two packed accumulators (4 partial sums)
+      // pass 2: exponentials, 32 columns at a time; chunk q + 1 is in flight (tcgen05.ld) while chunk q is processed.  P chunk q (16 packed
+      // columns at 16 q) lands on score columns that were read before (chunk q / 2), so the in-place overwrite is safe in program order.
+      uint32_t sa[32], sb[32];
+      tmem_ld_32x32(tS, sa);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint32_t* cur = (q & 1) ? sb : sa;
+        uint32_t* nxt = (q & 1) ? sa : sb;
+        tmem_ld_wait();
+        if (q < 3) tmem_ld_32x32(tS + (q + 1) * 32, nxt);
+        if (!full) {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) cur[c] = ((kw[q] >> c) & 1u) ? cur[c] : 0xff800000u;  // -inf
+        }
+        uint32_t pk[16];
+#pragma unroll
+        for (int c = 0; c < 32; c += 4) {
+          const unsigned long long xa = fma_f32x2(pack_f32x2(__uint_as_float(cur[c]), __uint_as_float(cur[c + 1])), sc2, nmb2);
+          const unsigned long long xb = fma_f32x2(pack_f32x2(__uint_as_float(cur[c + 2]), __uint_as_float(cur[c + 3])), sc2, nmb2);
+          float a0, a1, b0, b1;
+          unpack_f32x2(xa, a0, a1);
+          unpack_f32x2(xb, b0, b1);
+          a0 = ex2_approx(a0); a1 = ex2_approx(a1); b0 = ex2_approx(b0); b1 = ex2_approx(b1);
+          sum2a = add_f32x2(sum2a, pack_f32x2(a0, a1));
+          sum2b = add_f32x2(sum2b, pack_f32x2(b0, b1));
+          pk[c >> 1] = pack_bf16(a0, a1);
+          pk[(c >> 1) + 1] = pack_bf16(b0, b1);
+        }
+        tmem_st_32x16(tS + q * 16, pk);
+        if (HALF && q == 1) {   // first 64 keys of P: the MMA warp may start P V
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&p_half[g]);
+        }
+      }
+      if (PP) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tok[g ^ 1]);
+      }
+      {
+        float s0, s1, s2, s3;
+        unpack_f32x2(sum2a, s0, s1);
+        unpack_f32x2(sum2b, s2, s3);
+        l_run += (s0 + s1) + (s2 + s3);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[g]);
+      if (++j == n_kv) { j = 0; ++itl; }
+    }
+    if (Ug > 0) {  // last item of this group
+      mbar_wait(&o_full[g], (Ug - 1) & 1);
+      tc_fence_after();
+      write_item(A6_ITEM((Ug - 1) / n_kv, g), l_run);
+    }
+    if (PP && g == 1) {   // group 0 has n_kv more blocks than group 1 when the CTA's item count is odd: keep handing the token back
+      for (int n = U1; n < U0 - 1; ++n) {
+        mbar_wait(&tok[1], n & 1);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tok[0]);
+      }
+    }
+  }
+#undef A6_ITEM
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc<512>(tmem0);
+}
+
+inline int& opt_attn6() {   // attention kernel generation: 6 (this file; bit 0 on, bit 1 MUFU token, bit 2 P in two halves) or 4 (attention_tc4.cuh)
+  static int v = [] { const char* e = getenv("EZB_ATTN6"); return e ? atoi(e) : 0; }();
+  return v;
+}
+
+inline int attention_tc6(Device& dev, cudaStream_t st, const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* vt, const uint8_t* key_mask,
+                         __nv_bfloat16* out, int B, int H, int Lq, int Lk, int Lkpad, int dh, int dhp, int dvp, float scale) {
+  if (!((dh == 64 && dhp == 64 && dvp == 64) || (dh == 72 && (dhp == 128 || dhp == 80) && dvp == 80))) return fail(EZB_ERR_UNSUPPORTED, "attention_tc6: dh %d dhp %d dvp %d", dh, dhp, dvp);
+  const CUtensorMap *tq, *tk, *tv, *tqt, *tkt;
+  EZB_TRY(dev.tmaps.get3d(q, dhp, Lq, (uint64_t)B * H, dhp, (uint64_t)Lq * dhp, 128, &tq));
+  EZB_TRY(dev.tmaps.get3d(k, dhp, Lk, (uint64_t)B * H, dhp, (uint64_t)Lk * dhp, 128, &tk));
+  EZB_TRY(dev.tmaps.get3d(vt, Lk, dvp, (uint64_t)B * H, Lkpad, (uint64_t)dvp * Lkpad, dvp, &tv));
+  tqt = tq; tkt = tk;
+  if (dh == 72) {
+    EZB_TRY(get3d_sw32(dev.tmaps, q, dhp, Lq, (uint64_t)B * H, dhp, (uint64_t)Lq * dhp, 128, &tqt));
+    EZB_TRY(get3d_sw32(dev.tmaps, k, dhp, Lk, (uint64_t)B * H, dhp, (uint64_t)Lk * dhp, 128, &tkt));
+  }
+  Attn4Params p;
+  p.key_mask = key_mask; p.out = out; p.H = H; p.Lq = Lq; p.Lk = Lk; p.dvp = dvp;
+  p.n_qt = (Lq + 127) / 128;
+  p.n_items = p.n_qt * B * H;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  p.pp = 0; p.dbg = 0; p.dbg_buf = nullptr;
+  const int grid = p.n_items < dev.num_sms ? p.n_items : dev.num_sms;
+  auto go = [&](auto kern, int smem) -> int {
+    EZB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    return launch_k(kern, dim3(grid), dim3(A4_THREADS), smem, st, 1, *tq, *tk, *tv, *tqt, *tkt, p);
+  };
+  const int mode = (opt_attn6() >> 1) & 3;   // bit 0: token, bit 1: halves
+  if (dh == 64) {
+    const int smem = Attn4Smem<64>::total(dvp);
+    switch (mode) {
+      case 0: return go(attn6_kernel<64, 0, 0>, smem);
+      case 1: return go(attn6_kernel<64, 1, 0>, smem);
+      case 2: return go(attn6_kernel<64, 0, 1>, smem);
+      default: return go(attn6_kernel<64, 1, 1>, smem);
+    }
+  }
+  const int smem = Attn4Smem<72>::total(dvp);
+  switch (mode) {
+    case 0: return go(attn6_kernel<72, 0, 0>, smem);
+    case 1: return go(attn6_kernel<72, 1, 0>, smem);
+    case 2: return go(attn6_kernel<72, 0, 1>, smem);
+    default: return go(attn6_kernel<72, 1, 1>, smem);
+  }
+}
+
+}  // namespace ezb

@@ -212,6 +212,10 @@ inline int& opt_attn_res() {   // attention with K / V^T resident per (b, h) (at
   static int v = [] { const char* e = getenv("EZB_ATTN_RES"); return e ? atoi(e) : 0; }();
   return v;
 }
+inline int& opt_attn_pp() {   // attention: the two softmax groups alternate their exponent phases (MUFU token, attention_tc4.cuh)
+  static int v = [] { const char* e = getenv("EZB_ATTN_PP"); return e ? atoi(e) : 0; }();
+  return v;
+}
 inline int& opt_attn_mma2() {   // attention: one MMA-issuing warp per softmax group (attention_tc4.cuh)
   static int v = [] { const char* e = getenv("EZB_ATTN_MMA2"); return e ? atoi(e) : 0; }();
   return v;

@@ -94,3 +94,42 @@ def test_attention_kv_resident(B, H, Lq, Lk, dh, masked):
         test_attention(101, B, H, Lq, Lk, dh, masked)
     finally:
         _lib.check(L.ezb_set_option(b"attn_res", 0))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,H,Lq,Lk,dh,masked", [(2, 4, 500, 500, 72, False), (3, 2, 500, 100, 72, True), (2, 2, 40, 12, 72, True), (1, 16, 1500, 1500, 72, False),
+                                                 (2, 3, 256, 256, 64, False), (8, 16, 500, 500, 72, False), (2, 5, 400, 512, 72, "grow"), (5, 3, 300, 100, 64, True),
+                                                 (16, 16, 500, 500, 72, False), (2, 2, 130, 385, 72, True), (1, 1, 100, 300, 72, False), (1, 3, 128, 128, 72, True)])
+@pytest.mark.parametrize("res", [0, 1])
+def test_attention_mufu_token(B, H, Lq, Lk, dh, masked, res):
+    """attn4 with the exponent phases of the two softmax groups strictly alternating (option attn_pp): CTAs with an odd and an even number of
+    items (the group without a last item keeps passing the token), a single item, one to twelve key blocks, with and without resident K / V^T."""
+    from ezaudio_b200 import _lib
+    L = _lib.lib()
+    _lib.check(L.ezb_set_option(b"attn_pp", 1))
+    _lib.check(L.ezb_set_option(b"attn_res", res))
+    try:
+        test_attention(1, B, H, Lq, Lk, dh, masked)
+        test_attention(101, B, H, Lq, Lk, dh, masked)
+    finally:
+        _lib.check(L.ezb_set_option(b"attn_pp", 0))
+        _lib.check(L.ezb_set_option(b"attn_res", 0))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,H,Lq,Lk,dh,masked", [(2, 4, 500, 500, 72, False), (3, 2, 500, 100, 72, True), (2, 2, 40, 12, 72, True), (1, 16, 1500, 1500, 72, False),
+                                                 (2, 3, 256, 256, 64, False), (8, 16, 500, 500, 72, False), (2, 5, 400, 512, 72, "grow"), (5, 3, 300, 100, 64, True),
+                                                 (16, 16, 500, 500, 72, False), (2, 2, 130, 385, 72, True), (1, 1, 100, 300, 72, False), (1, 3, 128, 128, 72, True)])
+@pytest.mark.parametrize("mode", [1, 3, 5, 7])
+def test_attention_gen6(B, H, Lq, Lk, dh, masked, mode):
+    """attn6 (attention_tc6.cuh: chunked two-pass softmax, packed f32x2 arithmetic; bit 1 of the option = MUFU token between the two softmax
+    groups, bit 2 = P handed to the MMA warp in two halves): every mode on odd / even item counts per CTA, a single item, one to twelve key
+    blocks, key masks, score growth (in-place O rescale before the exponent phase), dh = 64 and 72, both q / k row pitches."""
+    from ezaudio_b200 import _lib
+    L = _lib.lib()
+    _lib.check(L.ezb_set_option(b"attn6", mode))
+    try:
+        test_attention(1, B, H, Lq, Lk, dh, masked)
+        test_attention(101, B, H, Lq, Lk, dh, masked)
+    finally:
+        _lib.check(L.ezb_set_option(b"attn6", 0))
