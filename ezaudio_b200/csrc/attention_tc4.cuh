@@ -62,17 +62,12 @@ struct Attn4Smem {
   static __host__ __device__ constexpr int total(int dvp) { return 1024 + 2 * Q_BYTES + A4_STAGES * K_BYTES + A4_STAGES * v_bytes(dvp) + 512; }
 };
 
-// MMA2 = 1: one MMA-issuing warp PER softmax group (352 threads) instead of one for both.  The CTA-0 cycle counters (profiles/r2/
-// attention_time_attribution.txt) show the single MMA thread busy ~2000 cycles per score block -- ~1150 of bookkeeping (four mbarrier waits at
-// ~90 cycles even when already complete, five tcgen05.commit, fences) plus ~830 blocked behind the tensor pipe while issuing -- for 16 blocks per
-// CTA: 32 K of the kernel's 48 K cycles are serialised on that one thread.  With two issuers each group's chain is independent; K / V^T rings become
-// two 2-deep rings (stage = 2 g + (s & 1)) filled in the same order.
 // RES = 1 ("K/V resident"): one CTA per (b, h); its K and V^T key blocks (at most A4_STAGES = 4, i.e. Lk <= 512) are loaded ONCE and stay in
 // the ring slots while the CTA walks all query tiles of that head.  The MMA thread then has no k_full / v_full waits (after the first pass) and
 // no k_empty / v_empty commits per score block -- it was the longest pole (32 K of 48 K cycles, ~1150 cycles of bookkeeping per block) --
 // every CTA has the same number of blocks (no 4-items-vs-3 tail) and K / V^T are read from L2 once instead of once per query tile.
-template <int DH, int POLY, int DBG = 0, int MMA2 = 0, int RES = 0>
-__global__ void __launch_bounds__(A4_THREADS + 32 * MMA2, 1)
+template <int DH, int POLY, int DBG = 0, int RES = 0>
+__global__ void __launch_bounds__(A4_THREADS, 1)
 attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
              const __grid_constant__ CUtensorMap tmQt, const __grid_constant__ CUtensorMap tmKt, const Attn4Params p) {
   using SM = Attn4Smem<DH>;
@@ -123,7 +118,7 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
   pdl_launch();
   pdl_wait();
 
-  if (warp == 9 + MMA2) {
+  if (warp == 9) {
     // ------------------------------------------------ TMA producer (static ping-pong order).  Warp-uniform loop, copies issued under
     // elect.sync (inside an `if (lane == 0)` region ptxas serialises every UTMALDG / UTCHMMA / UTCBAR through an ELECT ... BRA.U.ANY loop).
     {
@@ -133,7 +128,6 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
       for (int s = 0; s < maxU; ++s) {
         for (int g = 0; g < 2; ++g) {
           if (s >= (g ? U1 : U0)) continue;
-          if (MMA2) kc = (g * 2 + (s & 1)) + A4_STAGES * (s >> 1);   // per-group 2-deep ring: same stage / phase arithmetic as below
           const int item = A4_ITEM(itl, g);
           const int bh = item / p.n_qt, q0 = (item - bh * p.n_qt) * 128;
           if (j == 0) {
@@ -168,7 +162,6 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
         }
         for (int g = 0; g < 2; ++g) {
           if (s >= (g ? U1 : U0)) continue;
-          if (MMA2) vc = (g * 2 + (s & 1)) + A4_STAGES * (s >> 1);
           const int item = A4_ITEM(itl, g);
           const int bh = item / p.n_qt;
           if (RES) {
@@ -194,8 +187,8 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
       }
       if (cnt && lane == 0) p.dbg_buf[6] = (unsigned long long)c_a;
     }
-  } else if (warp == 8 || (MMA2 && warp == 9)) {
-    // ------------------------------------------------ MMA issuer(s): warp-uniform control flow, one elected lane issues
+  } else if (warp == 8) {
+    // ------------------------------------------------ MMA issuer: warp-uniform control flow, one elected lane issues
     {
       const uint32_t idesc_s = umma_idesc_bf16(128, 128), idesc_o = umma_idesc_bf16(128, p.dvp);
       int kc = 0, vc = 0;
@@ -204,7 +197,6 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
       int pj[2] = {0, 0};                    // next P V per group: key block j
       if (cnt) t_begin = clock64();
       auto issue_s = [&](int g, int s) {
-        if (MMA2) kc = (g * 2 + (s & 1)) + A4_STAGES * (s >> 1);
         const int itl = sit[g], j = sj[g];
         if (j == 0) A4_TIMED(c_c, mbar_wait(&q_full[g], itl & 1));
         const int st = RES ? j : kc % A4_STAGES;
@@ -230,7 +222,6 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
         if (++sj[g] == n_kv) { sj[g] = 0; ++sit[g]; }
       };
       auto issue_pv = [&](int g, int s) {
-        if (MMA2) vc = (g * 2 + (s & 1)) + A4_STAGES * (s >> 1);
         const int j = pj[g];
         A4_TIMED(c_a, mbar_wait(&p_full[g], s & 1));
         const int st = RES ? j : vc % A4_STAGES;
@@ -253,14 +244,6 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
         ++vc;
         if (++pj[g] == n_kv) pj[g] = 0;
       };
-      if (MMA2) {   // this warp's own group only
-        const int g = warp - 8, Ug = g ? U1 : U0;
-        if (Ug > 0) issue_s(g, 0);
-        for (int s = 0; s < Ug; ++s) {
-          issue_pv(g, s);
-          if (s + 1 < Ug) issue_s(g, s + 1);
-        }
-      } else {
       const int maxU = U0 > U1 ? U0 : U1;
       if (U0 > 0) issue_s(0, 0);
       if (U1 > 0) issue_s(1, 0);
@@ -272,7 +255,6 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
           issue_pv(g, s);
           if (s + 1 < Ug) issue_s(g, s + 1);
         }
-      }
       }
       if (cnt && warp == 8 && lane == 0) { p.dbg_buf[3] = (unsigned long long)c_a; p.dbg_buf[4] = (unsigned long long)c_b; p.dbg_buf[5] = (unsigned long long)c_c;
                  p.dbg_buf[7] = (unsigned long long)(clock64() - t_begin); }
@@ -469,26 +451,19 @@ inline int attention_tc4(Device& dev, cudaStream_t st, const __nv_bfloat16* q, c
   p.dbg = opt_attn_dbg() & 31;
   p.dbg_buf = (opt_attn_dbg() & 32) ? gemm_dbg_buf() : nullptr;
   const int grid = p.n_items < dev.num_sms ? p.n_items : dev.num_sms;
-  auto go = [&](auto kern, int smem, int threads = A4_THREADS) -> int {
+  auto go = [&](auto kern, int smem) -> int {
     EZB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    return launch_k(kern, dim3(grid), dim3(threads), smem, st, 1, *tq, *tk, *tv, *tqt, *tkt, p);
+    return launch_k(kern, dim3(grid), dim3(A4_THREADS), smem, st, 1, *tq, *tk, *tv, *tqt, *tkt, p);
   };
   const bool poly = opt_attn_poly() != 0;
-  if (opt_attn_dbg() != 0 && dh == 72) {   // profiling instantiations
-    if (opt_attn_mma2()) return go(attn4_kernel<72, 0, 1, 1>, Attn4Smem<72>::total(dvp), A4_THREADS + 32);
-    return go(attn4_kernel<72, 0, 1>, Attn4Smem<72>::total(dvp));
-  }
+  if (opt_attn_dbg() != 0 && dh == 72) return go(attn4_kernel<72, 0, 1>, Attn4Smem<72>::total(dvp));   // profiling instantiation
   if (opt_attn_res() && (Lk + 127) / 128 <= A4_STAGES && !opt_attn_dbg()) {   // K / V^T resident: one CTA per (b, h), all its query tiles
     auto go_res = [&](auto kern, int smem) -> int {
       EZB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       return launch_k(kern, dim3(B * H), dim3(A4_THREADS), smem, st, 1, *tq, *tk, *tv, *tqt, *tkt, p);
     };
-    if (dh == 64) return go_res(attn4_kernel<64, 0, 0, 0, 1>, Attn4Smem<64>::total(dvp));
-    return go_res(attn4_kernel<72, 0, 0, 0, 1>, Attn4Smem<72>::total(dvp));
-  }
-  if (opt_attn_mma2()) {
-    if (dh == 64) return go(attn4_kernel<64, 0, 0, 1>, Attn4Smem<64>::total(dvp), A4_THREADS + 32);
-    return go(attn4_kernel<72, 0, 0, 1>, Attn4Smem<72>::total(dvp), A4_THREADS + 32);
+    if (dh == 64) return go_res(attn4_kernel<64, 0, 0, 1>, Attn4Smem<64>::total(dvp));
+    return go_res(attn4_kernel<72, 0, 0, 1>, Attn4Smem<72>::total(dvp));
   }
   if (dh == 64) {
     EZB_TRY(poly ? go(attn4_kernel<64, 1>, Attn4Smem<64>::total(dvp)) : go(attn4_kernel<64, 0>, Attn4Smem<64>::total(dvp)));

@@ -10,7 +10,13 @@
 //   * MUFU token: the exponent phases of the two groups strictly alternate (G0 #0, G1 #0, G0 #1, ...), so one group's exponentials run at the
 //     full MUFU rate while the other group's P V / next-S MMAs, tcgen05.ld and row max are in flight;
 //   * P is handed to the MMA warp in two halves (64 keys each): the first four P V MMAs run under the second half of the exponentials;
-//   * the previous item's write-out and the (rare) in-place O rescale happen BEFORE the exponent phase (they must precede the first P V of the block).
+//   * the (rare) in-place O rescale happens BEFORE the exponent phase (it must precede the first P V of the block);
+//   * per-item overhead (measured on attn4 from four shapes: time = 0.85 us + 2.2 us x items per CTA + 0.85 us x score blocks per CTA, i.e. 38 % of the
+//     XL self-attention launch and 67 % of the cross-attention launch): the finished tile is written out at the END of its item, inside the bubble in
+//     which the group waits for the next item's first S anyway, through shared memory and ONE TMA store (attn4: nine 16-byte stores per thread, every
+//     warp-level store touching 32 different lines, issued before the group's next hand-off); Q tiles are double-buffered per group and fetched one
+//     item ahead by their own producer warp (attn4: one Q buffer per group, reloaded only after the previous item's last S had completed, behind the
+//     K / V producer's static order); the staging area of the TMA store is the Q buffer of the item that has just ended.  K / V^T rings are 3 deep.
 // Replaces F.scaled_dot_product_attention in src/models/utils/attention.py:107-110 (self: mask None; cross: bool key mask, attention.py:30-37).
 // Layouts as produced by the QKV GEMM epilogue: Q, K [B*H, L, DHP] bf16; V^T [B*H, DVP, Lpad] bf16.  Output [B, Lq, H*dh] bf16 token-major.
 #pragma once
@@ -43,40 +49,63 @@ __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t* r)
 }
 
 // PP: MUFU token between the softmax groups.  HALF: P handed over in two halves.
+constexpr int A6_THREADS = 352;   // warps 0-3 / 4-7 softmax groups, 8 MMA, 9 K / V producer, 10 Q producer
+constexpr int A6_STAGES = 3;
+
+template <int DH>
+struct Attn6Smem {
+  static constexpr int TAIL = DH > 64 ? 4096 : 0;
+  static constexpr int Q_BYTES = 16384 + TAIL;
+  static constexpr int K_BYTES = 16384 + TAIL;
+  static __host__ __device__ constexpr int v_bytes(int dvp) { return 2 * dvp * 128; }
+  static __host__ __device__ constexpr int total(int dvp) { return 1024 + 4 * Q_BYTES + A6_STAGES * K_BYTES + A6_STAGES * v_bytes(dvp) + 512; }
+  static_assert(128 * DH * 2 <= Q_BYTES, "the output tile is staged in a Q buffer");
+};
+
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)),
+               "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 template <int DH, int PP, int HALF>
-__global__ void __launch_bounds__(A4_THREADS, 1)
+__global__ void __launch_bounds__(A6_THREADS, 1)
 attn6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
-             const __grid_constant__ CUtensorMap tmQt, const __grid_constant__ CUtensorMap tmKt, const Attn4Params p) {
-  using SM = Attn4Smem<DH>;
+             const __grid_constant__ CUtensorMap tmQt, const __grid_constant__ CUtensorMap tmKt, const __grid_constant__ CUtensorMap tmO, const Attn4Params p) {
+  using SM = Attn6Smem<DH>;
   constexpr bool HAS_TAIL = DH > 64;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int VB = SM::v_bytes(p.dvp);
-  uint8_t* sQ = smem;                              // [2 groups][Q_BYTES]
-  uint8_t* sK = sQ + 2 * SM::Q_BYTES;              // [STAGES][K_BYTES]
-  uint8_t* sV = sK + A4_STAGES * SM::K_BYTES;      // [STAGES][VB]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + A4_STAGES * VB);
-  uint64_t *q_full = bars, *q_empty = bars + 2, *s_full = bars + 4, *p_full = bars + 6, *o_full = bars + 8;
-  uint64_t *k_full = bars + 10, *k_empty = k_full + A4_STAGES, *v_full = k_empty + A4_STAGES, *v_empty = v_full + A4_STAGES;
-  uint64_t* tok = v_empty + A4_STAGES;   // [2] tok[g] completes a phase when the OTHER group has finished an exponent phase
-  uint64_t* p_half = tok + 2;            // [2] first 64 keys of P are in tensor memory
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_half + 2);
+  uint8_t* sQ = smem;                              // [2 groups][2 buffers][Q_BYTES]; buffer (item & 1) of a group doubles as its output staging tile
+  uint8_t* sK = sQ + 4 * SM::Q_BYTES;              // [STAGES][K_BYTES]
+  uint8_t* sV = sK + A6_STAGES * SM::K_BYTES;      // [STAGES][VB]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + A6_STAGES * VB);
+  uint64_t *q_full = bars, *q_free = bars + 4;     // [g * 2 + buffer]
+  uint64_t *s_full = bars + 8, *p_full = bars + 10, *p_half = bars + 12, *o_full = bars + 14, *tok = bars + 16;
+  uint64_t *k_full = bars + 18, *k_empty = k_full + A6_STAGES, *v_full = k_empty + A6_STAGES, *v_empty = v_full + A6_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(v_empty + A6_STAGES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_kv = (p.Lk + 127) / 128;
   const int my_items = (p.n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 #define A6_ITEM(itl_, g_) ((int)blockIdx.x + (2 * (itl_) + (g_)) * (int)gridDim.x)
-  const int U0 = ((my_items + 1) >> 1) * n_kv, U1 = (my_items >> 1) * n_kv;   // score blocks of softmax group 0 / 1
+  const int I0 = (my_items + 1) >> 1, I1 = my_items >> 1;   // items of softmax group 0 / 1
+  const int U0 = I0 * n_kv, U1 = I1 * n_kv;                 // score blocks of softmax group 0 / 1
 
   if (warp == 8) {
     if (lane == 0) {
-      tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+      tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmO);
       if (HAS_TAIL) { tma_prefetch_desc(&tmQt); tma_prefetch_desc(&tmKt); }
+      for (int i = 0; i < 4; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_free[i], 1); }
       for (int i = 0; i < 2; ++i) {
-        mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); mbar_init(&s_full[i], 1); mbar_init(&o_full[i], 1);
+        mbar_init(&s_full[i], 1); mbar_init(&o_full[i], 1);
         mbar_init(&p_full[i], 4); mbar_init(&p_half[i], 4); mbar_init(&tok[i], 4);   // one elected arrival per softmax warp
       }
-      for (int i = 0; i < A4_STAGES; ++i) {
+      for (int i = 0; i < A6_STAGES; ++i) {
         mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
       }
       fence_mbar_init();
@@ -91,27 +120,36 @@ attn6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
   pdl_launch();
   pdl_wait();
 
-  if (warp == 9) {
-    // ------------------------------------------------ TMA producer (static ping-pong order; warp-uniform, copies issued under elect.sync)
+  if (warp == 10) {
+    // ------------------------------------------------ Q producer: item (g, itl) goes to buffer itl & 1 of its group, one item ahead of its use.
+    // A buffer is free again when the TMA store that staged the output of its previous item (itl - 2) has read it (q_free, arrived by the
+    // storing thread); the first two items of a group find their buffers free.
+    for (int itl = 0; itl < I0; ++itl) {
+      for (int g = 0; g < 2; ++g) {
+        if (itl >= (g ? I1 : I0)) continue;
+        const int bf = g * 2 + (itl & 1), u = itl >> 1;
+        if (u > 0) mbar_wait(&q_free[bf], (u - 1) & 1);
+        if (elect_one()) {
+          const int item = A6_ITEM(itl, g);
+          const int bh = item / p.n_qt, q0 = (item - bh * p.n_qt) * 128;
+          mbar_expect_tx(&q_full[bf], SM::Q_BYTES);
+          tma_load_3d(sQ + bf * SM::Q_BYTES, &tmQ, &q_full[bf], 0, q0, bh);
+          if (HAS_TAIL) tma_load_3d(sQ + bf * SM::Q_BYTES + 16384, &tmQt, &q_full[bf], 64, q0, bh);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 9) {
+    // ------------------------------------------------ K / V^T producer (static ping-pong order; warp-uniform, copies issued under elect.sync)
     int kc = 0, vc = 0;
     const int maxU = U0 > U1 ? U0 : U1;
     int itl = 0, j = 0;   // s = itl * n_kv + j
     for (int s = 0; s < maxU; ++s) {
       for (int g = 0; g < 2; ++g) {
         if (s >= (g ? U1 : U0)) continue;
-        const int item = A6_ITEM(itl, g);
-        const int bh = item / p.n_qt, q0 = (item - bh * p.n_qt) * 128;
-        if (j == 0) {
-          mbar_wait(&q_empty[g], (itl & 1) ^ 1);
-          if (elect_one()) {
-            mbar_expect_tx(&q_full[g], SM::Q_BYTES);
-            tma_load_3d(sQ + g * SM::Q_BYTES, &tmQ, &q_full[g], 0, q0, bh);
-            if (HAS_TAIL) tma_load_3d(sQ + g * SM::Q_BYTES + 16384, &tmQt, &q_full[g], 64, q0, bh);
-          }
-          __syncwarp();
-        }
-        const int st = kc % A4_STAGES;
-        mbar_wait(&k_empty[st], ((kc / A4_STAGES) & 1) ^ 1);
+        const int bh = A6_ITEM(itl, g) / p.n_qt;
+        const int st = kc % A6_STAGES;
+        mbar_wait(&k_empty[st], ((kc / A6_STAGES) & 1) ^ 1);
         if (elect_one()) {
           mbar_expect_tx(&k_full[st], SM::K_BYTES);
           tma_load_3d(sK + st * SM::K_BYTES, &tmK, &k_full[st], 0, j * 128, bh);
@@ -122,10 +160,9 @@ attn6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
       }
       for (int g = 0; g < 2; ++g) {
         if (s >= (g ? U1 : U0)) continue;
-        const int item = A6_ITEM(itl, g);
-        const int bh = item / p.n_qt;
-        const int st = vc % A4_STAGES;
-        mbar_wait(&v_empty[st], ((vc / A4_STAGES) & 1) ^ 1);
+        const int bh = A6_ITEM(itl, g) / p.n_qt;
+        const int st = vc % A6_STAGES;
+        mbar_wait(&v_empty[st], ((vc / A6_STAGES) & 1) ^ 1);
         if (elect_one()) {
           mbar_expect_tx(&v_full[st], VB);
           for (int hh = 0; hh < 2; ++hh) tma_load_3d(sV + st * VB + hh * (VB / 2), &tmV, &v_full[st], j * 128 + hh * 64, 0, bh);
@@ -144,19 +181,19 @@ attn6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
     int pj[2] = {0, 0};                    // next P V per group: key block
     auto issue_s = [&](int g) {
       const int itl = sit[g], j = sj[g];
-      if (j == 0) mbar_wait(&q_full[g], itl & 1);
-      const int st = kc % A4_STAGES;
-      mbar_wait(&k_full[st], (kc / A4_STAGES) & 1);
+      const int bf = g * 2 + (itl & 1);
+      if (j == 0) mbar_wait(&q_full[bf], (itl >> 1) & 1);
+      const int st = kc % A6_STAGES;
+      mbar_wait(&k_full[st], (kc / A6_STAGES) & 1);
       tc_fence_after();
       if (elect_one()) {
-        const uint64_t qd = umma_desc_sw128(smem_u32(sQ + g * SM::Q_BYTES)), kd = umma_desc_sw128(smem_u32(sK + st * SM::K_BYTES));
+        const uint64_t qd = umma_desc_sw128(smem_u32(sQ + bf * SM::Q_BYTES)), kd = umma_desc_sw128(smem_u32(sK + st * SM::K_BYTES));
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma_bf16(tmem0 + g * 128, qd + 2 * k, kd + 2 * k, idesc_s, k != 0);
         if (HAS_TAIL)
-          umma_bf16(tmem0 + g * 128, umma_desc_sw32(smem_u32(sQ + g * SM::Q_BYTES + 16384)), umma_desc_sw32(smem_u32(sK + st * SM::K_BYTES + 16384)), idesc_s, 1);
+          umma_bf16(tmem0 + g * 128, umma_desc_sw32(smem_u32(sQ + bf * SM::Q_BYTES + 16384)), umma_desc_sw32(smem_u32(sK + st * SM::K_BYTES + 16384)), idesc_s, 1);
         umma_commit(&k_empty[st]);
         umma_commit(&s_full[g]);
-        if (j == n_kv - 1) umma_commit(&q_empty[g]);
       }
       __syncwarp();
       ++kc;
@@ -164,10 +201,10 @@ attn6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
     };
     auto issue_pv = [&](int g, int s) {
       const int j = pj[g];
-      const int st = vc % A4_STAGES;
+      const int st = vc % A6_STAGES;
       if (HALF) {
         mbar_wait(&p_half[g], s & 1);
-        mbar_wait(&v_full[st], (vc / A4_STAGES) & 1);
+        mbar_wait(&v_full[st], (vc / A6_STAGES) & 1);
         tc_fence_after();
         if (elect_one()) {
           const uint64_t vd = umma_desc_sw128(smem_u32(sV + st * VB));
@@ -177,7 +214,7 @@ attn6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
         __syncwarp();
       }
       mbar_wait(&p_full[g], s & 1);
-      if (!HALF) mbar_wait(&v_full[st], (vc / A4_STAGES) & 1);
+      if (!HALF) mbar_wait(&v_full[st], (vc / A6_STAGES) & 1);
       tc_fence_after();
       if (elect_one()) {
         for (int hh = HALF ? 1 : 0; hh < 2; ++hh) {
@@ -213,8 +250,10 @@ attn6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
     const uint32_t tS = tmem0 + g * 128 + t_row, tO = tmem0 + 256 + g * 128 + t_row;
     const int Ug = g ? U1 : U0;
     float m_ref = -INFINITY, l_run = 0.f;
+    int release_bf = -1;   // thread r == 0 only: Q buffer whose TMA store has been issued but whose q_free arrival is still owed
 
-    auto write_item = [&](int item, float l_fin) {  // O / l of a finished item -> global (its last P V has completed)
+    // O / l of the item that has just ended -> its own (dead) Q buffer -> one TMA store.  The caller has waited for the item's last P V.
+    auto write_item = [&](int item, int bf, float l_fin) {
       uint32_t orr[64];
       uint32_t o8[8];
       tmem_ld_32x64(tO, orr);
@@ -222,19 +261,23 @@ attn6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
       tmem_ld_wait();
       tc_fence_before();
       const float inv = 1.f / l_fin;
-      const int bh = item / p.n_qt, b = bh / p.H, h = bh - b * p.H;
-      const int qrow = (item - bh * p.n_qt) * 128 + r;
-      if (qrow < p.Lq) {
-        uint4* orow = reinterpret_cast<uint4*>(p.out + ((size_t)b * p.Lq + qrow) * (size_t)(p.H * DH) + h * DH);
+      uint4* orow = reinterpret_cast<uint4*>(sQ + bf * SM::Q_BYTES + r * (DH * 2));
 #pragma unroll
-        for (int v = 0; v < 8; ++v)
-          orow[v] = make_uint4(pack_bf16(__uint_as_float(orr[8 * v]) * inv, __uint_as_float(orr[8 * v + 1]) * inv),
-                               pack_bf16(__uint_as_float(orr[8 * v + 2]) * inv, __uint_as_float(orr[8 * v + 3]) * inv),
-                               pack_bf16(__uint_as_float(orr[8 * v + 4]) * inv, __uint_as_float(orr[8 * v + 5]) * inv),
-                               pack_bf16(__uint_as_float(orr[8 * v + 6]) * inv, __uint_as_float(orr[8 * v + 7]) * inv));
-        if (DH > 64)
-          orow[8] = make_uint4(pack_bf16(__uint_as_float(o8[0]) * inv, __uint_as_float(o8[1]) * inv), pack_bf16(__uint_as_float(o8[2]) * inv, __uint_as_float(o8[3]) * inv),
-                               pack_bf16(__uint_as_float(o8[4]) * inv, __uint_as_float(o8[5]) * inv), pack_bf16(__uint_as_float(o8[6]) * inv, __uint_as_float(o8[7]) * inv));
+      for (int v = 0; v < 8; ++v)
+        orow[v] = make_uint4(pack_bf16(__uint_as_float(orr[8 * v]) * inv, __uint_as_float(orr[8 * v + 1]) * inv),
+                             pack_bf16(__uint_as_float(orr[8 * v + 2]) * inv, __uint_as_float(orr[8 * v + 3]) * inv),
+                             pack_bf16(__uint_as_float(orr[8 * v + 4]) * inv, __uint_as_float(orr[8 * v + 5]) * inv),
+                             pack_bf16(__uint_as_float(orr[8 * v + 6]) * inv, __uint_as_float(orr[8 * v + 7]) * inv));
+      if (DH > 64)
+        orow[8] = make_uint4(pack_bf16(__uint_as_float(o8[0]) * inv, __uint_as_float(o8[1]) * inv), pack_bf16(__uint_as_float(o8[2]) * inv, __uint_as_float(o8[3]) * inv),
+                             pack_bf16(__uint_as_float(o8[4]) * inv, __uint_as_float(o8[5]) * inv), pack_bf16(__uint_as_float(o8[6]) * inv, __uint_as_float(o8[7]) * inv));
+      fence_proxy_async_smem();          // generic-proxy writes -> visible to the TMA (async proxy) read
+      named_bar_sync(1 + g, 128);        // all 128 rows of the tile are staged
+      if (r == 0) {
+        const int bh = item / p.n_qt, b = bh / p.H, h = bh - b * p.H;
+        tma_store_3d(&tmO, sQ + bf * SM::Q_BYTES, h * DH, (item - bh * p.n_qt) * 128, b);   // rows >= Lq are clipped by the tensor map
+        bulk_commit();
+        release_bf = bf;
       }
     };
 
@@ -242,13 +285,30 @@ attn6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
     for (int s = 0; s < Ug; ++s) {
       const int item = A6_ITEM(itl, g);
       const int bh = item / p.n_qt, b = bh / p.H;
-      mbar_wait(&s_full[g], s & 1);
-      tc_fence_after();
-      // pass 1: row max over the 128 key columns (the score registers die here: the exponent pass below re-reads S from tensor memory chunk by
-      // chunk, so that nothing but a 32-column window is live across the write-out / rescale branches and the token wait)
+      // key validity bits of this block (one per key column, identical for every row), fetched BEFORE the S wait: with a key mask they come from
+      // global memory (cross-attention: a dependent ~800-cycle load per item if issued after S has arrived)
       const int kbase = j * 128;
       const bool full = (p.key_mask == nullptr) && (kbase + 128 <= p.Lk);
-      uint32_t kw[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};   // one validity bit per key column, identical for every row
+      uint32_t kw[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+      if (!full) {
+        const uint8_t* km = p.key_mask ? p.key_mask + (size_t)b * p.Lk : nullptr;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int kk = kbase + q * 32 + lane;
+          bool ok = kk < p.Lk;
+          if (ok && km != nullptr) ok = km[kk] != 0;
+          kw[q] = __ballot_sync(0xffffffffu, ok);
+        }
+      }
+      mbar_wait(&s_full[g], s & 1);
+      tc_fence_after();
+      if (release_bf >= 0) {   // the store issued at the end of the previous item has long read its staging tile: hand the buffer back
+        bulk_wait_read0();
+        mbar_arrive(&q_free[release_bf]);
+        release_bf = -1;
+      }
+      // pass 1: row max over the 128 key columns (the score registers die here: the exponent pass below re-reads S from tensor memory chunk by
+      // chunk, so that nothing but a 32-column window is live across the write-out / rescale branches and the token wait)
       float mx;
       {
         uint32_t sr[128];
@@ -256,13 +316,8 @@ attn6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
         for (int q = 0; q < 4; ++q) tmem_ld_32x32(tS + q * 32, sr + q * 32);
         tmem_ld_wait();
         if (!full) {
-          const uint8_t* km = p.key_mask ? p.key_mask + (size_t)b * p.Lk : nullptr;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const int kk = kbase + q * 32 + lane;
-            bool ok = kk < p.Lk;
-            if (ok && km != nullptr) ok = km[kk] != 0;
-            kw[q] = __ballot_sync(0xffffffffu, ok);
 #pragma unroll
             for (int c = 0; c < 32; ++c) sr[q * 32 + c] = ((kw[q] >> c) & 1u) ? sr[q * 32 + c] : 0xff800000u;  // -inf
           }
@@ -278,7 +333,6 @@ attn6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
       // reference max: fresh for the first key block of an item, afterwards only moved when the row max outgrew it by 2^8
       float fac = 1.f;
       bool need = false;
-      const float l_prev = l_run;  // the previous item's sum (retired below when j == 0)
       if (j == 0) {
         m_ref = mx;
         l_run = 0.f;
@@ -289,13 +343,6 @@ attn6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
           m_ref = mx;
           l_run *= fac;
         }
-      }
-      // Everything that touches O precedes the first P V of this block (arrive on p_half / p_full below): the previous item's write-out (its last
-      // P V completed before this block's S, same in-order pipe) and the in-place rescale of rows whose reference max moved.
-      if (s > 0 && j == 0) {
-        mbar_wait(&o_full[g], (s - 1) & 1);
-        tc_fence_after();
-        write_item(A6_ITEM(itl - 1, g), l_prev);
       }
       if (j != 0 && __any_sync(0xffffffffu, need)) {   // warp-collective TMEM access: every lane takes part
         mbar_wait(&o_full[g], (s - 1) & 1);  // P_{s-1} V_{s-1} has landed
@@ -371,12 +418,12 @@ attn6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[g]);
+      if (j == n_kv - 1) {   // the item ends here: retire it inside the bubble before the next item's first S (its last P V is the next thing on the pipe)
+        mbar_wait(&o_full[g], s & 1);
+        tc_fence_after();
+        write_item(item, g * 2 + (itl & 1), l_run);
+      }
       if (++j == n_kv) { j = 0; ++itl; }
-    }
-    if (Ug > 0) {  // last item of this group
-      mbar_wait(&o_full[g], (Ug - 1) & 1);
-      tc_fence_after();
-      write_item(A6_ITEM((Ug - 1) / n_kv, g), l_run);
     }
     if (PP && g == 1) {   // group 0 has n_kv more blocks than group 1 when the CTA's item count is odd: keep handing the token back
       for (int n = U1; n < U0 - 1; ++n) {
@@ -385,6 +432,7 @@ attn6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
         if (lane == 0) mbar_arrive(&tok[0]);
       }
     }
+    if (r == 0) bulk_wait0();   // the last store has left shared memory (and completed) before the CTA goes away
   }
 #undef A6_ITEM
   tc_fence_before();
@@ -393,17 +441,18 @@ attn6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
 }
 
 inline int& opt_attn6() {   // attention kernel generation: 6 (this file; bit 0 on, bit 1 MUFU token, bit 2 P in two halves) or 4 (attention_tc4.cuh)
-  static int v = [] { const char* e = getenv("EZB_ATTN6"); return e ? atoi(e) : 0; }();
+  static int v = [] { const char* e = getenv("EZB_ATTN6"); return e ? atoi(e) : 5; }();   // default: generation 6, P in two halves (call 19: self 23.1 -> 21.5 us, cross 13.4 -> 10.2 us)
   return v;
 }
 
 inline int attention_tc6(Device& dev, cudaStream_t st, const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* vt, const uint8_t* key_mask,
                          __nv_bfloat16* out, int B, int H, int Lq, int Lk, int Lkpad, int dh, int dhp, int dvp, float scale) {
   if (!((dh == 64 && dhp == 64 && dvp == 64) || (dh == 72 && (dhp == 128 || dhp == 80) && dvp == 80))) return fail(EZB_ERR_UNSUPPORTED, "attention_tc6: dh %d dhp %d dvp %d", dh, dhp, dvp);
-  const CUtensorMap *tq, *tk, *tv, *tqt, *tkt;
+  const CUtensorMap *tq, *tk, *tv, *tqt, *tkt, *to;
   EZB_TRY(dev.tmaps.get3d(q, dhp, Lq, (uint64_t)B * H, dhp, (uint64_t)Lq * dhp, 128, &tq));
   EZB_TRY(dev.tmaps.get3d(k, dhp, Lk, (uint64_t)B * H, dhp, (uint64_t)Lk * dhp, 128, &tk));
   EZB_TRY(dev.tmaps.get3d(vt, Lk, dvp, (uint64_t)B * H, Lkpad, (uint64_t)dvp * Lkpad, dvp, &tv));
+  EZB_TRY(get3d_plain(dev.tmaps, out, (uint64_t)H * dh, Lq, B, (uint64_t)H * dh, (uint64_t)Lq * H * dh, dh, 128, &to));
   tqt = tq; tkt = tk;
   if (dh == 72) {
     EZB_TRY(get3d_sw32(dev.tmaps, q, dhp, Lq, (uint64_t)B * H, dhp, (uint64_t)Lq * dhp, 128, &tqt));
@@ -418,11 +467,11 @@ inline int attention_tc6(Device& dev, cudaStream_t st, const __nv_bfloat16* q, c
   const int grid = p.n_items < dev.num_sms ? p.n_items : dev.num_sms;
   auto go = [&](auto kern, int smem) -> int {
     EZB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    return launch_k(kern, dim3(grid), dim3(A4_THREADS), smem, st, 1, *tq, *tk, *tv, *tqt, *tkt, p);
+    return launch_k(kern, dim3(grid), dim3(A6_THREADS), smem, st, 1, *tq, *tk, *tv, *tqt, *tkt, *to, p);
   };
   const int mode = (opt_attn6() >> 1) & 3;   // bit 0: token, bit 1: halves
   if (dh == 64) {
-    const int smem = Attn4Smem<64>::total(dvp);
+    const int smem = Attn6Smem<64>::total(dvp);
     switch (mode) {
       case 0: return go(attn6_kernel<64, 0, 0>, smem);
       case 1: return go(attn6_kernel<64, 1, 0>, smem);
@@ -430,7 +479,7 @@ inline int attention_tc6(Device& dev, cudaStream_t st, const __nv_bfloat16* q, c
       default: return go(attn6_kernel<64, 1, 1>, smem);
     }
   }
-  const int smem = Attn4Smem<72>::total(dvp);
+  const int smem = Attn6Smem<72>::total(dvp);
   switch (mode) {
     case 0: return go(attn6_kernel<72, 0, 0>, smem);
     case 1: return go(attn6_kernel<72, 1, 0>, smem);

@@ -8,7 +8,6 @@
 
 #include "attention_simt.cuh"
 #include "attention_tc4.cuh"
-#include "attention_tc5.cuh"
 #include "attention_tc6.cuh"
 #include "host.cuh"
 #include "gemm_ln.cuh"
@@ -651,7 +650,6 @@ struct Dit {
       return EZB_OK;
     }
     if (opt_attn6() & 1) return attention_tc6(*dev, st, q16_, k16_, vt16_, mask, attn_out, B, H, Lq, Lk, Lkpad, dh, DHP, DVP, scale);
-    if (opt_attn5()) return attention_tc5(*dev, st, q16_, k16_, vt16_, mask, attn_out, B, H, Lq, Lk, Lkpad, dh, DHP, DVP, scale);
     return attention_tc4(*dev, st, q16_, k16_, vt16_, mask, attn_out, B, H, Lq, Lk, Lkpad, dh, DHP, DVP, scale);
   }
 

@@ -256,9 +256,6 @@ EZB_API int ezb_test_attention(int device, const void* q, const void* k, const v
   if (impl == 6 || (impl == 1 && (opt_attn6() & 1)))
     return attention_tc6(device_ctx(device), ST(stream), reinterpret_cast<const __nv_bfloat16*>(q), reinterpret_cast<const __nv_bfloat16*>(k),
                          reinterpret_cast<const __nv_bfloat16*>(v), key_mask, reinterpret_cast<__nv_bfloat16*>(out), B, H, Lq, Lk, lkpad, dh, dhp, dvp, scale);
-  if (impl == 5 || (impl == 1 && opt_attn5()))
-    return attention_tc5(device_ctx(device), ST(stream), reinterpret_cast<const __nv_bfloat16*>(q), reinterpret_cast<const __nv_bfloat16*>(k),
-                         reinterpret_cast<const __nv_bfloat16*>(v), key_mask, reinterpret_cast<__nv_bfloat16*>(out), B, H, Lq, Lk, lkpad, dh, dhp, dvp, scale);
   return attention_tc4(device_ctx(device), ST(stream), reinterpret_cast<const __nv_bfloat16*>(q), reinterpret_cast<const __nv_bfloat16*>(k),
                        reinterpret_cast<const __nv_bfloat16*>(v), key_mask, reinterpret_cast<__nv_bfloat16*>(out), B, H, Lq, Lk, lkpad, dh, dhp, dvp, scale);
 }
@@ -280,12 +277,10 @@ EZB_API int ezb_set_option(const char* name, int value) {
   if (name && !strcmp(name, "attn_res")) { opt_attn_res() = value; return EZB_OK; }
   if (name && !strcmp(name, "attn_pp")) { opt_attn_pp() = value; return EZB_OK; }
   if (name && !strcmp(name, "attn6")) { opt_attn6() = value; return EZB_OK; }
-  if (name && !strcmp(name, "attn_mma2")) { opt_attn_mma2() = value; return EZB_OK; }
   if (name && !strcmp(name, "attn_dbg")) { opt_attn_dbg() = value; return EZB_OK; }
   if (name && !strcmp(name, "ln_variant")) { opt_ln_variant() = value; return EZB_OK; }
   if (name && !strcmp(name, "mlp_fused")) { opt_mlp_fused() = value; return EZB_OK; }
   if (name && !strcmp(name, "heads_direct")) { opt_heads_direct() = value; return EZB_OK; }
-  if (name && !strcmp(name, "attn5")) { opt_attn5() = value; return EZB_OK; }
   if (name && !strcmp(name, "dhp80")) { opt_dhp80() = value; return EZB_OK; }
   if (name && !strcmp(name, "ln_fold")) { opt_fold() = value; return EZB_OK; }
   if (name && !strcmp(name, "skip")) { opt_skip() = value; return EZB_OK; }

@@ -86,7 +86,7 @@ inline PFN_encodeTiled get_encode() {
 
 // bf16 tensor, innermost dim first; 128-byte swizzle, zero fill out of bounds.
 inline int make_tmap(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes /*rank-1*/,
-                     const uint32_t* box, bool swizzle32 = false) {
+                     const uint32_t* box, int swizzle = 0 /* 0: SWIZZLE_128B, 1: SWIZZLE_32B, 2: none (dense box rows in shared memory) */) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) return fail(EZB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
   cuuint64_t gd[5], gs[5];
@@ -101,7 +101,7 @@ inline int make_tmap(CUtensorMap* out, const void* ptr, int rank, const uint64_t
   for (int i = 0; i + 1 < rank; ++i)
     if (gs[i] % 16) return fail(EZB_ERR_ARG, "TMA stride %llu not a multiple of 16 B", (unsigned long long)gs[i]);
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   swizzle32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   swizzle == 1 ? CU_TENSOR_MAP_SWIZZLE_32B : swizzle == 2 ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(EZB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d): rank %d dims %llu,%llu box %u,%u", (int)r, rank,
                                      (unsigned long long)gd[0], (unsigned long long)gd[1], bx[0], bx[1]);
@@ -164,6 +164,22 @@ inline int get3d_sw32(TmapCache& c, const void* ptr, uint64_t inner, uint64_t ro
   return EZB_OK;
 }
 
+// 3-D [batch, rows, inner] bf16 map with an un-swizzled {box_inner, box_rows, 1} box (dense rows in shared memory): TMA stores of attention output tiles
+inline int get3d_plain(TmapCache& c, const void* ptr, uint64_t inner, uint64_t rows, uint64_t batch, uint64_t ld_row, uint64_t ld_batch, uint32_t box_inner,
+                       uint32_t box_rows, const CUtensorMap** out) {
+  TmapCache::Key k(ptr, inner, rows, batch, ld_row * 1000003ull + ld_batch, box_rows, 1000 + box_inner);
+  auto it = c.maps.find(k);
+  if (it == c.maps.end()) {
+    CUtensorMap m;
+    uint64_t dims[3] = {inner, rows, batch}, str[2] = {ld_row * 2, ld_batch * 2};
+    uint32_t box[3] = {box_inner, box_rows, 1};
+    EZB_TRY(make_tmap(&m, ptr, 3, dims, str, box, 2));
+    it = c.maps.emplace(k, m).first;
+  }
+  *out = &it->second;
+  return EZB_OK;
+}
+
 inline int make_tmap4_strided(CUtensorMap* out, const void* ptr, uint64_t C, uint64_t stride, uint64_t Tq, uint64_t B, uint64_t ldc) {
   // activations [B, Tq*stride, ldc] viewed as [B, Tq, stride, C]: box {64 channels, 1 phase, 128 rows, 1 clip}
   uint64_t dims[4] = {C, stride, Tq, B}, str[3] = {ldc * 2, stride * ldc * 2, Tq * stride * ldc * 2};
@@ -214,10 +230,6 @@ inline int& opt_attn_res() {   // attention with K / V^T resident per (b, h) (at
 }
 inline int& opt_attn_pp() {   // attention: the two softmax groups alternate their exponent phases (MUFU token, attention_tc4.cuh)
   static int v = [] { const char* e = getenv("EZB_ATTN_PP"); return e ? atoi(e) : 0; }();
-  return v;
-}
-inline int& opt_attn_mma2() {   // attention: one MMA-issuing warp per softmax group (attention_tc4.cuh)
-  static int v = [] { const char* e = getenv("EZB_ATTN_MMA2"); return e ? atoi(e) : 0; }();
   return v;
 }
 inline int& opt_attn_dbg() {

@@ -78,10 +78,12 @@ __global__ void latent_pack_kernel(const float* __restrict__ z, __nv_bfloat16* _
 // last layer: Conv1d(C -> 1, k=7, pad 3, no bias) on the snake-activated channels-last tensor; w folded fp32 [7][C] (C = 128 shipped).
 // HBM-bound (245 MB of bf16 activations per 4 clips).  One warp = 32 consecutive output samples: every input row (t0-3 .. t0+34) is read
 // once with 8-byte loads (lane = 4 channels, a 256-byte row per warp), multiplied into the up-to-7 outputs it feeds (weights in
-// registers), and the 32 per-lane partial sums are reduced with a 31-shuffle transpose-reduction so that lane i ends up with output i
-// (first version: scalar bf16 staging + one 5-shuffle reduction per output, 1045 us; this one is bound by the activation read).
-__global__ void __launch_bounds__(128) wave_out_kernel(const __nv_bfloat16* __restrict__ act, const float* __restrict__ w, float* __restrict__ wav, int C, int T,
-                                                       int kmul) {
+// registers), and the 32 per-lane partial sums are reduced with a 31-shuffle transpose-reduction so that lane i ends up with output i.
+// Round 2: the rows are fetched in two batches of 19 unconditional loads (row index clamped, contribution zeroed by a select) -- the
+// round-1 loop tested `0 <= t < T` around every load, which kept ptxas from hoisting any of them: each warp had ONE 256-byte request in
+// flight (488 us = 0.5 TB/s for the 4 x 10 s decode).  Same accumulation order, bit-identical output.
+template <int KMUL>
+__global__ void __launch_bounds__(128, 3) wave_out_kernel(const __nv_bfloat16* __restrict__ act, const float* __restrict__ w, float* __restrict__ wav, int C, int T) {
   const int lane = threadIdx.x & 31;
   const int chunk = blockIdx.x * 4 + (threadIdx.x >> 5);
   const int b = blockIdx.y, t0 = chunk * 32;
@@ -90,33 +92,47 @@ __global__ void __launch_bounds__(128) wave_out_kernel(const __nv_bfloat16* __re
 #pragma unroll
   for (int i = 0; i < 32; ++i) acc[i] = 0.f;
   for (int c0 = lane * 4; c0 < C; c0 += 128) {   // C = 128 in the shipped model: one pass
-    const __nv_bfloat16* ab = act + (size_t)b * T * kmul * C + c0;
+    const __nv_bfloat16* ab = act + (size_t)b * T * KMUL * C + c0;
     float wk[7][4];
 #pragma unroll
     for (int k = 0; k < 7; ++k) {
       const float4 t = *reinterpret_cast<const float4*>(w + k * C + c0);
       wk[k][0] = t.x; wk[k][1] = t.y; wk[k][2] = t.z; wk[k][3] = t.w;
     }
+    constexpr int NB = KMUL == 3 ? 10 : 19;   // rows per batch of loads
 #pragma unroll
-    for (int rr = 0; rr < 38; ++rr) {       // input sample t0 - 3 + rr feeds outputs o = rr - k, k = 0..6 (tap k reads x[t + k - 3])
-      const int t = t0 - 3 + rr;
-      float x[4] = {0.f, 0.f, 0.f, 0.f};
-      if (t >= 0 && t < T) {
-        const __nv_bfloat16* row = ab + (size_t)t * kmul * C;
-        const uint2 u = __ldg(reinterpret_cast<const uint2*>(row));
-        x[0] = __uint_as_float(u.x << 16); x[1] = __uint_as_float(u.x & 0xffff0000u);
-        x[2] = __uint_as_float(u.y << 16); x[3] = __uint_as_float(u.y & 0xffff0000u);
-        if (kmul == 3) {  // split-bf16 operand: hi | lo | hi
-          const uint2 v = __ldg(reinterpret_cast<const uint2*>(row + C));
-          x[0] += __uint_as_float(v.x << 16); x[1] += __uint_as_float(v.x & 0xffff0000u);
-          x[2] += __uint_as_float(v.y << 16); x[3] += __uint_as_float(v.y & 0xffff0000u);
+    for (int r0 = 0; r0 < 38; r0 += NB) {   // input sample t0 - 3 + rr, rr = 0..37, feeds outputs o = rr - k, k = 0..6 (tap k reads x[t + k - 3])
+      uint2 u[NB], v[KMUL == 3 ? NB : 1];
+#pragma unroll
+      for (int i = 0; i < NB; ++i) {
+        if (r0 + i >= 38) continue;
+        const int t = t0 - 3 + r0 + i;
+        const int tc = t < 0 ? 0 : (t >= T ? T - 1 : t);
+        const __nv_bfloat16* row = ab + (size_t)tc * KMUL * C;
+        u[i] = __ldg(reinterpret_cast<const uint2*>(row));
+        if (KMUL == 3) v[i] = __ldg(reinterpret_cast<const uint2*>(row + C));   // split-bf16 operand: hi | lo | hi
+      }
+#pragma unroll
+      for (int i = 0; i < NB; ++i) {
+        if (r0 + i >= 38) continue;
+        const int rr = r0 + i, t = t0 - 3 + rr;
+        const bool ok = t >= 0 && t < T;
+        float x[4];
+        x[0] = __uint_as_float(u[i].x << 16); x[1] = __uint_as_float(u[i].x & 0xffff0000u);
+        x[2] = __uint_as_float(u[i].y << 16); x[3] = __uint_as_float(u[i].y & 0xffff0000u);
+        if (KMUL == 3) {
+          x[0] += __uint_as_float(v[i].x << 16); x[1] += __uint_as_float(v[i].x & 0xffff0000u);
+          x[2] += __uint_as_float(v[i].y << 16); x[3] += __uint_as_float(v[i].y & 0xffff0000u);
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) x[e] = ok ? x[e] : 0.f;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) {
+          const int o = rr - k;
+          if (o >= 0 && o < 32) acc[o] = fmaf(wk[k][0], x[0], fmaf(wk[k][1], x[1], fmaf(wk[k][2], x[2], fmaf(wk[k][3], x[3], acc[o]))));
         }
       }
-#pragma unroll
-      for (int k = 0; k < 7; ++k) {
-        const int o = rr - k;
-        if (o >= 0 && o < 32) acc[o] = fmaf(wk[k][0], x[0], fmaf(wk[k][1], x[1], fmaf(wk[k][2], x[2], fmaf(wk[k][3], x[3], acc[o]))));
-      }
+      asm volatile("" ::: "memory");   // keep the next batch's loads behind this batch's arithmetic (register budget)
     }
   }
   // transpose-reduction: after the five steps lane i holds the sum over lanes of acc[i]
@@ -491,7 +507,8 @@ struct Vae {
     if (C0 % 4) return fail(EZB_ERR_UNSUPPORTED, "wave_out: %d channels in the last stage (multiple of 4 expected)", C0);
     dim3 g2((T + 127) / 128, B);
     ++launch_counter();
-    wave_out_kernel<<<g2, 128, 0, st>>>(cur, out_w, wav, C0, T, kmul);
+    if (kmul == 3) wave_out_kernel<3><<<g2, 128, 0, st>>>(cur, out_w, wav, C0, T);
+    else wave_out_kernel<1><<<g2, 128, 0, st>>>(cur, out_w, wav, C0, T);
     EZB_CUDA(cudaGetLastError());
     return EZB_OK;
   }

@@ -41,17 +41,14 @@ def run(B, H, Lq, Lk, dh, masked, label, impl, reps=20):
 
 
 MMA2 = int(sys.argv[1]) if len(sys.argv) > 1 else 0
-L.ezb_set_option(b"attn_mma2", MMA2 & 1)
 L.ezb_set_option(b"attn_res", (MMA2 >> 1) & 1)
 L.ezb_set_option(b"attn_poly", (MMA2 >> 2) & 1)
 L.ezb_set_option(b"attn_pp", (MMA2 >> 3) & 1)
 A6 = int(sys.argv[2]) if len(sys.argv) > 2 else 0   # attention_tc6.cuh: 1 on, +2 MUFU token, +4 P in two halves
 L.ezb_set_option(b"attn6", A6)
 print("attn6 =", A6)
-print("attn_mma2 =", MMA2 & 1, "attn_res =", (MMA2 >> 1) & 1, "attn_poly =", (MMA2 >> 2) & 1, "attn_pp =", (MMA2 >> 3) & 1)
-for impl in (1, 5, 101):
-    if (MMA2 or A6) and impl == 5:
-        continue
+print("attn_res =", (MMA2 >> 1) & 1, "attn_poly =", (MMA2 >> 2) & 1, "attn_pp =", (MMA2 >> 3) & 1)
+for impl in (1, 101):
     run(8, 16, 500, 500, 72, False, "self XL", impl)
     run(8, 16, 500, 100, 72, True, "cross XL", impl)
     run(4, 16, 1500, 1500, 72, False, "self XL 30s", impl)

@@ -11,9 +11,7 @@ from ezaudio_b200 import _lib  # noqa: E402
 import ctypes as C
 L = _lib.lib()
 _lib.check(L.ezb_set_option(b"gemm_debug", 1))
-if len(sys.argv) > 1:
-    _lib.check(L.ezb_set_option(b"attn_mma2", int(sys.argv[1])))
-    print("attn_mma2 =", sys.argv[1])   # allocates the 8-counter debug buffer
+_lib.check(L.ezb_set_option(b"attn6", 0))   # the profiling instantiation belongs to the generation-4 kernel
 B, H, Lq, Lk, dh = 8, 16, 500, 500, 72
 dhp, dvp, lkp = 128, 80, 504
 q = torch.randn(B * H, Lq, dhp, device="cuda").bfloat16()

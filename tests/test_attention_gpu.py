@@ -6,6 +6,8 @@ import math
 import pytest
 import torch
 
+ATTN6_DEFAULT = 5   # csrc/attention_tc6.cuh opt_attn6(): generation-6 kernel with P handed over in two halves
+
 pytestmark = pytest.mark.gpu
 
 
@@ -17,9 +19,9 @@ def _ref(q, k, v, mask):
     return o.permute(0, 2, 1, 3).reshape(q.shape[0], q.shape[2], -1)
 
 
-# 0 = fp32 CUDA-core kernel (parity mode); 1 = tcgen05 two-tile ping-pong kernel (attention_tc4.cuh); 5 = the same with two threads per query row
-# (attention_tc5.cuh); +100 = q / k rows of 80 elements for dh = 72 (160-byte pitch) instead of 128
-@pytest.mark.parametrize("impl", [0, 1, 5, 101, 105])
+# 0 = fp32 CUDA-core kernel (parity mode); 1 = the tcgen05 kernel the product uses (generation 6, attention_tc6.cuh, unless the option attn6 says
+# otherwise); 4 = generation 4 (attention_tc4.cuh); +100 = q / k rows of 80 elements for dh = 72 (160-byte pitch) instead of 128
+@pytest.mark.parametrize("impl", [0, 1, 4, 101, 104])
 @pytest.mark.parametrize("B,H,Lq,Lk,dh,masked", [(2, 4, 500, 500, 72, False), (2, 3, 256, 256, 64, False), (3, 2, 500, 100, 72, True),
                                                  (2, 2, 40, 12, 72, True), (1, 2, 130, 130, 64, False), (1, 16, 1500, 1500, 72, False),
                                                  (2, 2, 37, 100, 64, True), (8, 16, 500, 500, 72, False), (2, 5, 700, 700, 72, "grow")])
@@ -68,19 +70,6 @@ def _run(L, _lib, args, mask, out, B, H, Lq, Lk, dh, impl):
 
 
 @pytest.mark.parametrize("B,H,Lq,Lk,dh,masked", [(2, 4, 500, 500, 72, False), (3, 2, 500, 100, 72, True), (2, 2, 40, 12, 72, True), (1, 16, 1500, 1500, 72, False),
-                                                 (2, 3, 256, 256, 64, False), (8, 16, 500, 500, 72, False), (2, 5, 700, 700, 72, "grow"), (5, 3, 300, 100, 64, True)])
-def test_attention_two_mma_warps(B, H, Lq, Lk, dh, masked):
-    """attn4 with one MMA-issuing warp per softmax group (option attn_mma2): odd item counts per CTA (groups of unequal length), masks, growth."""
-    from ezaudio_b200 import _lib
-    L = _lib.lib()
-    _lib.check(L.ezb_set_option(b"attn_mma2", 1))
-    try:
-        test_attention(1, B, H, Lq, Lk, dh, masked)
-    finally:
-        _lib.check(L.ezb_set_option(b"attn_mma2", 0))
-
-
-@pytest.mark.parametrize("B,H,Lq,Lk,dh,masked", [(2, 4, 500, 500, 72, False), (3, 2, 500, 100, 72, True), (2, 2, 40, 12, 72, True), (1, 16, 1500, 1500, 72, False),
                                                  (2, 3, 256, 256, 64, False), (8, 16, 500, 500, 72, False), (2, 5, 400, 512, 72, "grow"), (5, 3, 300, 100, 64, True),
                                                  (16, 16, 500, 500, 72, False), (2, 2, 130, 385, 72, True)])
 def test_attention_kv_resident(B, H, Lq, Lk, dh, masked):
@@ -88,12 +77,14 @@ def test_attention_kv_resident(B, H, Lq, Lk, dh, masked):
     of query tiles per head, one to four key blocks, more heads than SMs (two waves of CTAs), masks, growth."""
     from ezaudio_b200 import _lib
     L = _lib.lib()
+    _lib.check(L.ezb_set_option(b"attn6", 0))   # generation-4 kernel (the default is generation 6)
     _lib.check(L.ezb_set_option(b"attn_res", 1))
     try:
         test_attention(1, B, H, Lq, Lk, dh, masked)
         test_attention(101, B, H, Lq, Lk, dh, masked)
     finally:
         _lib.check(L.ezb_set_option(b"attn_res", 0))
+        _lib.check(L.ezb_set_option(b"attn6", ATTN6_DEFAULT))
 
 
 @pytest.mark.gpu
@@ -106,6 +97,7 @@ def test_attention_mufu_token(B, H, Lq, Lk, dh, masked, res):
     items (the group without a last item keeps passing the token), a single item, one to twelve key blocks, with and without resident K / V^T."""
     from ezaudio_b200 import _lib
     L = _lib.lib()
+    _lib.check(L.ezb_set_option(b"attn6", 0))   # generation-4 kernel (the default is generation 6)
     _lib.check(L.ezb_set_option(b"attn_pp", 1))
     _lib.check(L.ezb_set_option(b"attn_res", res))
     try:
@@ -114,13 +106,14 @@ def test_attention_mufu_token(B, H, Lq, Lk, dh, masked, res):
     finally:
         _lib.check(L.ezb_set_option(b"attn_pp", 0))
         _lib.check(L.ezb_set_option(b"attn_res", 0))
+        _lib.check(L.ezb_set_option(b"attn6", ATTN6_DEFAULT))
 
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("B,H,Lq,Lk,dh,masked", [(2, 4, 500, 500, 72, False), (3, 2, 500, 100, 72, True), (2, 2, 40, 12, 72, True), (1, 16, 1500, 1500, 72, False),
                                                  (2, 3, 256, 256, 64, False), (8, 16, 500, 500, 72, False), (2, 5, 400, 512, 72, "grow"), (5, 3, 300, 100, 64, True),
                                                  (16, 16, 500, 500, 72, False), (2, 2, 130, 385, 72, True), (1, 1, 100, 300, 72, False), (1, 3, 128, 128, 72, True)])
-@pytest.mark.parametrize("mode", [1, 3, 5, 7])
+@pytest.mark.parametrize("mode", [0, 1, 3, 5, 7])
 def test_attention_gen6(B, H, Lq, Lk, dh, masked, mode):
     """attn6 (attention_tc6.cuh: chunked two-pass softmax, packed f32x2 arithmetic; bit 1 of the option = MUFU token between the two softmax
     groups, bit 2 = P handed to the MMA warp in two halves): every mode on odd / even item counts per CTA, a single item, one to twelve key
@@ -132,4 +125,4 @@ def test_attention_gen6(B, H, Lq, Lk, dh, masked, mode):
         test_attention(1, B, H, Lq, Lk, dh, masked)
         test_attention(101, B, H, Lq, Lk, dh, masked)
     finally:
-        _lib.check(L.ezb_set_option(b"attn6", 0))
+        _lib.check(L.ezb_set_option(b"attn6", ATTN6_DEFAULT))
