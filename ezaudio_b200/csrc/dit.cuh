@@ -896,6 +896,7 @@ struct Dit {
     if (d.is_controlnet) return fail(EZB_ERR_STATE, "ezb_dit_forward called on a controlnet handle");
     EZB_TRY(check_call(Be, L));
     dev->tmaps.trim();
+    WeightSeqScope ws(dev, this, cskips ? 1 : 0, ((long long)Be << 32) | (unsigned)L);   // L2 prefetch of the next GEMM's weights (host.cuh)
     const float *modr, *modf;
     int mbs, mbsf;
     EZB_TRY(select_mod(st, tidx, tall, Be, &modr, &modf, &mbs, &mbsf));
@@ -951,6 +952,7 @@ struct Dit {
     if (C % 4) return fail(EZB_ERR_UNSUPPORTED, "final conv: %d channels (multiple of 4 expected)", C);
     const size_t smem = (size_t)36 * C * sizeof(float);
     EZB_TRY(launch_k(final_conv_kernel, grid, dim3(128), smem, st, 1, (const float*)ybuf, (const float*)fc_w, (const float*)fc_b, out, Be, C, L));
+    ws.ok = true;
     return EZB_OK;
   }
 
@@ -968,6 +970,7 @@ inline int Dit::controlnet_forward(const float* x, const float* gt, const uint8_
   if (!d.is_controlnet) return fail(EZB_ERR_STATE, "ezb_controlnet_forward called on a DiT handle");
   EZB_TRY(check_call(Be, L));
   dev->tmaps.trim();
+  WeightSeqScope ws(dev, this, 2, ((long long)Be << 32) | (unsigned)L);
   const float *modr, *modf;
   int mbs, mbsf;
   EZB_TRY(select_mod(st, tidx, tall, Be, &modr, &modf, &mbs, &mbsf));
@@ -1011,6 +1014,7 @@ inline int Dit::controlnet_forward(const float* x, const float* gt, const uint8_
     e.bias = blk[i].zero_b; e.out_scale = cscale; e.out_f32 = skips_out[i]; e.ld32 = D;
     EZB_TRY(lin(st, A, D, blk[i].zero_w, M, D, e));
   }
+  ws.ok = true;
   return EZB_OK;
 }
 }  // namespace ezb

@@ -277,6 +277,7 @@ EZB_API int ezb_set_option(const char* name, int value) {
   if (name && !strcmp(name, "attn_res")) { opt_attn_res() = value; return EZB_OK; }
   if (name && !strcmp(name, "attn_pp")) { opt_attn_pp() = value; return EZB_OK; }
   if (name && !strcmp(name, "attn6")) { opt_attn6() = value; return EZB_OK; }
+  if (name && !strcmp(name, "w_prefetch")) { opt_w_prefetch() = value; return EZB_OK; }
   if (name && !strcmp(name, "attn_dbg")) { opt_attn_dbg() = value; return EZB_OK; }
   if (name && !strcmp(name, "ln_variant")) { opt_ln_variant() = value; return EZB_OK; }
   if (name && !strcmp(name, "mlp_fused")) { opt_mlp_fused() = value; return EZB_OK; }

@@ -36,7 +36,20 @@ struct GemmShape {
   int stride, pad;     // stride > 1: strided conv (VAE encoder): A is a 4-D map [B, T/stride, stride, C], tap k reads row q*stride + k - pad
   unsigned long long* dbg;  // optional cycle counters (CTA 0): [0] mma wait full, [1] mma wait tempty, [2] producer wait empty,
                             // [3] epilogue warp 2 wait tfull, [4] epilogue warp 2 busy, [5] total
+  // L2 prefetch of the weights the NEXT GEMM of the step will stream (host.cuh WeightSeq): every layer's weights are read once per step,
+  // i.e. from HBM, and a kernel's first k-blocks pay that latency on top of its ramp (GEGLU: 58 us with L2-resident weights, 68.6 us in situ).
+  const char* pf;
+  unsigned int pf_bytes;    // multiple of 16
 };
+
+// CTA c of `nctas` asks the L2 for its share (16 KB pieces, round-robin) of [pf, pf + bytes): a hint, no completion to wait for
+__device__ __forceinline__ void prefetch_weights_l2(const char* pf, unsigned int bytes, unsigned int cta, unsigned int nctas) {
+  constexpr unsigned int CH = 16384;
+  for (unsigned int off = cta * CH; off < bytes; off += nctas * CH) {
+    const unsigned int n = bytes - off < CH ? bytes - off : CH;
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(__cvta_generic_to_global(pf + off)), "r"(n) : "memory");
+  }
+}
 
 enum { ACT_NONE = 0, ACT_SILU = 1, ACT_SNAKE = 2 };
 
@@ -636,6 +649,10 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_launch();
+  if (warp == 0 && g.pf_bytes != 0) {   // constant data: no need to wait for the previous kernel
+    if (elect_one()) prefetch_weights_l2(g.pf, g.pf_bytes, blockIdx.x, gridDim.x);
+    __syncwarp();
+  }
   pdl_wait();  // everything above overlapped the previous kernel's tail; global memory is touched only below
 
   if (warp == 0) {
@@ -948,6 +965,10 @@ __device__ __forceinline__ void gemm2_body(const CUtensorMap& tmA, const CUtenso
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_launch();
+  if (warp == 0 && g.pf_bytes != 0) {   // constant data: no need to wait for the previous kernel
+    if (elect_one()) prefetch_weights_l2(g.pf, g.pf_bytes, blockIdx.x, gridDim.x);
+    __syncwarp();
+  }
   pdl_wait();
   EZB_DBG(const bool dbg = g.dbg != nullptr && blockIdx.x == 0; const long long t_start = clock64(); long long w0 = 0, w1 = 0;)
 
