@@ -950,8 +950,11 @@ struct Dit {
     EZB_TRY(lin(st, act, D, w_final, M, C, e));
     dim3 grid((L + 31) / 32, Be);
     if (C % 4) return fail(EZB_ERR_UNSUPPORTED, "final conv: %d channels (multiple of 4 expected)", C);
-    const size_t smem = (size_t)36 * C * sizeof(float);
-    EZB_TRY(launch_k(final_conv_kernel, grid, dim3(128), smem, st, 1, (const float*)ybuf, (const float*)fc_w, (const float*)fc_b, out, Be, C, L));
+    const size_t smem = ((size_t)36 * C + (size_t)(FC_GROUPS - 1) * 128 * 32) * sizeof(float);
+    static bool fc_attr[16] = {};   // function attributes are per device
+    if (!fc_attr[dev->id & 15]) { EZB_CUDA(cudaFuncSetAttribute(final_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); fc_attr[dev->id & 15] = true; }
+    if (smem > 160 * 1024) return fail(EZB_ERR_UNSUPPORTED, "final conv: %d channels exceed the shared-memory tile", C);
+    EZB_TRY(launch_k(final_conv_kernel, grid, dim3(128 * FC_GROUPS), smem, st, 1, (const float*)ybuf, (const float*)fc_w, (const float*)fc_b, out, Be, C, L));
     ws.ok = true;
     return EZB_OK;
   }

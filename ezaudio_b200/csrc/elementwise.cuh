@@ -395,29 +395,37 @@ __global__ void patch_pack_kernel(const float* __restrict__ x, const float* __re
 
 // ---------------------------------------------------------------------------------------------------------------
 // FinalBlock tail (blocks.py:207-211): y [B*L, C] token-major -> unpatchify (transpose) -> Conv1d(C, C, k=3, pad=1).
-// w packed [3][Cin][Cout].  CTA = 32 positions x all C = 128 output channels; thread = 4 output channels x 8 positions, so one
-// input channel costs 10 broadcast LDS + 3 coalesced float4 weight loads for 96 FMAs (the first version issued one dependent
-// global weight load per (tap, channel) and ran 211 us; FMA-bound this is ~10 us).
-__global__ void __launch_bounds__(128) final_conv_kernel(const float* __restrict__ y, const float* __restrict__ wp, const float* __restrict__ bias,
-                                                         float* __restrict__ out, int B, int C, int L) {
+// w packed [3][Cin][Cout].  CTA = 32 positions x all C = 128 output channels, 512 threads = 4 input-channel groups x 128; within a group
+// thread = 4 output channels x 8 positions, so one input channel costs 10 broadcast LDS + 3 coalesced float4 weight loads for 96 FMAs; the four
+// groups' partial sums meet in shared memory.  (Round 1: one dependent global weight load per (tap, channel), 211 us; round 2a: 128 threads
+// walking all 128 input channels, 62.5 us per step -- four warps per SM cannot hide the L2 latency of the weight loads; this one: 16 warps.)
+constexpr int FC_GROUPS = 4;
+__global__ void __launch_bounds__(128 * FC_GROUPS) final_conv_kernel(const float* __restrict__ y, const float* __restrict__ wp, const float* __restrict__ bias,
+                                                                     float* __restrict__ out, int B, int C, int L) {
   pdl_launch();
   pdl_wait();
   constexpr int TL = 32, TP = TL + 2 + 2;  // 34 positions (+2 so that the 10-wide window of the last thread group stays in bounds)
-  extern __shared__ float sy[];             // [C][TP] channel-major
+  extern __shared__ float sy[];             // [C][TP] channel-major, then [FC_GROUPS - 1][128][32] partial sums
+  float* red = sy + (size_t)C * TP;
   const int b = blockIdx.y, l0 = blockIdx.x * TL;
   for (int i = threadIdx.x; i < (TL + 2) * C; i += blockDim.x) {
     const int r = i / C, c = i - r * C, l = l0 + r - 1;
     sy[c * TP + r] = (l >= 0 && l < L) ? y[((size_t)b * L + l) * C + c] : 0.f;
   }
   __syncthreads();
-  const int tq = threadIdx.x >> 5;           // positions tq*8 .. tq*8+7 of the tile
-  for (int co = (threadIdx.x & 31) * 4; co < C; co += 128) {
+  const int gq = threadIdx.x >> 7, t128 = threadIdx.x & 127;
+  const int tq = t128 >> 5;                  // positions tq*8 .. tq*8+7 of the tile
+  const int cq = (C + FC_GROUPS - 1) / FC_GROUPS, ci0 = gq * cq, ci1 = ci0 + cq < C ? ci0 + cq : C;
+  for (int cb = 0; cb < C; cb += 128) {   // C = 128 shipped: one pass.  The trip count is uniform (barriers inside); lanes beyond C idle.
+    const int co = cb + (t128 & 31) * 4;
+    const bool live = co < C;
     float acc[8][4];
-    const float4 bv = *reinterpret_cast<const float4*>(bias + co);
+    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (gq == 0 && live) bv = *reinterpret_cast<const float4*>(bias + co);
 #pragma unroll
     for (int t = 0; t < 8; ++t) { acc[t][0] = bv.x; acc[t][1] = bv.y; acc[t][2] = bv.z; acc[t][3] = bv.w; }
 #pragma unroll 4
-    for (int ci = 0; ci < C; ++ci) {
+    for (int ci = ci0; ci < (live ? ci1 : ci0); ++ci) {
       float4 w[3];
 #pragma unroll
       for (int k = 0; k < 3; ++k) w[k] = __ldg(reinterpret_cast<const float4*>(wp + ((size_t)k * C + ci) * C + co));
@@ -434,13 +442,31 @@ __global__ void __launch_bounds__(128) final_conv_kernel(const float* __restrict
           acc[t][3] = fmaf(w[k].w, x[t + k], acc[t][3]);
         }
     }
+    if (gq > 0) {
+      float* rr = red + ((size_t)(gq - 1) * 128 + t128) * 32;
 #pragma unroll
-    for (int e = 0; e < 4; ++e)
+      for (int t = 0; t < 8; ++t) *reinterpret_cast<float4*>(rr + t * 4) = make_float4(acc[t][0], acc[t][1], acc[t][2], acc[t][3]);
+    }
+    __syncthreads();
+    if (gq == 0 && live) {
 #pragma unroll
-      for (int t = 0; t < 8; ++t) {
-        const int l = l0 + tq * 8 + t;
-        if (l < L) out[((size_t)b * C + co + e) * L + l] = acc[t][e];
+      for (int q = 0; q < FC_GROUPS - 1; ++q) {
+        const float* rr = red + ((size_t)q * 128 + t128) * 32;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          const float4 v = *reinterpret_cast<const float4*>(rr + t * 4);
+          acc[t][0] += v.x; acc[t][1] += v.y; acc[t][2] += v.z; acc[t][3] += v.w;
+        }
       }
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          const int l = l0 + tq * 8 + t;
+          if (l < L) out[((size_t)b * C + co + e) * L + l] = acc[t][e];
+        }
+    }
+    __syncthreads();
   }
 }
 
