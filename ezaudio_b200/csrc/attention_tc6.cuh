@@ -281,24 +281,28 @@ attn6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
       }
     };
 
+    uint8_t pm[4] = {1, 1, 1, 1};   // key-mask bytes of the NEXT block's columns q * 32 + lane (1 without a mask)
+    auto load_mask = [&](int itl_, int j_) {
+      if (p.key_mask == nullptr) return;
+      const int bb = (A6_ITEM(itl_, g) / p.n_qt) / p.H;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int kk = j_ * 128 + q * 32 + lane;
+        pm[q] = kk < p.Lk ? p.key_mask[(size_t)bb * p.Lk + kk] : (uint8_t)0;
+      }
+    };
+    if (Ug > 0) load_mask(0, 0);
     int itl = 0, j = 0;   // s = itl * n_kv + j
     for (int s = 0; s < Ug; ++s) {
       const int item = A6_ITEM(itl, g);
-      const int bh = item / p.n_qt, b = bh / p.H;
-      // key validity bits of this block (one per key column, identical for every row), fetched BEFORE the S wait: with a key mask they come from
-      // global memory (cross-attention: a dependent ~800-cycle load per item if issued after S has arrived)
+      // key validity bits of this block (one per key column, identical for every row).  With a key mask they come from global memory: the bytes
+      // were requested one block ahead (load_mask below; cross-attention: a dependent ~800-cycle load per item if issued after S has arrived)
       const int kbase = j * 128;
       const bool full = (p.key_mask == nullptr) && (kbase + 128 <= p.Lk);
       uint32_t kw[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
       if (!full) {
-        const uint8_t* km = p.key_mask ? p.key_mask + (size_t)b * p.Lk : nullptr;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int kk = kbase + q * 32 + lane;
-          bool ok = kk < p.Lk;
-          if (ok && km != nullptr) ok = km[kk] != 0;
-          kw[q] = __ballot_sync(0xffffffffu, ok);
-        }
+        for (int q = 0; q < 4; ++q) kw[q] = __ballot_sync(0xffffffffu, (kbase + q * 32 + lane < p.Lk) && pm[q] != 0);
       }
       mbar_wait(&s_full[g], s & 1);
       tc_fence_after();
@@ -418,6 +422,7 @@ attn6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[g]);
+      if (s + 1 < Ug) load_mask(j == n_kv - 1 ? itl + 1 : itl, j == n_kv - 1 ? 0 : j + 1);   // mask bytes of the next block: a whole block to arrive
       if (j == n_kv - 1) {   // the item ends here: retire it inside the bubble before the next item's first S (its last P V is the next thing on the pipe)
         mbar_wait(&o_full[g], s & 1);
         tc_fence_after();
