@@ -157,10 +157,14 @@ typedef struct {
 int ezb_test_gemm(int device, const void* A_bf16, int lda, const void* W_bf16, int ldw, int M, int N, int K, int bn, int epi_kind,
                   const ezb_test_epilogue* e, int conv_taps, int conv_center, int conv_dil, int conv_cin_pad, int conv_T,
                   int conv_B, void* stream);
+/* impl 0: fp32 CUDA-core kernel (q, k, v fp32 [B,H,L,dh]); 1: the tcgen05 kernel the product uses (generation 6 unless the option "attn6" says
+   otherwise); 4 / 6: generation 4 / 6 forced; +100: q / k rows of 80 elements for dh = 72 (the product's layout) instead of 128 */
 int ezb_test_attention(int device, const void* q, const void* k, const void* vt, const uint8_t* key_mask, void* out_bf16,
                        int B, int H, int Lq, int Lk, int dh, int impl, void* stream);
 
-/* runtime switch for A/B measurements: "pair_gemm" (1 = cta_group::2 256-row tiles, default; 0 = single-CTA 128x128) */
+/* runtime switches for A/B measurements and profiling (csrc/host.cuh, csrc/ezb.cu list them with their measured verdicts): e.g. "pair_gemm" (1 =
+   cta_group::2 256-row tiles, default), "attn6" (attention kernel generation / mode, default 5), "ksub2", "ln_variant", "skip" (profiling: kernel
+   classes not launched).  Defaults are the measured-best settings; products never need to call this. */
 int ezb_set_option(const char* name, int value);
 /* incremented by every ezb_set_option call: hosts that cache captured CUDA graphs key them on it (options change kernel selection) */
 unsigned long long ezb_option_epoch(void);
