@@ -9,6 +9,7 @@
 #include "attention_simt.cuh"
 #include "attention_tc4.cuh"
 #include "attention_tc6.cuh"
+#include "attention_tc7.cuh"
 #include "host.cuh"
 #include "gemm_ln.cuh"
 
@@ -649,6 +650,7 @@ struct Dit {
       EZB_CUDA(cudaGetLastError());
       return EZB_OK;
     }
+    if (opt_attn7()) return attention_tc7(*dev, st, q16_, k16_, vt16_, mask, attn_out, B, H, Lq, Lk, Lkpad, dh, DHP, DVP, scale);
     if (opt_attn6() & 1) return attention_tc6(*dev, st, q16_, k16_, vt16_, mask, attn_out, B, H, Lq, Lk, Lkpad, dh, DHP, DVP, scale);
     return attention_tc4(*dev, st, q16_, k16_, vt16_, mask, attn_out, B, H, Lq, Lk, Lkpad, dh, DHP, DVP, scale);
   }

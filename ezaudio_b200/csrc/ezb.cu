@@ -253,6 +253,9 @@ EZB_API int ezb_test_attention(int device, const void* q, const void* k, const v
   int dhp = (dh + 63) / 64 * 64;
   if (impl >= 100) { impl -= 100; if (dh == 72) dhp = 80; }
   const int dvp = (dh + 15) / 16 * 16, lkpad = (Lk + 7) / 8 * 8;
+  if (impl == 7 || (impl == 1 && opt_attn7()))
+    return attention_tc7(device_ctx(device), ST(stream), reinterpret_cast<const __nv_bfloat16*>(q), reinterpret_cast<const __nv_bfloat16*>(k),
+                         reinterpret_cast<const __nv_bfloat16*>(v), key_mask, reinterpret_cast<__nv_bfloat16*>(out), B, H, Lq, Lk, lkpad, dh, dhp, dvp, scale);
   if (impl == 6 || (impl == 1 && (opt_attn6() & 1)))
     return attention_tc6(device_ctx(device), ST(stream), reinterpret_cast<const __nv_bfloat16*>(q), reinterpret_cast<const __nv_bfloat16*>(k),
                          reinterpret_cast<const __nv_bfloat16*>(v), key_mask, reinterpret_cast<__nv_bfloat16*>(out), B, H, Lq, Lk, lkpad, dh, dhp, dvp, scale);
@@ -277,6 +280,7 @@ EZB_API int ezb_set_option(const char* name, int value) {
   if (name && !strcmp(name, "attn_res")) { opt_attn_res() = value; return EZB_OK; }
   if (name && !strcmp(name, "attn_pp")) { opt_attn_pp() = value; return EZB_OK; }
   if (name && !strcmp(name, "attn6")) { opt_attn6() = value; return EZB_OK; }
+  if (name && !strcmp(name, "attn7")) { opt_attn7() = value; return EZB_OK; }
   if (name && !strcmp(name, "w_prefetch")) { opt_w_prefetch() = value; return EZB_OK; }
   if (name && !strcmp(name, "attn_dbg")) { opt_attn_dbg() = value; return EZB_OK; }
   if (name && !strcmp(name, "ln_variant")) { opt_ln_variant() = value; return EZB_OK; }

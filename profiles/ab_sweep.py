@@ -14,7 +14,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from ezaudio_b200 import _lib, api  # noqa: E402
 from ezaudio_b200.inference import _ddim_step  # noqa: E402
 
-DEFAULTS = {"w_prefetch": 0, "attn6": 5, "attn_pp": 0, "attn_res": 0, "attn_poly": 0, "cq_single": 0, "heads_direct": 0, "ksub2": 1, "mlp2_pair": 0, "swap_mc": 0,
+DEFAULTS = {"attn7": 0, "w_prefetch": 0, "attn6": 5, "attn_pp": 0, "attn_res": 0, "attn_poly": 0, "cq_single": 0, "heads_direct": 0, "ksub2": 1, "mlp2_pair": 0, "swap_mc": 0,
             "mlp_fused": 0, "ln_variant": 2, "ln_tail": 0, "skip": 0}
 for a in sys.argv[1:]:
     if a.startswith("default:"):   # e.g. default:attn_res=1 changes the baseline every set is applied on top of

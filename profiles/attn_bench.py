@@ -46,7 +46,9 @@ L.ezb_set_option(b"attn_poly", (MMA2 >> 2) & 1)
 L.ezb_set_option(b"attn_pp", (MMA2 >> 3) & 1)
 A6 = int(sys.argv[2]) if len(sys.argv) > 2 else 0   # attention_tc6.cuh: 1 on, +2 MUFU token, +4 P in two halves
 L.ezb_set_option(b"attn6", A6)
-print("attn6 =", A6)
+A7 = int(sys.argv[3]) if len(sys.argv) > 3 else 0   # attention_tc7.cuh
+L.ezb_set_option(b"attn7", A7)
+print("attn6 =", A6, "attn7 =", A7)
 print("attn_res =", (MMA2 >> 1) & 1, "attn_poly =", (MMA2 >> 2) & 1, "attn_pp =", (MMA2 >> 3) & 1)
 for impl in (1, 101):
     run(8, 16, 500, 500, 72, False, "self XL", impl)

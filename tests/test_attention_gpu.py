@@ -126,3 +126,17 @@ def test_attention_gen6(B, H, Lq, Lk, dh, masked, mode):
         test_attention(101, B, H, Lq, Lk, dh, masked)
     finally:
         _lib.check(L.ezb_set_option(b"attn6", ATTN6_DEFAULT))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,H,Lq,Lk,dh,masked", [(2, 4, 500, 500, 72, False), (3, 2, 500, 100, 72, True), (2, 2, 40, 12, 72, True), (1, 16, 1500, 1500, 72, False),
+                                                 (2, 3, 256, 256, 64, False), (8, 16, 500, 500, 72, False), (2, 5, 400, 512, 72, "grow"), (5, 3, 300, 100, 64, True),
+                                                 (16, 16, 500, 500, 72, False), (2, 2, 130, 385, 72, True), (1, 1, 100, 300, 72, False), (1, 3, 128, 128, 72, True),
+                                                 (3, 5, 200, 65, 72, True), (1, 2, 640, 192, 64, False), (37, 4, 512, 512, 72, False)])
+def test_attention_gen7(B, H, Lq, Lk, dh, masked):
+    """attn7 (attention_tc7.cuh: 64-key score blocks, two S buffers per group, scores issued two blocks ahead, output stores issued by the Q producer
+    warp): odd / even item counts per CTA, a single item, an odd number of 64-key blocks per item (385, 65, 192 keys), a lone key in the last block,
+    up to 24 blocks, key masks, score growth (in-place O rescale), dh = 64 and 72, both q / k row pitches, Lk <= 64 (falls back to generation 6),
+    exactly four items on every CTA."""
+    test_attention(7, B, H, Lq, Lk, dh, masked)
+    test_attention(107, B, H, Lq, Lk, dh, masked)

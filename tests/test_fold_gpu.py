@@ -133,7 +133,7 @@ def test_loop_graphs_and_short_clips_with_fold():
 
 
 DEFAULTS = {"ln_fold": FOLD_DEFAULT, "attn6": 5, "attn_pp": 0, "dhp80": 1, "heads_direct": 0, "ln_tail": 0, "mlp_fused": 0, "ln_variant": 2, "ksub2": 1, "cq_single": 0, "mlp2_pair": 0,
-            "attn_res": 0, "w_prefetch": 0}
+            "attn_res": 0, "w_prefetch": 0, "attn7": 0}
 
 
 @contextlib.contextmanager
@@ -152,9 +152,9 @@ def options(**kw):
 @pytest.mark.parametrize("opts", [dict(heads_direct=1), dict(dhp80=0), dict(attn6=0), dict(attn6=7, dhp80=1, heads_direct=1, ln_fold=1), dict(ln_tail=1),
                                   dict(ln_variant=1), dict(mlp_fused=1), dict(mlp_fused=1, ln_tail=1, dhp80=1),
                                   dict(attn6=0, attn_pp=1), dict(ksub2=3), dict(ksub2=0), dict(ln_variant=0), dict(cq_single=1), dict(mlp2_pair=1), dict(attn6=0, attn_res=1),
-                                  dict(attn6=1), dict(attn6=3), dict(w_prefetch=1)],
+                                  dict(attn6=1), dict(attn6=3), dict(w_prefetch=1), dict(attn7=1)],
                          ids=["heads_direct", "dhp128", "attn_gen4", "all", "ln_tail", "ln_variant1", "mlp_fused", "mlp_fused+ln_tail+dhp80", "attn_gen4_token", "ksub2_qkv", "ksub2_off", "ln_variant0", "cq_single", "mlp2_pair", "attn_gen4_res",
-                              "attn6_plain", "attn6_token", "w_prefetch"])
+                              "attn6_plain", "attn6_token", "w_prefetch", "attn7"])
 @pytest.mark.parametrize("name", ["dit_tiny72", "dit_tiny64", "dit_XL", "dit_tiny72_inpaint", "dit_XL_inpaint_30s", "dit_L_c1"])
 def test_fast_path_options_keep_parity(name, opts):
     """Every fast-path variant behind a runtime switch (q/k epilogue without smem staging, 80-element q/k rows, attention generations 4 / 6 and their modes, folded LayerNorm)
