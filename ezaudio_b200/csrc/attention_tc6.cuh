@@ -437,7 +437,7 @@ attn6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
         if (lane == 0) mbar_arrive(&tok[0]);
       }
     }
-    if (r == 0) bulk_wait0();   // the last store has left shared memory (and completed) before the CTA goes away
+    if (r == 0) bulk_wait_read0();   // the last store has left shared memory before the CTA goes away (its global writes complete with the grid)
   }
 #undef A6_ITEM
   tc_fence_before();

@@ -34,7 +34,7 @@ attn7_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
              const __grid_constant__ CUtensorMap tmQt, const __grid_constant__ CUtensorMap tmKt, const __grid_constant__ CUtensorMap tmO, const Attn4Params p) {
   using SM = Attn7Smem<DH>;
   constexpr bool HAS_TAIL = DH > 64;
-  constexpr uint32_t GCOLS = 208;   // tensor-memory columns per group: S0 @ 0, S1 @ 64, O @ 128 (<= 80 columns)
+  constexpr uint32_t GCOLS = 256;   // tensor-memory columns per group: S0 @ 0, S1 @ 64, O @ 128 (<= 80 columns); 32-column aligned bases (208 per group failed on hardware)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int VB = SM::v_bytes(p.dvp);
@@ -44,8 +44,12 @@ attn7_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
   uint64_t* bars = reinterpret_cast<uint64_t*>(sV + A7_VSTAGES * VB);
   uint64_t *q_full = bars, *o_staged = bars + 4;   // [g * 2 + buffer]: Q tile has landed / the item's output tile is staged in the buffer
   uint64_t *s_full = bars + 8, *p_full = bars + 12; // [g * 2 + (u & 1)]
-  uint64_t* o_full = bars + 16;                    // [g]: P V(u) has completed
-  uint64_t *k_full = bars + 18, *k_empty = k_full + A7_KSTAGES, *v_full = k_empty + A7_KSTAGES, *v_empty = v_full + A7_VSTAGES;
+  // [g * 2 + (u & 1)]: P V(u) has completed.  Two barriers per group: scores are issued two blocks ahead, so when a softmax warp has S(u) only
+  // P V(u - 2) is known to be complete -- a single barrier per group would be one or two phases behind the phase waited for, and a parity wait two
+  // phases ahead returns at once (first hardware run: the item-end read of O raced with the last two P V of the item whenever the MMA warp was busy
+  // with the other group).
+  uint64_t* o_full = bars + 16;
+  uint64_t *k_full = bars + 20, *k_empty = k_full + A7_KSTAGES, *v_full = k_empty + A7_KSTAGES, *v_empty = v_full + A7_VSTAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(v_empty + A7_VSTAGES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -62,7 +66,7 @@ attn7_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
       tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmO);
       if (HAS_TAIL) { tma_prefetch_desc(&tmQt); tma_prefetch_desc(&tmKt); }
       for (int i = 0; i < 4; ++i) { mbar_init(&q_full[i], 1); mbar_init(&o_staged[i], 4); mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4); }
-      for (int i = 0; i < 2; ++i) mbar_init(&o_full[i], 1);
+      for (int i = 0; i < 4; ++i) mbar_init(&o_full[i], 1);
       for (int i = 0; i < A7_KSTAGES; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
       for (int i = 0; i < A7_VSTAGES; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
       fence_mbar_init();
@@ -192,7 +196,7 @@ attn7_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma_bf16_ts(od, pa + k * 8, vd + 2 * k, idesc_o, (b != 0) || (k != 0));
         if ((b & 1) == 1 || b == nb - 1) umma_commit(&v_empty[st]);
-        umma_commit(&o_full[g]);
+        umma_commit(&o_full[g * 2 + (u & 1)]);
       }
       __syncwarp();
       ++pu[g];
@@ -300,7 +304,7 @@ attn7_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
         }
       }
       if (b != 0 && __any_sync(0xffffffffu, need)) {   // in-place rescale of O before this block's P V (warp-collective TMEM access)
-        mbar_wait(&o_full[g], (u - 1) & 1);  // P V(u - 1) has landed
+        mbar_wait(&o_full[g * 2 + ((u - 1) & 1)], ((u - 1) >> 1) & 1);  // P V(u - 1) has landed
         tc_fence_after();
         uint32_t orr[64];
         tmem_ld_32x64(tO, orr);
@@ -352,7 +356,7 @@ attn7_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
       if (lane == 0) mbar_arrive(&p_full[g * 2 + (u & 1)]);
       if (u + 1 < Bg) load_mask(b == nb - 1 ? itl + 1 : itl, b == nb - 1 ? 0 : b + 1);   // mask bytes of the next block: a whole block to arrive
       if (b == nb - 1) {   // the item ends here: retire it (its last P V is the next thing on the pipe; the next item's scores are already there)
-        mbar_wait(&o_full[g], u & 1);
+        mbar_wait(&o_full[g * 2 + (u & 1)], (u >> 1) & 1);
         tc_fence_after();
         stage_item(g * 2 + (itl & 1), l_run);
       }
@@ -365,7 +369,9 @@ attn7_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
   if (warp == 8) tmem_dealloc<512>(tmem0);
 }
 
-inline int& opt_attn7() {   // attention kernel generation 7 (this file): 64-key blocks, two S buffers per group
+inline int& opt_attn7() {   // attention kernel generation 7 (this file): 64-key blocks, two S buffers per group.  Measured (call 25, parity-green): self 22.2 vs
+                            // 21.3 us, 30-s shape 82.4 vs 73.0 us, cross 9.6 vs 9.6 us, step 7.38 vs 7.31-7.56 ms: twice as many hand-offs and tcgen05.ld / st
+                            // round trips per key cost more than the early S buys -- off.
   static int v = [] { const char* e = getenv("EZB_ATTN7"); return e ? atoi(e) : 0; }();
   return v;
 }
