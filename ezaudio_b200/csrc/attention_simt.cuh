@@ -11,15 +11,21 @@ constexpr int SA_TK = 64;   // keys per smem tile
 constexpr int SA_QW = 8;    // queries per warp
 constexpr int SA_WARPS = 4;
 
+// Shared-memory traffic is what bounds this kernel (one T5 layer: 160 heads x 100 x 100 x 64): round 2a read K values once per d and reused them for the
+// warp's 8 queries but still issued 10 scalar LDS per 16 FMAs in the score loop and one SHFL per (key, query) in P V (512 per tile per warp).  Now
+// (dh % 4 == 0): K rows at a 16-byte-aligned pitch whose quarter-warp LDS.128 phases are conflict-free, q / k / p read as float4 (10 LDS.128 per 64
+// FMAs), and the probabilities go through a per-warp shared tile and come back as broadcast LDS.128 (no shuffles).  Every accumulator still sums in the
+// same order (d ascending, keys ascending), so the output bits are unchanged.
 __global__ void __launch_bounds__(SA_WARPS * 32) attn_simt_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
                                                                   const uint8_t* __restrict__ key_mask, __nv_bfloat16* __restrict__ out, int H, int Lq,
                                                                   int Lk, int dh, float scale, int kmul,
                                                                   const float* __restrict__ bias = nullptr /* [H, Lq, Lk] added to the scores (T5) */) {
-  extern __shared__ float sm[];
-  const int ldk = dh | 1;  // odd pitch: conflict-free row-per-lane reads
+  extern __shared__ __align__(16) float sm[];
+  const int ldk = ((dh >> 2) & 1) ? dh : dh + 4;   // pitch / 4 odd: the 8 lanes of an LDS.128 phase hit 8 different 16-byte bank groups
   float* sK = sm;                       // [SA_TK][ldk]
   float* sV = sK + SA_TK * ldk;         // [SA_TK][dh]
   float* sQ = sV + SA_TK * dh;          // [SA_WARPS*SA_QW][dh]
+  float* sP = sQ + SA_WARPS * SA_QW * dh;   // [SA_WARPS][SA_QW][SA_TK]
   const int bh = blockIdx.y, b = bh / H, h = bh - b * H;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * (SA_WARPS * SA_QW);
@@ -33,6 +39,7 @@ __global__ void __launch_bounds__(SA_WARPS * 32) attn_simt_kernel(const float* _
   float m[SA_QW], l[SA_QW], acc[SA_QW][3];
 #pragma unroll
   for (int i = 0; i < SA_QW; ++i) { m[i] = -INFINITY; l[i] = 0.f; acc[i][0] = acc[i][1] = acc[i][2] = 0.f; }
+  float* sPw = sP + warp * (SA_QW * SA_TK);
   for (int k0 = 0; k0 < Lk; k0 += SA_TK) {
     __syncthreads();
     for (int i = threadIdx.x; i < SA_TK * dh; i += blockDim.x) {
@@ -47,25 +54,23 @@ __global__ void __launch_bounds__(SA_WARPS * 32) attn_simt_kernel(const float* _
       ok0 = ok0 && key_mask[(size_t)b * Lk + k0 + lane];
       ok1 = ok1 && key_mask[(size_t)b * Lk + k0 + lane + 32];
     }
-    // scores of this warp's SA_QW queries against the lane's two keys: the K values are read once per d and reused by all queries
-    // (the first version re-read them per query: 3 shared loads per 2 FMAs, LDS-bound at 199 us per T5 layer)
+    // scores of this warp's SA_QW queries against the lane's two keys
     float s0[SA_QW], s1[SA_QW];
 #pragma unroll
     for (int qi = 0; qi < SA_QW; ++qi) { s0[qi] = 0.f; s1[qi] = 0.f; }
     const float* qw = sQ + (warp * SA_QW) * dh;
     const float* kr0 = sK + lane * ldk;
     const float* kr1 = sK + (lane + 32) * ldk;
-#pragma unroll 4
-    for (int d = 0; d < dh; ++d) {
-      const float k0v = kr0[d], k1v = kr1[d];
+#pragma unroll 2
+    for (int d = 0; d < dh; d += 4) {
+      const float4 ka = *reinterpret_cast<const float4*>(kr0 + d), kc = *reinterpret_cast<const float4*>(kr1 + d);
 #pragma unroll
       for (int qi = 0; qi < SA_QW; ++qi) {
-        const float qv = qw[qi * dh + d];
-        s0[qi] = fmaf(qv, k0v, s0[qi]);
-        s1[qi] = fmaf(qv, k1v, s1[qi]);
+        const float4 qv = *reinterpret_cast<const float4*>(qw + qi * dh + d);
+        s0[qi] = fmaf(qv.w, ka.w, fmaf(qv.z, ka.z, fmaf(qv.y, ka.y, fmaf(qv.x, ka.x, s0[qi]))));
+        s1[qi] = fmaf(qv.w, kc.w, fmaf(qv.z, kc.z, fmaf(qv.y, kc.y, fmaf(qv.x, kc.x, s1[qi]))));
       }
     }
-    float p0[SA_QW], p1[SA_QW];
 #pragma unroll
     for (int qi = 0; qi < SA_QW; ++qi) {
       float a0 = s0[qi], a1 = s1[qi];
@@ -81,26 +86,38 @@ __global__ void __launch_bounds__(SA_WARPS * 32) attn_simt_kernel(const float* _
       a1 = ok1 ? a1 : -INFINITY;
       const float mn = fmaxf(m[qi], warp_max(fmaxf(a0, a1)));
       const float corr = (mn == -INFINITY) ? 1.f : expf(m[qi] - mn);
-      p0[qi] = (mn == -INFINITY) ? 0.f : expf(a0 - mn);
-      p1[qi] = (mn == -INFINITY) ? 0.f : expf(a1 - mn);
-      l[qi] = l[qi] * corr + warp_sum(p0[qi] + p1[qi]);
+      const float p0 = (mn == -INFINITY) ? 0.f : expf(a0 - mn);
+      const float p1 = (mn == -INFINITY) ? 0.f : expf(a1 - mn);
+      l[qi] = l[qi] * corr + warp_sum(p0 + p1);
       m[qi] = mn;
       acc[qi][0] *= corr; acc[qi][1] *= corr; acc[qi][2] *= corr;
+      sPw[qi * SA_TK + lane] = p0;
+      sPw[qi * SA_TK + lane + 32] = p1;
     }
-    // P V: a V row is read once and reused by all queries
+    __syncwarp();
+    // P V: a V row is read once and reused by all queries; four keys' probabilities per broadcast LDS.128
     const bool d1 = lane + 32 < dh, d2 = lane + 64 < dh;
 #pragma unroll 2
-    for (int j = 0; j < SA_TK; ++j) {
-      const float* vr = sV + j * dh;
-      const float v0 = vr[lane], v1 = d1 ? vr[lane + 32] : 0.f, v2 = d2 ? vr[lane + 64] : 0.f;
+    for (int j = 0; j < SA_TK; j += 4) {
+      float v0[4], v1[4], v2[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float* vr = sV + (j + t) * dh;
+        v0[t] = vr[lane]; v1[t] = d1 ? vr[lane + 32] : 0.f; v2[t] = d2 ? vr[lane + 64] : 0.f;
+      }
 #pragma unroll
       for (int qi = 0; qi < SA_QW; ++qi) {
-        const float pj = __shfl_sync(0xffffffffu, j < 32 ? p0[qi] : p1[qi], j & 31);
-        acc[qi][0] = fmaf(pj, v0, acc[qi][0]);
-        acc[qi][1] = fmaf(pj, v1, acc[qi][1]);
-        acc[qi][2] = fmaf(pj, v2, acc[qi][2]);
+        const float4 pj = *reinterpret_cast<const float4*>(sPw + qi * SA_TK + j);
+        const float pp[4] = {pj.x, pj.y, pj.z, pj.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          acc[qi][0] = fmaf(pp[t], v0[t], acc[qi][0]);
+          acc[qi][1] = fmaf(pp[t], v1[t], acc[qi][1]);
+          acc[qi][2] = fmaf(pp[t], v2[t], acc[qi][2]);
+        }
       }
     }
+    __syncwarp();   // the probabilities of this tile are consumed before the next tile overwrites them
   }
   const int D = H * dh;
 #pragma unroll
@@ -115,6 +132,7 @@ __global__ void __launch_bounds__(SA_WARPS * 32) attn_simt_kernel(const float* _
   }
 }
 
-inline size_t attn_simt_smem(int dh) { return sizeof(float) * (SA_TK * (dh | 1) + SA_TK * dh + SA_WARPS * SA_QW * dh); }
+// dh must be a multiple of 4 (float4 rows)
+inline size_t attn_simt_smem(int dh) { return sizeof(float) * (SA_TK * (dh + 4) + SA_TK * dh + SA_WARPS * SA_QW * dh + SA_WARPS * SA_QW * SA_TK); }
 
 }  // namespace ezb

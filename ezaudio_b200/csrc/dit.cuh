@@ -641,6 +641,7 @@ struct Dit {
     const float scale = 1.0f / sqrtf((float)dh);
     if (opt_skip() & 2) return EZB_OK;
     if (!use_tc_attention) {
+      if (dh % 4) return fail(EZB_ERR_UNSUPPORTED, "fp32 attention: head dimension %d is not a multiple of 4", dh);
       const size_t smem = attn_simt_smem(dh);
       static bool set[16] = {};  // function attributes are per device
       if (!set[dev->id & 15]) { EZB_CUDA(cudaFuncSetAttribute(attn_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); set[dev->id & 15] = true; }

@@ -240,6 +240,7 @@ EZB_API int ezb_test_attention(int device, const void* q, const void* k, const v
   EZB_CUDA(cudaSetDevice(device));
   const float scale = 1.0f / sqrtf((float)dh);
   if (impl == 0) {
+    if (dh % 4) return fail(EZB_ERR_UNSUPPORTED, "fp32 attention: head dimension %d is not a multiple of 4", dh);
     EZB_CUDA(cudaFuncSetAttribute(attn_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     dim3 grid((Lq + SA_WARPS * SA_QW - 1) / (SA_WARPS * SA_QW), B * H);
     ++launch_counter();

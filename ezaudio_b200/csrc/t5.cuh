@@ -149,7 +149,7 @@ struct T5 {
     D = d.d_model; H = d.num_heads; dk = d.d_kv; inner = H * dk; F = d.d_ff; nl = d.num_layers;
     kmul = d.precision == 1 ? 3 : 1;
     if (d.precision != 0 && d.precision != 1) return fail(EZB_ERR_UNSUPPORTED, "t5: precision %d", d.precision);
-    if (D <= 0 || D % 8 || inner % 8 || F % 8 || dk <= 0 || dk > 96 || nl <= 0 || d.vocab_size <= 0 || d.num_buckets <= 1 || d.max_batch <= 0 || d.max_len <= 0)
+    if (D <= 0 || D % 8 || inner % 8 || F % 8 || dk <= 0 || dk > 96 || dk % 4 || nl <= 0 || d.vocab_size <= 0 || d.num_buckets <= 1 || d.max_batch <= 0 || d.max_len <= 0)
       return fail(EZB_ERR_UNSUPPORTED, "t5: d_model %d d_kv %d heads %d d_ff %d layers %d", D, dk, H, F, nl);
     EZB_TRY(reg_f32("shared.weight", {d.vocab_size, D}, &emb));
     EZB_TRY(reg_f32("encoder.block.0.layer.0.SelfAttention.relative_attention_bias.weight", {d.num_buckets, H}, &rel));
