@@ -354,7 +354,7 @@ def main():
         _lib.check(Lb.ezb_prof_gemm_stats(0.99 * gf, C.byref(n2), C.byref(f2), C.byref(t2)))
         ach = f2.value / (t2.value * 1e-3) / 1e12 if n2.value else 0.0
         traffic, tsrc = ncu_traffic()
-        roof = dict(bound="tensor", kernel="gemm2_tcgen05_kernel<256, EpiGeglu<256>, 1> (GEGLU MLP-in GEMM: M=%d N=9216 K=1152)" % (B * n_e * L),
+        roof = dict(bound="tensor", kernel="gemm2_tcgen05_kernel<256, EpiGeglu<256>, KSUB 2> (GEGLU MLP-in GEMM, CTA pairs, 128-deep stages: M=%d N=9216 K=1152)" % (B * n_e * L),
                     achieved=ach, peak=pk["sustained"], unit="TFLOP/s", frac=ach / pk["sustained"],
                     peak_source=pk["src"] + ", sustained figure (kernel timed inside a long step)",
                     traffic=traffic, traffic_source=f"dram__bytes_read.sum + dram__bytes_write.sum of one launch, parsed from {tsrc} (ncu --set full); "
